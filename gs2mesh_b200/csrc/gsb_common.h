@@ -1,0 +1,68 @@
+// Shared host/device helpers for the gs2mesh_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "gs2mesh_b200.h"
+
+namespace gsb {
+
+constexpr int kTile = 16;          // DGR/cuda_rasterizer/config.h:16-17 (BLOCK_X, BLOCK_Y)
+constexpr int kTilePixels = 256;
+
+extern thread_local char g_error[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define GSB_CUDA_OK(expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return ::gsb::fail(GSB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),    \
+                         __FILE__, __LINE__);                                                      \
+  } while (0)
+
+// Cheap launch check (cudaPeekAtLastError); with `sync` also waits for the stream, like the
+// reference's debug mode (auxiliary.h:166-173).
+inline int check_launch(const char* what, cudaStream_t s, bool sync) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e == cudaSuccess && sync) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(GSB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  }
+  return GSB_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Carves consecutive 256-byte aligned regions out of one caller-owned block.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+  size_t total() const { return align_up(off, 256); }
+};
+
+}  // namespace gsb

@@ -1,0 +1,781 @@
+// Forward Gaussian-splat rasterizer for sm_100a.
+//
+// Behavioural contract = the reference's forward pass
+//   DGR/cuda_rasterizer/rasterizer_impl.cu:198-336 (Rasterizer::forward)
+//   DGR/cuda_rasterizer/forward.cu:155-256 (preprocess), :261-374 (render)
+// (DGR = third_party/gaussian-splatting/submodules/diff-gaussian-rasterization), but the
+// pipeline is organised differently:
+//
+//   preprocess   one WARP per 32 consecutive Gaussians.  The warp's parameter block is
+//                contiguous in every reference tensor ([P,3] xyz / scales, [P,4] quaternions,
+//                [P] opacities, [P,M,3] SH = 6 KB per warp) and is staged into shared memory
+//                with 1-D bulk TMA copies (cp.async.bulk + mbarrier).  The 6 KB SH block is
+//                only fetched when at least one Gaussian of the warp survives culling.
+//                Results are written as three coalesced record planes:
+//                  recA = (px, py, z_view, opacity)  recB = (conic a, b, c, red)  recC = (green, blue)
+//   binning      exact (Gaussian,tile) test: a pair is kept only if the tile's pixel lattice can
+//                reach alpha >= 1/255 -- the image is bit-identical to rectangle binning
+//                (rasterizer_impl.cu:88-107) with far fewer instances to sort and blend.
+//   sort         stable LSD radix sort on (tile << 32 | depth bits), value = Gaussian index.
+//   render       per 16x16 tile; the batch staged in shared memory carries colour and depth
+//                too, so the blend loop touches no global memory; also accumulates the
+//                expected-depth channel (sum z*alpha*T) the TSDF stage consumes.
+//
+// All kernels run on the caller's stream.
+#include <cub/cub.cuh>
+
+#include "gsb_common.h"
+
+namespace gsb {
+
+thread_local char g_error[512] = {0};
+std::atomic<uint64_t> g_launches{0};
+static thread_local int64_t g_required_instances = 0;
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kPreThreads = kWarpsPerBlock * 32;
+constexpr int kMaxShFloats = 48;  // 16 coefficients x RGB
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D bulk TMA (global -> shared)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-Gaussian maths.  Expressions are kept in the reference's algebraic form so nvcc contracts
+// them the same way it contracts the reference's device code.
+// ---------------------------------------------------------------------------------------------
+struct Mat3 {  // column-major, m[col][row] (glm convention)
+  float m[3][3];
+};
+__device__ __forceinline__ Mat3 mat_mul(const Mat3& a, const Mat3& b) {
+  Mat3 r;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r.m[j][i] = a.m[0][i] * b.m[j][0] + a.m[1][i] * b.m[j][1] + a.m[2][i] * b.m[j][2];
+  return r;
+}
+__device__ __forceinline__ Mat3 mat_t(const Mat3& a) {
+  Mat3 r;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r.m[j][i] = a.m[i][j];
+  return r;
+}
+
+struct TileRect {
+  uint32_t x0, y0, x1, y1;
+};
+// auxiliary.h:46-56
+__device__ __forceinline__ TileRect tile_rect(float px, float py, int radius, uint32_t gx, uint32_t gy) {
+  TileRect r;
+  r.x0 = min(gx, (uint32_t)max(0, (int)((px - radius) / kTile)));
+  r.y0 = min(gy, (uint32_t)max(0, (int)((py - radius) / kTile)));
+  r.x1 = min(gx, (uint32_t)max(0, (int)((px + radius + kTile - 1) / kTile)));
+  r.y1 = min(gy, (uint32_t)max(0, (int)((py + radius + kTile - 1) / kTile)));
+  return r;
+}
+
+// Exact tile test.  A pixel of tile (tx,ty) can only be blended if
+//   power = -0.5*(a dx^2 + c dy^2) - b dx dy <= 0  and  opacity*exp(power) >= 1/255
+// (forward.cu:336-346), i.e. q(d) = a dx^2 + 2b dx dy + c dy^2 <= 2 ln(255*opacity).  q is convex,
+// so its minimum over the tile's pixel box is 0 if the centre lies inside and otherwise sits on
+// one of the four box edges.  A safety margin covers fp32 rounding of both evaluations; pairs
+// inside the margin are kept, so no contributing pair is ever dropped.
+// __noinline__: the counting and the emitting kernel must execute the same instructions.
+__device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, float b, float c, float two_tau,
+                                                 uint32_t tx, uint32_t ty) {
+  if (!(a > 0.f && c > 0.f && a * c - b * b > 0.f)) return true;  // degenerate conic: stay conservative
+  const float x0 = (float)(tx * kTile), y0 = (float)(ty * kTile);
+  const float dx_lo = gxp - (x0 + (kTile - 1)), dx_hi = gxp - x0;
+  const float dy_lo = gyp - (y0 + (kTile - 1)), dy_hi = gyp - y0;
+  if (dx_lo <= 0.f && dx_hi >= 0.f && dy_lo <= 0.f && dy_hi >= 0.f) return true;
+  const float DX = fmaxf(fabsf(dx_lo), fabsf(dx_hi)), DY = fmaxf(fabsf(dy_lo), fabsf(dy_hi));
+  const float margin = 1e-3f + 8e-6f * (a * DX * DX + c * DY * DY + 2.f * fabsf(b) * DX * DY);
+  float qmin = 3.0e38f;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const float dx = e ? dx_hi : dx_lo;
+    const float dy = fminf(dy_hi, fmaxf(dy_lo, -b * dx / c));
+    qmin = fminf(qmin, a * dx * dx + 2.f * b * dx * dy + c * dy * dy);
+    const float ey = e ? dy_hi : dy_lo;
+    const float ex = fminf(dx_hi, fmaxf(dx_lo, -b * ey / a));
+    qmin = fminf(qmin, a * ex * ex + 2.f * b * ex * ey + c * ey * ey);
+  }
+  return qmin <= two_tau + margin;
+}
+
+struct PreParams {
+  int P, D, M, W, H;
+  const float* means3D;
+  const float* shs;
+  const float* colors;
+  const float* opacities;
+  const float* scales;
+  const float* rotations;
+  const float* cov3D;
+  float scale_modifier;
+  const float* view;
+  const float* proj;
+  const float* campos;
+  float tan_fovx, tan_fovy, focal_x, focal_y;
+  uint32_t gx, gy;
+  uint32_t flags;
+  int use_tma;
+  float4* recA;
+  float4* recB;
+  float2* recC;
+  uint32_t* tiles;
+  int* radii;
+  unsigned long long* ref_count;  // sum of reference tile rectangles
+};
+
+struct WarpStage {  // one warp's staged parameter block; every member offset is a multiple of 128 B
+  float sh[32 * kMaxShFloats];  // 6144 B
+  float rot[32 * 4];            // 512 B
+  float xyz[32 * 3];            // 384 B
+  float scale[32 * 3];          // 384 B
+  float opac[32];               // 128 B
+  uint64_t bar;
+  uint64_t pad[15];
+};
+
+__global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams p) {
+  __shared__ __align__(128) WarpStage stage[kWarpsPerBlock];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpStage& st = stage[warp];
+  const int base = (blockIdx.x * kWarpsPerBlock + warp) * 32;
+  if (base >= p.P) return;
+  const int idx = base + lane;
+  const int count = min(32, p.P - base);
+  const bool has_sr = p.cov3D == nullptr;
+  const bool full_tma = p.use_tma && count == 32;
+
+  // ---- stage 1: positions, scales, rotations, opacities -------------------------------------
+  if (full_tma) {
+    if (lane == 0) {
+      mbar_init(&st.bar, 1);
+      uint32_t bytes = 384 + 128 + (has_sr ? 384 + 512 : 0);
+      mbar_expect_tx(&st.bar, bytes);
+      tma_load_1d(st.xyz, p.means3D + (size_t)base * 3, 384, &st.bar);
+      tma_load_1d(st.opac, p.opacities + base, 128, &st.bar);
+      if (has_sr) {
+        tma_load_1d(st.scale, p.scales + (size_t)base * 3, 384, &st.bar);
+        tma_load_1d(st.rot, p.rotations + (size_t)base * 4, 512, &st.bar);
+      }
+    }
+    __syncwarp();
+    mbar_wait(&st.bar, 0);
+  } else {
+    for (int k = lane; k < count * 3; k += 32) {
+      st.xyz[k] = p.means3D[(size_t)base * 3 + k];
+      if (has_sr) st.scale[k] = p.scales[(size_t)base * 3 + k];
+    }
+    if (lane < count) st.opac[lane] = p.opacities[base + lane];
+    if (has_sr)
+      for (int k = lane; k < count * 4; k += 32) st.rot[k] = p.rotations[(size_t)base * 4 + k];
+    __syncwarp();
+  }
+
+  const bool valid = lane < count;
+  bool visible = false;
+  float px = 0.f, py = 0.f, zv = 0.f, opacity = 0.f, ca = 0.f, cb = 0.f, cc = 0.f;
+  float3 pos = make_float3(0.f, 0.f, 0.f);
+  int radius = 0;
+  uint32_t ntiles = 0, nref = 0;
+
+  if (valid) {
+    pos = make_float3(st.xyz[lane * 3], st.xyz[lane * 3 + 1], st.xyz[lane * 3 + 2]);
+    const float* vm = p.view;
+    const float* pm = p.proj;
+    // auxiliary.h:139-164 (in_frustum): view-space point, near cull at 0.2
+    float3 t = make_float3(vm[0] * pos.x + vm[4] * pos.y + vm[8] * pos.z + vm[12],
+                           vm[1] * pos.x + vm[5] * pos.y + vm[9] * pos.z + vm[13],
+                           vm[2] * pos.x + vm[6] * pos.y + vm[10] * pos.z + vm[14]);
+    if (t.z > 0.2f) {
+      zv = t.z;
+      const float hx = pm[0] * pos.x + pm[4] * pos.y + pm[8] * pos.z + pm[12];
+      const float hy = pm[1] * pos.x + pm[5] * pos.y + pm[9] * pos.z + pm[13];
+      const float hw = pm[3] * pos.x + pm[7] * pos.y + pm[11] * pos.z + pm[15];
+      const float p_w = 1.0f / (hw + 0.0000001f);
+      const float projx = hx * p_w, projy = hy * p_w;
+
+      // forward.cu:118-152: Sigma = (S R)^T (S R); quaternion is w-first and NOT renormalised
+      float c3[6];
+      if (has_sr) {
+        const float4 q = reinterpret_cast<const float4*>(st.rot)[lane];
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        Mat3 S;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) S.m[j][i] = 0.f;
+        S.m[0][0] = p.scale_modifier * st.scale[lane * 3];
+        S.m[1][1] = p.scale_modifier * st.scale[lane * 3 + 1];
+        S.m[2][2] = p.scale_modifier * st.scale[lane * 3 + 2];
+        Mat3 R;
+        R.m[0][0] = 1.f - 2.f * (y * y + z * z);
+        R.m[0][1] = 2.f * (x * y - r * z);
+        R.m[0][2] = 2.f * (x * z + r * y);
+        R.m[1][0] = 2.f * (x * y + r * z);
+        R.m[1][1] = 1.f - 2.f * (x * x + z * z);
+        R.m[1][2] = 2.f * (y * z - r * x);
+        R.m[2][0] = 2.f * (x * z - r * y);
+        R.m[2][1] = 2.f * (y * z + r * x);
+        R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+        const Mat3 Mx = mat_mul(S, R);
+        const Mat3 Sg = mat_mul(mat_t(Mx), Mx);
+        c3[0] = Sg.m[0][0];
+        c3[1] = Sg.m[0][1];
+        c3[2] = Sg.m[0][2];
+        c3[3] = Sg.m[1][1];
+        c3[4] = Sg.m[1][2];
+        c3[5] = Sg.m[2][2];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c3[k] = p.cov3D[(size_t)idx * 6 + k];
+      }
+
+      // forward.cu:74-113: EWA projection with the 1.3*tan(fov) guard band and +0.3 low-pass
+      const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
+      const float txtz = t.x / t.z, tytz = t.y / t.z;
+      t.x = min(limx, max(-limx, txtz)) * t.z;
+      t.y = min(limy, max(-limy, tytz)) * t.z;
+      Mat3 J;
+      J.m[0][0] = p.focal_x / t.z;
+      J.m[0][1] = 0.f;
+      J.m[0][2] = -(p.focal_x * t.x) / (t.z * t.z);
+      J.m[1][0] = 0.f;
+      J.m[1][1] = p.focal_y / t.z;
+      J.m[1][2] = -(p.focal_y * t.y) / (t.z * t.z);
+      J.m[2][0] = 0.f;
+      J.m[2][1] = 0.f;
+      J.m[2][2] = 0.f;
+      Mat3 Wm;
+      Wm.m[0][0] = vm[0];
+      Wm.m[0][1] = vm[4];
+      Wm.m[0][2] = vm[8];
+      Wm.m[1][0] = vm[1];
+      Wm.m[1][1] = vm[5];
+      Wm.m[1][2] = vm[9];
+      Wm.m[2][0] = vm[2];
+      Wm.m[2][1] = vm[6];
+      Wm.m[2][2] = vm[10];
+      const Mat3 T = mat_mul(Wm, J);
+      Mat3 V;
+      V.m[0][0] = c3[0];
+      V.m[0][1] = c3[1];
+      V.m[0][2] = c3[2];
+      V.m[1][0] = c3[1];
+      V.m[1][1] = c3[3];
+      V.m[1][2] = c3[4];
+      V.m[2][0] = c3[2];
+      V.m[2][1] = c3[4];
+      V.m[2][2] = c3[5];
+      const Mat3 cov = mat_mul(mat_mul(mat_t(T), mat_t(V)), T);
+      const float cxx = cov.m[0][0] + 0.3f, cxy = cov.m[0][1], cyy = cov.m[1][1] + 0.3f;
+
+      const float det = (cxx * cyy - cxy * cxy);
+      if (det != 0.0f) {
+        const float det_inv = 1.f / det;
+        ca = cyy * det_inv;
+        cb = -cxy * det_inv;
+        cc = cxx * det_inv;
+        const float mid = 0.5f * (cxx + cyy);
+        const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+        const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+        const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+        // auxiliary.h:41-44: ndc2Pix is evaluated in double
+        px = (float)(((projx + 1.0) * p.W - 1.0) * 0.5);
+        py = (float)(((projy + 1.0) * p.H - 1.0) * 0.5);
+        const TileRect rc = tile_rect(px, py, (int)my_radius, p.gx, p.gy);
+        nref = (rc.x1 - rc.x0) * (rc.y1 - rc.y0);
+        if (nref != 0) {
+          visible = true;
+          radius = (int)my_radius;
+          opacity = st.opac[lane];
+          if (p.flags & GSB_RASTER_EXACT_TILE_CULL) {
+            const float two_tau = 2.f * logf(255.f * opacity);
+            for (uint32_t ty = rc.y0; ty < rc.y1; ++ty)
+              for (uint32_t tx = rc.x0; tx < rc.x1; ++tx)
+                ntiles += tile_can_contribute(px, py, ca, cb, cc, two_tau, tx, ty) ? 1u : 0u;
+          } else {
+            ntiles = nref;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- stage 2: colour.  The 6 KB SH block is fetched only if some lane needs it -------------
+  float cr = 0.f, cg = 0.f, cbl = 0.f;
+  const bool any_visible = __any_sync(0xffffffffu, visible);
+  if (p.colors == nullptr) {
+    const int shf = p.M * 3;  // floats per Gaussian
+    if (any_visible) {
+      const bool tma_sh = full_tma && (shf * 4) % 16 == 0 && shf <= kMaxShFloats;
+      if (tma_sh) {
+        if (lane == 0) {
+          mbar_expect_tx(&st.bar, (uint32_t)(32 * shf * 4));
+          tma_load_1d(st.sh, p.shs + (size_t)base * shf, (uint32_t)(32 * shf * 4), &st.bar);
+        }
+        __syncwarp();
+        mbar_wait(&st.bar, 1);
+      } else {
+        for (int k = lane; k < count * shf; k += 32) st.sh[k] = p.shs[(size_t)base * shf + k];
+        __syncwarp();
+      }
+      if (visible) {
+        // forward.cu:20-71
+        const float* sh = st.sh + lane * shf;
+        const float3 cam = make_float3(p.campos[0], p.campos[1], p.campos[2]);
+        float3 dir = make_float3(pos.x - cam.x, pos.y - cam.y, pos.z - cam.z);
+        const float len = sqrt(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+        dir.x = dir.x / len;
+        dir.y = dir.y / len;
+        dir.z = dir.z / len;
+        const float SH_C0 = 0.28209479177387814f, SH_C1 = 0.4886025119029199f;
+        const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                                0.5462742152960396f};
+        const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+        float res[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          float v = SH_C0 * sh[ch];
+          if (p.D > 0) {
+            const float x = dir.x, y = dir.y, z = dir.z;
+            v = v - SH_C1 * y * sh[3 + ch] + SH_C1 * z * sh[6 + ch] - SH_C1 * x * sh[9 + ch];
+            if (p.D > 1) {
+              const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+              v = v + SH_C2[0] * xy * sh[12 + ch] + SH_C2[1] * yz * sh[15 + ch] +
+                  SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + ch] + SH_C2[3] * xz * sh[21 + ch] +
+                  SH_C2[4] * (xx - yy) * sh[24 + ch];
+              if (p.D > 2) {
+                v = v + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + ch] + SH_C3[1] * xy * z * sh[30 + ch] +
+                    SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + ch] +
+                    SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + ch] +
+                    SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + ch] + SH_C3[5] * z * (xx - yy) * sh[42 + ch] +
+                    SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + ch];
+              }
+            }
+          }
+          v += 0.5f;
+          res[ch] = max(v, 0.0f);
+        }
+        cr = res[0];
+        cg = res[1];
+        cbl = res[2];
+      }
+    }
+  } else if (visible) {
+    cr = p.colors[(size_t)idx * 3];
+    cg = p.colors[(size_t)idx * 3 + 1];
+    cbl = p.colors[(size_t)idx * 3 + 2];
+  }
+
+  // ---- outputs --------------------------------------------------------------------------------
+  if (valid) {
+    if (visible) {
+      p.recA[idx] = make_float4(px, py, zv, opacity);
+      p.recB[idx] = make_float4(ca, cb, cc, cr);
+      p.recC[idx] = make_float2(cg, cbl);
+    }
+    p.tiles[idx] = ntiles;
+    p.radii[idx] = radius;
+  }
+  unsigned long long wsum = nref;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  if (lane == 0 && wsum) atomicAdd(p.ref_count, wsum);
+}
+
+// rasterizer_impl.cu:70-111: one (key, value) per kept (Gaussian, tile) pair, written at the
+// Gaussian's prefix-sum offset in ascending tile order (the stable sort then preserves ascending
+// Gaussian index among equal keys).
+__global__ void __launch_bounds__(256) emit_instances_kernel(int P, const float4* __restrict__ recA,
+                                                             const float4* __restrict__ recB,
+                                                             const uint32_t* __restrict__ tiles,
+                                                             const uint32_t* __restrict__ offsets,
+                                                             const int* __restrict__ radii, uint32_t gx, uint32_t gy,
+                                                             uint32_t flags, int64_t capacity,
+                                                             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const uint32_t n = tiles[idx];
+  if (n == 0) return;
+  const uint32_t end = offsets[idx];
+  uint32_t off = end - n;
+  if ((int64_t)end > capacity) return;  // host reports GSB_ERR_WORKSPACE
+  const float4 A = recA[idx];
+  const float4 B = recB[idx];
+  const TileRect rc = tile_rect(A.x, A.y, radii[idx], gx, gy);
+  const uint32_t depth_bits = __float_as_uint(A.z);
+  const bool exact = flags & GSB_RASTER_EXACT_TILE_CULL;
+  const float two_tau = exact ? 2.f * logf(255.f * A.w) : 0.f;
+  for (uint32_t ty = rc.y0; ty < rc.y1; ++ty)
+    for (uint32_t tx = rc.x0; tx < rc.x1; ++tx) {
+      if (exact && !tile_can_contribute(A.x, A.y, B.x, B.y, B.z, two_tau, tx, ty)) continue;
+      if (off >= end) return;
+      keys[off] = ((uint64_t)(ty * gx + tx) << 32) | depth_bits;
+      vals[off] = (uint32_t)idx;
+      ++off;
+    }
+}
+
+// rasterizer_impl.cu:116-138
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const uint64_t* __restrict__ keys,
+                                                          uint2* __restrict__ ranges) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L) return;
+  const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+  if (idx == 0) {
+    ranges[cur].x = 0;
+  } else {
+    const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+    if (cur != prev) {
+      ranges[prev].y = (uint32_t)idx;
+      ranges[cur].x = (uint32_t)idx;
+    }
+  }
+  if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+}
+
+// forward.cu:261-374, with colour + depth carried in the shared-memory batch and an
+// expected-depth accumulator next to the colour.
+__global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __restrict__ ranges,
+                                                            const uint32_t* __restrict__ point_list, int W, int H,
+                                                            const float4* __restrict__ recA,
+                                                            const float4* __restrict__ recB,
+                                                            const float2* __restrict__ recC,
+                                                            const float* __restrict__ bg, float* __restrict__ out_color,
+                                                            float* __restrict__ out_depth, float* __restrict__ out_T) {
+  __shared__ float4 sA[kTilePixels];
+  __shared__ float4 sB[kTilePixels];
+  __shared__ float2 sC[kTilePixels];
+  const uint32_t tiles_x = (W + kTile - 1) / kTile;
+  const uint32_t lx = threadIdx.x & (kTile - 1), ly = threadIdx.x >> 4;
+  const uint32_t pix_x = blockIdx.x * kTile + lx, pix_y = blockIdx.y * kTile + ly;
+  const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+  const float pfx = (float)pix_x, pfy = (float)pix_y;
+  const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
+  const int rounds = (range.y - range.x + kTilePixels - 1) / kTilePixels;
+  int todo = range.y - range.x;
+  bool done = !inside;
+  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
+
+  for (int i = 0; i < rounds; ++i, todo -= kTilePixels) {
+    if (__syncthreads_count(done) == kTilePixels) break;
+    const uint32_t slot = range.x + i * kTilePixels + threadIdx.x;
+    if (slot < range.y) {
+      const uint32_t g = point_list[slot];
+      sA[threadIdx.x] = recA[g];
+      sB[threadIdx.x] = recB[g];
+      sC[threadIdx.x] = recC[g];
+    }
+    __syncthreads();
+    const int batch = min(kTilePixels, todo);
+    for (int j = 0; !done && j < batch; ++j) {
+      const float4 A = sA[j];
+      const float4 B = sB[j];
+      const float dx = A.x - pfx, dy = A.y - pfy;
+      const float power = -0.5f * (B.x * dx * dx + B.z * dy * dy) - B.y * dx * dy;
+      if (power > 0.0f) continue;
+      const float alpha = min(0.99f, A.w * exp(power));
+      if (alpha < 1.0f / 255.0f) continue;
+      const float test_T = T * (1 - alpha);
+      if (test_T < 0.0001f) {
+        done = true;
+        continue;
+      }
+      const float2 gb = sC[j];
+      C0 += B.w * alpha * T;
+      C1 += gb.x * alpha * T;
+      C2 += gb.y * alpha * T;
+      Dz += A.z * alpha * T;
+      T = test_T;
+    }
+  }
+  if (inside) {
+    const size_t pid = (size_t)pix_y * W + pix_x;
+    const size_t plane = (size_t)H * W;
+    out_color[pid] = C0 + T * bg[0];
+    out_color[plane + pid] = C1 + T * bg[1];
+    out_color[2 * plane + pid] = C2 + T * bg[2];
+    if (out_depth) out_depth[pid] = Dz;
+    if (out_T) out_T[pid] = T;
+  }
+}
+
+__global__ void write_counts_kernel(const uint32_t* __restrict__ offsets, int P, const unsigned long long* ref_count,
+                                    int64_t* out) {
+  out[0] = P > 0 ? (int64_t)offsets[P - 1] : 0;
+  out[1] = (int64_t)*ref_count;
+}
+
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means,
+                                                           const float* __restrict__ vm, uint8_t* present) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float x = means[3 * (size_t)idx], y = means[3 * (size_t)idx + 1], z = means[3 * (size_t)idx + 2];
+  present[idx] = (vm[2] * x + vm[6] * y + vm[10] * z + vm[14]) > 0.2f ? 1 : 0;
+}
+
+// cv::saturate_cast<uchar>(v): round half to even, clamp to [0,255]
+__global__ void __launch_bounds__(256) to_u8_kernel(const float* __restrict__ chw, int W, int H, uint8_t* __restrict__ hwc) {
+  const size_t n = (size_t)W * H;
+  const size_t pid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pid >= n) return;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float v = chw[ch * n + pid] * 255.f;
+    int q = __float2int_rn(v);
+    q = q < 0 ? 0 : (q > 255 ? 255 : q);
+    if (!(v == v)) q = 0;
+    hwc[pid * 3 + ch] = (uint8_t)q;
+  }
+}
+
+// rasterizer_impl.cu:35-50
+uint32_t higher_msb(uint32_t n) {
+  uint32_t msb = sizeof(n) * 4, step = msb;
+  while (step > 1) {
+    step /= 2;
+    if (n >> msb)
+      msb += step;
+    else
+      msb -= step;
+  }
+  if (n >> msb) msb++;
+  return msb;
+}
+
+struct Workspace {
+  float4* recA;
+  float4* recB;
+  float2* recC;
+  uint32_t* tiles;
+  uint32_t* offsets;
+  int* radii;
+  unsigned long long* counters;  // [0] reference instance count
+  uint2* ranges;
+  uint64_t* keys_in;
+  uint64_t* keys_out;
+  uint32_t* vals_in;
+  uint32_t* vals_out;
+  void* scan_temp;
+  size_t scan_temp_bytes;
+  void* sort_temp;
+  size_t sort_temp_bytes;
+  size_t total;
+};
+
+Workspace carve(void* base, int32_t P, int32_t W, int32_t H, int64_t R) {
+  Workspace w{};
+  Carver c(base);
+  const size_t Pn = (size_t)(P > 1 ? P : 1), Rn = (size_t)(R > 1 ? R : 1);
+  const size_t ntiles = (size_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
+  w.recA = c.take<float4>(Pn);
+  w.recB = c.take<float4>(Pn);
+  w.recC = c.take<float2>(Pn);
+  w.tiles = c.take<uint32_t>(Pn);
+  w.offsets = c.take<uint32_t>(Pn);
+  w.radii = c.take<int>(Pn);
+  w.counters = c.take<unsigned long long>(8);
+  w.ranges = c.take<uint2>(ntiles);
+  w.keys_in = c.take<uint64_t>(Rn);
+  w.keys_out = c.take<uint64_t>(Rn);
+  w.vals_in = c.take<uint32_t>(Rn);
+  w.vals_out = c.take<uint32_t>(Rn);
+  cub::DeviceScan::InclusiveSum(nullptr, w.scan_temp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)Pn);
+  w.scan_temp = c.take<char>(w.scan_temp_bytes);
+  cub::DeviceRadixSort::SortPairs(nullptr, w.sort_temp_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int64_t)Rn);
+  w.sort_temp = c.take<char>(w.sort_temp_bytes);
+  w.total = c.total();
+  return w;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace gsb
+
+using namespace gsb;
+
+extern "C" {
+
+const char* gsb_last_error(void) { return g_error; }
+int gsb_version(void) { return GSB_VERSION; }
+uint64_t gsb_kernel_launch_count(void) { return g_launches.load(); }
+int64_t gsb_raster_required_instances(void) { return g_required_instances; }
+
+size_t gsb_raster_workspace_bytes(int32_t P, int32_t width, int32_t height, int64_t max_instances) {
+  return carve(nullptr, P, width, height, max_instances).total;
+}
+
+int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!a) return fail(GSB_ERR_INVALID, "args is NULL");
+  if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(GSB_ERR_INVALID, "bad P / image size");
+  if (!a->out_color || !a->background || !a->viewmatrix || !a->projmatrix || !a->cam_pos)
+    return fail(GSB_ERR_INVALID, "out_color, background, viewmatrix, projmatrix and cam_pos are required");
+  // DGR/diff_gaussian_rasterization/__init__.py:191-195
+  if ((a->shs == nullptr) == (a->colors_precomp == nullptr))
+    return fail(GSB_ERR_INVALID, "Please provide excatly one of either SHs or precomputed colors!");
+  const bool has_sr = a->scales != nullptr && a->rotations != nullptr;
+  if (((a->scales == nullptr || a->rotations == nullptr) && a->cov3D_precomp == nullptr) ||
+      ((a->scales != nullptr || a->rotations != nullptr) && a->cov3D_precomp != nullptr))
+    return fail(GSB_ERR_INVALID,
+                "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+  if (a->shs && (a->sh_coeffs <= 0 || a->sh_coeffs > 16 || a->sh_degree < 0 || a->sh_degree > 3 ||
+                 (a->sh_degree + 1) * (a->sh_degree + 1) > a->sh_coeffs))
+    return fail(GSB_ERR_INVALID, "SH degree %d needs %d coefficients, tensor has %d (max 16)", a->sh_degree,
+                (a->sh_degree + 1) * (a->sh_degree + 1), a->sh_coeffs);
+  if (!a->workspace) return fail(GSB_ERR_WORKSPACE, "workspace is NULL");
+  const int P = a->P, W = a->width, H = a->height;
+  const int64_t cap = a->max_instances;
+  Workspace ws = carve(a->workspace, P, W, H, cap);
+  if (ws.total > a->workspace_bytes)
+    return fail(GSB_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", a->workspace_bytes, ws.total);
+  const bool dbg = a->flags & GSB_RASTER_DEBUG_SYNC;
+  const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+  const size_t npix = (size_t)W * H;
+  int rc;
+
+  if (P == 0) {  // rasterize_points.cu:77: outputs stay zero-filled
+    GSB_CUDA_OK(cudaMemsetAsync(a->out_color, 0, 3 * npix * sizeof(float), stream));
+    if (a->out_depth) GSB_CUDA_OK(cudaMemsetAsync(a->out_depth, 0, npix * sizeof(float), stream));
+    if (a->out_final_T) GSB_CUDA_OK(cudaMemsetAsync(a->out_final_T, 0, npix * sizeof(float), stream));
+    if (a->num_rendered) GSB_CUDA_OK(cudaMemsetAsync(a->num_rendered, 0, 2 * sizeof(int64_t), stream));
+    return GSB_OK;
+  }
+
+  PreParams pp{};
+  pp.P = P;
+  pp.D = a->sh_degree;
+  pp.M = a->sh_coeffs;
+  pp.W = W;
+  pp.H = H;
+  pp.means3D = a->means3D;
+  pp.shs = a->shs;
+  pp.colors = a->colors_precomp;
+  pp.opacities = a->opacities;
+  pp.scales = a->scales;
+  pp.rotations = a->rotations;
+  pp.cov3D = a->cov3D_precomp;
+  pp.scale_modifier = a->scale_modifier;
+  pp.view = a->viewmatrix;
+  pp.proj = a->projmatrix;
+  pp.campos = a->cam_pos;
+  pp.tan_fovx = a->tan_fovx;
+  pp.tan_fovy = a->tan_fovy;
+  pp.focal_y = H / (2.0f * a->tan_fovy);  // rasterizer_impl.cu:222-223
+  pp.focal_x = W / (2.0f * a->tan_fovx);
+  pp.gx = gx;
+  pp.gy = gy;
+  pp.flags = a->flags;
+  pp.use_tma = !(a->flags & GSB_RASTER_NO_TMA) && aligned16(a->means3D) && aligned16(a->opacities) &&
+               (!has_sr || (aligned16(a->scales) && aligned16(a->rotations))) && (!a->shs || aligned16(a->shs));
+  pp.recA = ws.recA;
+  pp.recB = ws.recB;
+  pp.recC = ws.recC;
+  pp.tiles = ws.tiles;
+  pp.radii = a->radii ? a->radii : ws.radii;
+  pp.ref_count = ws.counters;
+
+  GSB_CUDA_OK(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream));
+  const int pre_blocks = (P + kPreThreads - 1) / kPreThreads;
+  preprocess_kernel<<<pre_blocks, kPreThreads, 0, stream>>>(pp);
+  count_launch();
+  if ((rc = check_launch("preprocess_kernel", stream, dbg))) return rc;
+
+  GSB_CUDA_OK(cub::DeviceScan::InclusiveSum(ws.scan_temp, ws.scan_temp_bytes, ws.tiles, ws.offsets, P, stream));
+  if (a->num_rendered) {
+    write_counts_kernel<<<1, 1, 0, stream>>>(ws.offsets, P, ws.counters, a->num_rendered);
+    count_launch();
+  }
+
+  // Instance count -> host (the reference does the same blocking read, rasterizer_impl.cu:281).
+  uint32_t R32 = 0;
+  GSB_CUDA_OK(cudaMemcpyAsync(&R32, ws.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  GSB_CUDA_OK(cudaStreamSynchronize(stream));
+  const int64_t R = (int64_t)R32;
+  g_required_instances = R;
+  if (R > cap) return fail(GSB_ERR_WORKSPACE, "frame needs %lld instances, workspace sized for %lld", (long long)R, (long long)cap);
+
+  if (R > 0) {
+    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ws.recA, ws.recB, ws.tiles, ws.offsets, pp.radii, gx, gy,
+                                                               a->flags, cap, ws.keys_in, ws.vals_in);
+    count_launch();
+    if ((rc = check_launch("emit_instances_kernel", stream, dbg))) return rc;
+    const int bit = (int)higher_msb(gx * gy);
+    GSB_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.sort_temp, ws.sort_temp_bytes, ws.keys_in, ws.keys_out, ws.vals_in,
+                                                ws.vals_out, R, 0, 32 + bit, stream));
+    if ((rc = check_launch("radix sort", stream, dbg))) return rc;
+  }
+  GSB_CUDA_OK(cudaMemsetAsync(ws.ranges, 0, (size_t)gx * gy * sizeof(uint2), stream));
+  if (R > 0) {
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, ws.keys_out, ws.ranges);
+    count_launch();
+    if ((rc = check_launch("tile_ranges_kernel", stream, dbg))) return rc;
+  }
+  render_kernel<<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, ws.vals_out, W, H, ws.recA, ws.recB, ws.recC,
+                                                         a->background, a->out_color, a->out_depth, a->out_final_T);
+  count_launch();
+  if ((rc = check_launch("render_kernel", stream, dbg))) return rc;
+  return GSB_OK;
+}
+
+int gsb_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                            uint8_t* present, void* stream_v) {
+  (void)projmatrix;  // the reference computes p_proj but only tests z_view (auxiliary.h:154)
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(GSB_ERR_INVALID, "mark_visible: bad arguments");
+  if (P == 0) return GSB_OK;
+  mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+  count_launch();
+  return check_launch("mark_visible_kernel", stream, false);
+}
+
+int gsb_image_to_u8(const float* chw, int32_t width, int32_t height, uint8_t* hwc, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!chw || !hwc || width <= 0 || height <= 0) return fail(GSB_ERR_INVALID, "image_to_u8: bad arguments");
+  const size_t n = (size_t)width * height;
+  to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(chw, width, height, hwc);
+  count_launch();
+  return check_launch("to_u8_kernel", stream, false);
+}
+
+}  // extern "C"

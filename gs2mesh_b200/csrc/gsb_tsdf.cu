@@ -1,0 +1,454 @@
+// TSDF integration for sm_100a: a bounded, brick-addressed window of Open3D's
+// ScalableTSDFVolume lattice (what gs2mesh_utils/tsdf_utils.py:53-56,107 drives).
+//
+// The reference integrates through Open3D 0.17.0 (CPU): per frame it back-projects every
+// 4th pixel, opens all 16^3 "volume units" within +-sdf_trunc of those points and runs
+// UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier on each unit once
+// (SURVEY.md rows T1/T2).  Here the same two steps are two kernels over a dense brick store:
+//
+//   mark_bricks   one thread per sampled pixel; fp64 back-projection (Open3D builds the point
+//                 cloud in double), brick box of the point +- trunc, de-duplication with a
+//                 per-brick frame stamp (atomicExch) and an append-only work list.
+//   integrate     persistent CTAs pull bricks from the list.  A brick is 32 KB of contiguous
+//                 (tsdf, weight) pairs: thread t owns voxel pairs (2 consecutive z) and moves
+//                 them with 16-byte loads/stores, 8 independent loads in flight per thread.
+//                 Projection, truncated distance and the running weighted mean are fused; the
+//                 depth-to-camera-distance multiplier is recomputed instead of read.
+//
+// fp32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) in Open3D's
+// operation order, so results are bit-identical to oracle/tsdf_oracle.cpp.
+#include "gsb_common.h"
+
+struct GsbVolume {
+  GsbVolumeDesc d;
+  uint32_t frame = 0;
+  size_t n_bricks = 0;
+};
+
+namespace gsb {
+namespace {
+
+struct MarkParams {
+  int W, H, nsx, nsy;
+  double fx, fy, cx, cy;
+  double pose[12];  // rows 0..2 of extrinsic^-1 (camera -> world)
+  double trunc, unit_length;
+  int b0[3], nb[3];
+};
+
+__global__ void __launch_bounds__(256) mark_bricks_kernel(const MarkParams m, const float* __restrict__ depth,
+                                                          uint32_t* __restrict__ stamp, uint32_t* __restrict__ list,
+                                                          uint32_t* __restrict__ counters, uint32_t frame) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= m.nsx * m.nsy) return;
+  const int i = (s / m.nsx) * 4, j = (s % m.nsx) * 4;  // depth_sampling_stride = 4
+  const float p = depth[(size_t)i * m.W + j];
+  if (!(p > 0.f)) return;
+  // PointCloudFactory.cpp CreatePointCloudFromFloatDepthImage, all in double
+  const double z = (double)p;
+  const double x = __ddiv_rn(__dmul_rn((double)j - m.cx, z), m.fx);
+  const double y = __ddiv_rn(__dmul_rn((double)i - m.cy, z), m.fy);
+  int lo[3], hi[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m.pose[4 * r], x), __dmul_rn(m.pose[4 * r + 1], y)),
+                                         __dmul_rn(m.pose[4 * r + 2], z)),
+                               m.pose[4 * r + 3]);
+    lo[r] = (int)floor(__ddiv_rn(__dadd_rn(w, -m.trunc), m.unit_length));
+    hi[r] = (int)floor(__ddiv_rn(__dadd_rn(w, m.trunc), m.unit_length));
+  }
+  for (int bx = lo[0]; bx <= hi[0]; ++bx)
+    for (int by = lo[1]; by <= hi[1]; ++by)
+      for (int bz = lo[2]; bz <= hi[2]; ++bz) {
+        const int rx = bx - m.b0[0], ry = by - m.b0[1], rz = bz - m.b0[2];
+        if (rx < 0 || ry < 0 || rz < 0 || rx >= m.nb[0] || ry >= m.nb[1] || rz >= m.nb[2]) {
+          atomicAdd(&counters[1], 1u);  // point needs a brick outside the window (diagnostic)
+          continue;
+        }
+        const uint32_t b = ((uint32_t)rx * m.nb[1] + ry) * m.nb[2] + rz;
+        if (stamp[b] == frame) continue;
+        if (atomicExch(&stamp[b], frame) != frame) list[atomicAdd(&counters[0], 1u)] = b;
+      }
+}
+
+struct FrameParams {
+  float E[12];  // rows 0..2 of the world->camera extrinsic, cast to float
+  float fx, fy, cx, cy, inv_fx, inv_fy;
+  float vl, half, trunc, trunc_inv;
+  float sx, sy, sz;  // E(:,2) * voxel_length
+  float safe_w, safe_h;
+  int W, H;
+  int b0[3], nb[3];
+  double unit_length;
+};
+
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// One voxel of UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier.
+// Returns true when (tsdf, w) was updated; `pix` receives the depth-image index used.
+__device__ __forceinline__ bool fuse_voxel(const FrameParams& f, const float* __restrict__ depth, float pcx, float pcy,
+                                           float pcz, float& tsdf, float& w, float& w_before, int& pix) {
+  if (pcz <= 0.f) return false;
+  const float u_f = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(pcx, f.fx), pcz), f.cx), 0.5f);
+  const float v_f = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(pcy, f.fy), pcz), f.cy), 0.5f);
+  if (!(u_f >= 0.0001f && u_f < f.safe_w && v_f >= 0.0001f && v_f < f.safe_h)) return false;
+  const int u = (int)u_f, v = (int)v_f;
+  pix = v * f.W + u;
+  const float d = __ldg(depth + pix);
+  if (d <= 0.0f) return false;
+  // CreateDepthToCameraDistanceMultiplierFloatImage, recomputed per lookup
+  const float xx = __fmul_rn(__fsub_rn((float)u, f.cx), f.inv_fx);
+  const float yy = __fmul_rn(__fsub_rn((float)v, f.cy), f.inv_fy);
+  const float mult = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy)), 1.0f));
+  const float sdf = __fmul_rn(__fsub_rn(d, pcz), mult);
+  if (!(sdf > -f.trunc)) return false;
+  const float t = fminf(1.0f, __fmul_rn(sdf, f.trunc_inv));
+  w_before = w;
+  tsdf = __fdiv_rn(__fadd_rn(__fmul_rn(tsdf, w), t), __fadd_rn(w, 1.0f));
+  w = __fadd_rn(w, 1.0f);
+  return true;
+}
+
+__device__ __forceinline__ void fuse_color(float4& c, float w_before, const uint8_t* __restrict__ rgb, int pix) {
+  const float r = (float)rgb[3 * (size_t)pix], g = (float)rgb[3 * (size_t)pix + 1], b = (float)rgb[3 * (size_t)pix + 2];
+  const float den = __fadd_rn(w_before, 1.0f);
+  c.x = __fdiv_rn(__fadd_rn(__fmul_rn(c.x, w_before), r), den);
+  c.y = __fdiv_rn(__fadd_rn(__fmul_rn(c.y, w_before), g), den);
+  c.z = __fdiv_rn(__fadd_rn(__fmul_rn(c.z, w_before), b), den);
+}
+
+constexpr int kIntThreads = 256;
+constexpr int kPasses = GSB_BRICK_VOXELS / 2 / kIntThreads;  // 8 voxel-pair passes per brick
+
+__global__ void __launch_bounds__(kIntThreads) integrate_kernel(const FrameParams f, const float* __restrict__ depth,
+                                                               const uint8_t* __restrict__ rgb, float4* __restrict__ tw,
+                                                               float4* __restrict__ color,
+                                                               const uint32_t* __restrict__ list,
+                                                               const uint32_t* __restrict__ counters) {
+  const uint32_t n = counters[0];
+  const int t = threadIdx.x;
+  // thread -> voxel pair: pair q = pass*256 + t, first voxel 2q = (x, y, z) with
+  //   x = 2*pass + (t >> 7), y = (t >> 3) & 15, z = 2 * (t & 7)
+  const int y = (t >> 3) & 15, z0 = 2 * (t & 7), xo = t >> 7;
+  for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
+    const uint32_t brick = list[it];
+    const int bz = brick % f.nb[2], by = (brick / f.nb[2]) % f.nb[1], bx = brick / (f.nb[2] * f.nb[1]);
+    const double ox = (double)(f.b0[0] + bx) * f.unit_length;  // origin = index * unit_length (OpenVolumeUnit)
+    const double oy = (double)(f.b0[1] + by) * f.unit_length;
+    const double oz = (double)(f.b0[2] + bz) * f.unit_length;
+    float4* base = tw + (size_t)brick * (GSB_BRICK_VOXELS / 2);
+    float4 v[kPasses];
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p) v[p] = ld_stream(base + p * kIntThreads + t);
+
+    const float py = (float)((double)__fadd_rn(f.half, __fmul_rn(f.vl, (float)y)) + oy);
+    const float pz = (float)((double)f.half + oz);
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p) {
+      const int x = 2 * p + xo;
+      const float px = (float)((double)__fadd_rn(f.half, __fmul_rn(f.vl, (float)x)) + ox);
+      // pt_camera = extrinsic * (px,py,pz,1), then z0 incremental steps along the brick's z axis
+      float cxm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.E[0], px), __fmul_rn(f.E[1], py)), __fmul_rn(f.E[2], pz)), f.E[3]);
+      float cym = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.E[4], px), __fmul_rn(f.E[5], py)), __fmul_rn(f.E[6], pz)), f.E[7]);
+      float czm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.E[8], px), __fmul_rn(f.E[9], py)), __fmul_rn(f.E[10], pz)), f.E[11]);
+      for (int k = 0; k < z0; ++k) {
+        cxm = __fadd_rn(cxm, f.sx);
+        cym = __fadd_rn(cym, f.sy);
+        czm = __fadd_rn(czm, f.sz);
+      }
+      float wb0 = 0.f, wb1 = 0.f;
+      int pix0 = 0, pix1 = 0;
+      const bool up0 = fuse_voxel(f, depth, cxm, cym, czm, v[p].x, v[p].y, wb0, pix0);
+      cxm = __fadd_rn(cxm, f.sx);
+      cym = __fadd_rn(cym, f.sy);
+      czm = __fadd_rn(czm, f.sz);
+      const bool up1 = fuse_voxel(f, depth, cxm, cym, czm, v[p].z, v[p].w, wb1, pix1);
+      if (up0 || up1) {
+        st_stream(base + p * kIntThreads + t, v[p]);
+        if (color != nullptr && rgb != nullptr) {
+          float4* cp = color + ((size_t)brick * GSB_BRICK_VOXELS + 2 * (size_t)(p * kIntThreads + t));
+          if (up0) {
+            float4 c = ld_stream(cp);
+            fuse_color(c, wb0, rgb, pix0);
+            st_stream(cp, c);
+          }
+          if (up1) {
+            float4 c = ld_stream(cp + 1);
+            fuse_color(c, wb1, rgb, pix1);
+            st_stream(cp + 1, c);
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) prepare_depth_kernel(const float* __restrict__ in, const float* __restrict__ final_T,
+                                                            const uint8_t* __restrict__ mask, size_t n, float alpha_min,
+                                                            float min_depth, float depth_scale, double depth_trunc,
+                                                            float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float d = in[i];
+  if (final_T) {
+    const float alpha = 1.0f - final_T[i];
+    d = alpha > alpha_min ? __fdiv_rn(d, alpha) : 0.f;
+  }
+  if (mask) d = d * (float)mask[i];
+  if (d < min_depth) d = 0.f;          // tsdf_utils.py:83
+  d = __fdiv_rn(d, depth_scale);       // ConvertDepthToFloatImage
+  if ((double)d >= depth_trunc) d = 0.f;
+  out[i] = d;
+}
+
+// (mean, weight) <-> (sum, weight) over the whole store; mode 0: to sums, 1: from sums
+__global__ void __launch_bounds__(256) sums_kernel(float4* __restrict__ tw, float4* __restrict__ color, size_t n_pairs, int mode) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  float4 v = tw[i];
+  if (v.y == 0.f && v.w == 0.f) return;
+  const float w0 = v.y, w1 = v.w;
+  if (mode == 0) {
+    v.x *= w0;
+    v.z *= w1;
+  } else {
+    v.x = w0 > 0.f ? v.x / w0 : 0.f;
+    v.z = w1 > 0.f ? v.z / w1 : 0.f;
+  }
+  tw[i] = v;
+  if (color) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float w = k ? w1 : w0;
+      if (w == 0.f) continue;
+      float4 c = color[2 * i + k];
+      if (mode == 0) {
+        c.x *= w;
+        c.y *= w;
+        c.z *= w;
+      } else {
+        c.x /= w;
+        c.y /= w;
+        c.z /= w;
+      }
+      color[2 * i + k] = c;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) export_dense_kernel(const float2* __restrict__ tw, int nbx, int nby, int nbz,
+                                                           float* __restrict__ tsdf, float* __restrict__ weight) {
+  const size_t n = (size_t)nbx * nby * nbz * GSB_BRICK_VOXELS;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // brick-layout index
+  if (i >= n) return;
+  const size_t brick = i / GSB_BRICK_VOXELS;
+  const int vi = (int)(i % GSB_BRICK_VOXELS);
+  const int bz = (int)(brick % nbz), by = (int)((brick / nbz) % nby), bx = (int)(brick / ((size_t)nbz * nby));
+  const int x = bx * 16 + (vi >> 8), y = by * 16 + ((vi >> 4) & 15), z = bz * 16 + (vi & 15);
+  const size_t o = ((size_t)x * (nby * 16) + y) * (nbz * 16) + z;
+  const float2 v = tw[i];
+  if (tsdf) tsdf[o] = v.x;
+  if (weight) weight[o] = v.y;
+}
+
+__global__ void copy_stats_kernel(const uint32_t* counters, uint32_t frame, uint32_t* out) {
+  out[0] = counters[0];
+  out[1] = counters[1];
+  out[2] = frame;
+  out[3] = 0;
+}
+
+// general 4x4 inverse in double (Gauss-Jordan with partial pivoting)
+bool invert4(const double* m, double* out) {
+  double a[4][8];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      a[r][c] = m[4 * r + c];
+      a[r][4 + c] = r == c ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 4; ++r)
+      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    if (a[piv][c] == 0.0) return false;
+    if (piv != c)
+      for (int k = 0; k < 8; ++k) {
+        double tmp = a[c][k];
+        a[c][k] = a[piv][k];
+        a[piv][k] = tmp;
+      }
+    const double d = a[c][c];
+    for (int k = 0; k < 8; ++k) a[c][k] /= d;
+    for (int r = 0; r < 4; ++r)
+      if (r != c) {
+        const double fct = a[r][c];
+        for (int k = 0; k < 8; ++k) a[r][k] -= fct * a[c][k];
+      }
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) out[4 * r + c] = a[r][4 + c];
+  return true;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace
+}  // namespace gsb
+
+using namespace gsb;
+
+extern "C" {
+
+GsbVolume* gsb_tsdf_create(const GsbVolumeDesc* desc) {
+  if (!desc || !desc->tsdf_weight || !desc->brick_stamp || !desc->brick_list || !desc->counters) {
+    fail(GSB_ERR_INVALID, "tsdf_create: tsdf_weight, brick_stamp, brick_list and counters are required");
+    return nullptr;
+  }
+  for (int k = 0; k < 3; ++k)
+    if (desc->brick_count[k] <= 0) {
+      fail(GSB_ERR_INVALID, "tsdf_create: brick_count must be positive");
+      return nullptr;
+    }
+  if (!(desc->voxel_length > 0) || !(desc->sdf_trunc > 0)) {
+    fail(GSB_ERR_INVALID, "tsdf_create: voxel_length and sdf_trunc must be positive");
+    return nullptr;
+  }
+  const size_t nb = (size_t)desc->brick_count[0] * desc->brick_count[1] * desc->brick_count[2];
+  if (nb > 0x7fffffffull) {
+    fail(GSB_ERR_INVALID, "tsdf_create: too many bricks");
+    return nullptr;
+  }
+  GsbVolume* v = new GsbVolume();
+  v->d = *desc;
+  v->n_bricks = nb;
+  return v;
+}
+
+void gsb_tsdf_destroy(GsbVolume* vol) { delete vol; }
+
+int gsb_tsdf_prepare_depth(const float* depth_in, const float* final_T, const uint8_t* mask, int32_t width, int32_t height,
+                           float alpha_min, float min_depth, double depth_scale, double depth_trunc, float* depth_out,
+                           void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!depth_in || !depth_out || width <= 0 || height <= 0) return fail(GSB_ERR_INVALID, "prepare_depth: bad arguments");
+  const size_t n = (size_t)width * height;
+  prepare_depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(depth_in, final_T, mask, n, alpha_min, min_depth,
+                                                                        (float)depth_scale, depth_trunc, depth_out);
+  count_launch();
+  return check_launch("prepare_depth_kernel", stream, false);
+}
+
+int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, int32_t width, int32_t height, double fx,
+                       double fy, double cx, double cy, const double* extrinsic, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!vol || !depth || !extrinsic || width <= 0 || height <= 0) return fail(GSB_ERR_INVALID, "tsdf_integrate: bad arguments");
+  const GsbVolumeDesc& d = vol->d;
+  double pose[16];
+  if (!invert4(extrinsic, pose)) return fail(GSB_ERR_INVALID, "tsdf_integrate: extrinsic is singular");
+  vol->frame += 1;
+  if (vol->frame == 0) {  // stamp wrap-around: start over
+    GSB_CUDA_OK(cudaMemsetAsync(d.brick_stamp, 0, vol->n_bricks * sizeof(uint32_t), stream));
+    vol->frame = 1;
+  }
+  GSB_CUDA_OK(cudaMemsetAsync(d.counters, 0, 8 * sizeof(uint32_t), stream));
+
+  MarkParams m{};
+  m.W = width;
+  m.H = height;
+  m.nsx = (width + 3) / 4;
+  m.nsy = (height + 3) / 4;
+  m.fx = fx;
+  m.fy = fy;
+  m.cx = cx;
+  m.cy = cy;
+  for (int k = 0; k < 12; ++k) m.pose[k] = pose[k];
+  m.trunc = d.sdf_trunc;
+  m.unit_length = d.voxel_length * GSB_BRICK;
+  for (int k = 0; k < 3; ++k) {
+    m.b0[k] = d.brick_origin[k];
+    m.nb[k] = d.brick_count[k];
+  }
+  const int ns = m.nsx * m.nsy;
+  mark_bricks_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(m, depth, d.brick_stamp, d.brick_list, d.counters, vol->frame);
+  count_launch();
+  int rc;
+  if ((rc = check_launch("mark_bricks_kernel", stream, false))) return rc;
+
+  FrameParams f{};
+  for (int k = 0; k < 12; ++k) f.E[k] = (float)extrinsic[k];
+  f.fx = (float)fx;
+  f.fy = (float)fy;
+  f.cx = (float)cx;
+  f.cy = (float)cy;
+  f.inv_fx = 1.0f / f.fx;
+  f.inv_fy = 1.0f / f.fy;
+  f.vl = (float)d.voxel_length;
+  f.half = f.vl * 0.5f;
+  f.trunc = (float)d.sdf_trunc;
+  f.trunc_inv = 1.0f / f.trunc;
+  f.sx = f.E[2] * f.vl;
+  f.sy = f.E[6] * f.vl;
+  f.sz = f.E[10] * f.vl;
+  f.safe_w = width - 0.0001f;
+  f.safe_h = height - 0.0001f;
+  f.W = width;
+  f.H = height;
+  f.unit_length = m.unit_length;
+  for (int k = 0; k < 3; ++k) {
+    f.b0[k] = d.brick_origin[k];
+    f.nb[k] = d.brick_count[k];
+  }
+  const int grid = (int)((size_t)num_sms() * 8 < vol->n_bricks ? (size_t)num_sms() * 8 : vol->n_bricks);
+  integrate_kernel<<<grid, kIntThreads, 0, stream>>>(f, depth, rgb, reinterpret_cast<float4*>(d.tsdf_weight),
+                                                     reinterpret_cast<float4*>(d.color), d.brick_list, d.counters);
+  count_launch();
+  return check_launch("integrate_kernel", stream, false);
+}
+
+static int run_sums(GsbVolume* vol, int mode, cudaStream_t stream) {
+  if (!vol) return fail(GSB_ERR_INVALID, "tsdf: volume is NULL");
+  const size_t n_pairs = vol->n_bricks * (GSB_BRICK_VOXELS / 2);
+  sums_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, stream>>>(reinterpret_cast<float4*>(vol->d.tsdf_weight),
+                                                                     reinterpret_cast<float4*>(vol->d.color), n_pairs, mode);
+  count_launch();
+  return check_launch("sums_kernel", stream, false);
+}
+
+int gsb_tsdf_to_sums(GsbVolume* vol, void* stream) { return run_sums(vol, 0, static_cast<cudaStream_t>(stream)); }
+int gsb_tsdf_from_sums(GsbVolume* vol, void* stream) { return run_sums(vol, 1, static_cast<cudaStream_t>(stream)); }
+
+int gsb_tsdf_export_dense(const GsbVolume* vol, float* tsdf, float* weight, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!vol || (!tsdf && !weight)) return fail(GSB_ERR_INVALID, "tsdf_export_dense: bad arguments");
+  const size_t n = vol->n_bricks * GSB_BRICK_VOXELS;
+  export_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float2*>(vol->d.tsdf_weight),
+                                                                       vol->d.brick_count[0], vol->d.brick_count[1],
+                                                                       vol->d.brick_count[2], tsdf, weight);
+  count_launch();
+  return check_launch("export_dense_kernel", stream, false);
+}
+
+int gsb_tsdf_last_stats(const GsbVolume* vol, uint32_t* out, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!vol || !out) return fail(GSB_ERR_INVALID, "tsdf_last_stats: bad arguments");
+  copy_stats_kernel<<<1, 1, 0, stream>>>(vol->d.counters, vol->frame, out);
+  count_launch();
+  return check_launch("copy_stats_kernel", stream, false);
+}
+
+}  // extern "C"

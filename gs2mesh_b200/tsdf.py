@@ -1,0 +1,357 @@
+"""TSDF fusion stage: B200-native replacement for the Open3D calls in
+gs2mesh_utils/tsdf_utils.py (reference), behind the reference's own class surface.
+
+Three layers, thinnest first:
+
+* `TSDFVolume`          torch-owned device memory + the C-ABI volume handle
+                        (`gsb_tsdf_*` in include/gs2mesh_b200.h).
+* `ScalableTSDFVolume`  Open3D-shaped facade (`integrate(rgbd, intrinsic, extrinsic)`,
+                        `extract_triangle_mesh()`), so the body of tsdf_utils.py:53-108 reads the
+                        same with `o3d` replaced by `gs2mesh_b200.o3d_compat`.
+* `TSDF`                the stage class run_single.py:154-174 drives:
+                        `TSDF(renderer, stereo, args, out_name)`, `.run()`, `.save_mesh()`,
+                        `.clean_mesh()`, plus the `integrate()` / `extract_mesh()` aliases
+                        BASELINE.json's north_star names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BRICK, BRICK_VOXELS, GsbVolumeDesc, ptr
+
+
+def default_window(resolution: int = 512):
+    """Brick window of the dense `resolution`^3 lattice centred on the origin: the dense equivalent
+    of `voxel_length = TSDF_voxel / 512` (tsdf_utils.py:51)."""
+    nb = resolution // BRICK
+    return (-(nb // 2),) * 3, (nb,) * 3
+
+
+class TSDFVolume:
+    """A bounded window of Open3D's ScalableTSDFVolume lattice, resident in HBM (brick layout,
+    see GsbVolumeDesc in include/gs2mesh_b200.h)."""
+
+    def __init__(self, voxel_length: float, sdf_trunc: float, brick_origin: Sequence[int] = (-16, -16, -16),
+                 brick_count: Sequence[int] = (32, 32, 32), with_color: bool = True, device="cuda"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("TSDFVolume needs a CUDA device (gs2mesh_b200 has no CPU path)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.voxel_length = float(voxel_length)
+        self.sdf_trunc = float(sdf_trunc)
+        self.brick_origin = tuple(int(v) for v in brick_origin)
+        self.brick_count = tuple(int(v) for v in brick_count)
+        self.n_bricks = int(np.prod(self.brick_count))
+        n_vox = self.n_bricks * BRICK_VOXELS
+        dev = self.device
+        self.tsdf_weight = torch.zeros(n_vox * 2, dtype=torch.float32, device=dev)
+        self.color = torch.zeros(n_vox * 4, dtype=torch.float32, device=dev) if with_color else None
+        self._stamp = torch.zeros(self.n_bricks, dtype=torch.int32, device=dev)
+        self._list = torch.zeros(self.n_bricks, dtype=torch.int32, device=dev)
+        self._counters = torch.zeros(8, dtype=torch.int32, device=dev)
+        self._depth_buf = None
+        desc = GsbVolumeDesc()
+        desc.brick_origin = (C.c_int32 * 3)(*self.brick_origin)
+        desc.brick_count = (C.c_int32 * 3)(*self.brick_count)
+        desc.voxel_length = self.voxel_length
+        desc.sdf_trunc = self.sdf_trunc
+        desc.tsdf_weight = ptr(self.tsdf_weight)
+        desc.color = ptr(self.color)
+        desc.brick_stamp = ptr(self._stamp)
+        desc.brick_list = ptr(self._list)
+        desc.counters = ptr(self._counters)
+        self._L = _lib.lib()
+        self._h = self._L.gsb_tsdf_create(C.byref(desc))
+        if not self._h:
+            raise _lib.GsbError(_lib.GSB_ERR_INVALID, self._L.gsb_last_error().decode())
+        self.frames_integrated = 0
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.gsb_tsdf_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def resolution(self):
+        return tuple(n * BRICK for n in self.brick_count)
+
+    @property
+    def origin(self):
+        """World position of the window's minimum corner."""
+        return tuple(o * BRICK * self.voxel_length for o in self.brick_origin)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t, name):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float32))
+        if not t.is_cuda:
+            t = t.to(self.device, non_blocking=True)
+        return t.contiguous().float()
+
+    def _u8(self, t):
+        if t is None:
+            return None
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.ascontiguousarray(t, dtype=np.uint8))
+        if not t.is_cuda:
+            t = t.to(self.device, non_blocking=True)
+        if t.dtype == torch.bool:
+            t = t.to(torch.uint8)
+        return t.contiguous()
+
+    # ------------------------------------------------------------------ hot path
+    def prepare_depth(self, depth, width, height, *, final_T=None, mask=None, alpha_min=0.5, min_depth=0.0,
+                      depth_scale=1.0, depth_trunc=float("inf"), out=None):
+        """Fused per-view depth preparation (tsdf_utils.py:78-93 + Open3D's depth conversion)."""
+        with torch.cuda.device(self.device):
+            depth = self._f32(depth, "depth")
+            final_T = None if final_T is None else self._f32(final_T, "final_T")
+            mask = self._u8(mask)
+            if out is None:
+                out = torch.empty(height, width, dtype=torch.float32, device=self.device)
+            trunc = float(depth_trunc) if np.isfinite(depth_trunc) else 3.0e38
+            _lib.check(self._L.gsb_tsdf_prepare_depth(ptr(depth), ptr(final_T), ptr(mask), int(width), int(height),
+                                                      float(alpha_min), float(min_depth), float(depth_scale), trunc,
+                                                      ptr(out), self._stream()))
+        return out
+
+    def integrate(self, depth, rgb, width, height, fx, fy, cx, cy, extrinsic_w2c):
+        """`volume.integrate(rgbd, intrinsic, extrinsic)` (tsdf_utils.py:107) on prepared inputs:
+        depth = float32 [H,W] already converted (see prepare_depth), rgb = uint8 [H,W,3] or None,
+        extrinsic_w2c = 4x4 world->camera (float64, host)."""
+        with torch.cuda.device(self.device):
+            depth = self._f32(depth, "depth")
+            if depth.numel() != width * height:
+                raise RuntimeError("[TSDFVolume::integrate] Unsupported image format.")  # Open3D's size check
+            rgb = self._u8(rgb)
+            if rgb is not None and rgb.numel() != width * height * 3:
+                raise RuntimeError("[TSDFVolume::integrate] Unsupported image format.")
+            e = np.ascontiguousarray(np.asarray(extrinsic_w2c, dtype=np.float64).reshape(16))
+            _lib.check(self._L.gsb_tsdf_integrate(self._h, ptr(depth), ptr(rgb if self.color is not None else None), int(width),
+                                                  int(height), float(fx), float(fy), float(cx), float(cy),
+                                                  e.ctypes.data_as(C.POINTER(C.c_double)), self._stream()))
+        self.frames_integrated += 1
+
+    def last_stats(self):
+        """(bricks touched, points needing bricks outside the window, frame id) of the last integrate (syncs)."""
+        out = torch.zeros(4, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.gsb_tsdf_last_stats(self._h, ptr(out), self._stream()))
+        v = out.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        return int(v[0]), int(v[1]), int(v[2])
+
+    # ------------------------------------------------------------------ multi-GPU merge
+    def to_sums(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.gsb_tsdf_to_sums(self._h, self._stream()))
+
+    def from_sums(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.gsb_tsdf_from_sums(self._h, self._stream()))
+
+    def reduce_across_ranks(self, group=None, dst: Optional[int] = None, chunk_bytes: int = 256 << 20):
+        """Merge view-sharded volumes: (mean, w) -> (sum, w), ONE NCCL SUM reduce of the volume
+        (chunked), -> (mean, w).  With dst=None every rank ends with the merged volume."""
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        self.to_sums()
+        for buf in (self.tsdf_weight, self.color):
+            if buf is None:
+                continue
+            step = max(1, chunk_bytes // 4)
+            for s in range(0, buf.numel(), step):
+                piece = buf[s:s + step]
+                if dst is None:
+                    dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group)
+                else:
+                    dist.reduce(piece, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        self.from_sums()
+
+    # ------------------------------------------------------------------ read-back
+    def bricks(self):
+        """View [n_bricks, 4096, 2] of the brick store (no copy)."""
+        return self.tsdf_weight.view(self.n_bricks, BRICK_VOXELS, 2)
+
+    def dense(self):
+        """(tsdf, weight) as dense [X,Y,Z] grids in Open3D UniformTSDFVolume index order."""
+        rx, ry, rz = self.resolution
+        tsdf = torch.empty(rx, ry, rz, dtype=torch.float32, device=self.device)
+        weight = torch.empty_like(tsdf)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.gsb_tsdf_export_dense(self._h, ptr(tsdf), ptr(weight), self._stream()))
+        return tsdf, weight
+
+    def reset(self):
+        self.tsdf_weight.zero_()
+        if self.color is not None:
+            self.color.zero_()
+        self._stamp.zero_()
+        self.frames_integrated = 0
+
+
+def merge_bricks_reference(volumes_tw):
+    """Host-side statement of the cross-rank merge (used by the CPU gloo tests):
+    given per-rank [n,4096,2] (mean, weight) arrays returns the merged (mean, weight)."""
+    total_w = sum(tw[..., 1] for tw in volumes_tw)
+    total_s = sum(tw[..., 0] * tw[..., 1] for tw in volumes_tw)
+    mean = np.where(total_w > 0, total_s / np.maximum(total_w, 1e-30), 0.0).astype(np.float32)
+    return np.stack([mean, total_w.astype(np.float32)], axis=-1)
+
+
+def shard_views(num_views: int, rank: int, world_size: int):
+    """View -> rank assignment of the multi-GPU path: round-robin."""
+    return list(range(rank, num_views, world_size))
+
+
+class TSDF:
+    """Stage class with the reference's surface (gs2mesh_utils/tsdf_utils.py:23-142)."""
+
+    def __init__(self, renderer, stereo, args, out_name, *, window_resolution: int = 512, device=None):
+        self.model_name = getattr(stereo, "model_name", "rendered")  # tsdf_utils.py:34
+        self.renderer = renderer
+        self.out_name = out_name
+        self.args = args
+        self.window_resolution = window_resolution
+        self.device = device or getattr(renderer, "device", "cuda")
+        self.volume: Optional[TSDFVolume] = None
+        self.mesh = None
+
+    # -- argument access with the reference's defaults (argument_utils.py:74-90)
+    def _arg(self, name, default):
+        return getattr(self.args, name, default)
+
+    def _make_volume(self):
+        voxel_length = float(self._arg("TSDF_voxel", 2)) / 512  # tsdf_utils.py:51
+        origin, count = default_window(self.window_resolution)
+        return TSDFVolume(voxel_length, float(self._arg("TSDF_sdf_trunc", 0.04)), origin, count, with_color=True,
+                          device=self.device)
+
+    def _selected(self, camera_number):
+        valid = self._arg("TSDF_valid", None)
+        skip = self._arg("TSDF_skip", None)
+        if camera_number % int(self._arg("TSDF_dilate", 1)) != 0:
+            return False
+        if valid is not None and camera_number not in valid:
+            return False
+        if skip is not None and camera_number in skip:
+            return False
+        return True
+
+    def _load_view(self, camera_number):
+        """(rgb uint8 [H,W,3], depth float32 [H,W], object_mask|None, occlusion_mask|None) for one view: from the
+        renderer's in-memory frames when it kept them, else from the files the reference stages exchange
+        (tsdf_utils.py:65-80)."""
+        frame = None
+        getter = getattr(self.renderer, "get_frame", None)
+        if getter is not None:
+            frame = getter(camera_number)
+        out_dir = self.renderer.render_folder_name(camera_number)
+        obj_mask = occ_mask = None
+        if frame is not None:
+            rgb, depth = frame["left_u8"], frame["depth"]
+        else:
+            from PIL import Image
+
+            rgb = np.array(Image.open(os.path.join(out_dir, "left.png"))).astype(np.uint8)
+            depth = np.load(os.path.join(out_dir, f"out_{self.model_name}", "depth.npy"))
+        if self._arg("TSDF_use_mask", False):
+            import cv2
+
+            m = np.load(os.path.join(out_dir, "left_mask.npy")).astype(bool)
+            if self._arg("TSDF_invert_mask", False):
+                m = ~m
+            if self._arg("TSDF_erode_mask", True):
+                ck = int(self._arg("TSDF_closing_kernel_size", 10))
+                ek = int(self._arg("TSDF_erosion_kernel_size", 10))
+                closing = cv2.morphologyEx(m.astype(np.uint8), cv2.MORPH_CLOSE, np.ones((ck, ck), np.uint8))
+                m = cv2.erode(closing, np.ones((ek, ek), np.uint8), iterations=1) > 0.5
+            obj_mask = m
+        if self._arg("TSDF_use_occlusion_mask", True) and frame is None:
+            occ_path = os.path.join(out_dir, f"out_{self.model_name}", "occlusion_mask.npy")
+            if os.path.exists(occ_path):
+                occ_mask = np.load(occ_path).astype(bool)
+        return rgb, depth, obj_mask, occ_mask
+
+    # -- north_star alias: one view
+    def integrate(self, depth, rgb, left_camera, *, final_T=None, mask=None):
+        """Fuse one view.  `depth`: float [H,W] metric depth (host or device); when `final_T` is
+        given `depth` is the rasterizer's sum(z*alpha*T) and is normalised by alpha on the GPU."""
+        if self.volume is None:
+            self.volume = self._make_volume()
+        scale = float(self._arg("TSDF_scale", 1.0))
+        baseline = float(self.renderer.baseline)
+        w, h = int(left_camera["width"]), int(left_camera["height"])
+        extrinsic = np.array(left_camera["extrinsic"], dtype=np.float64).copy()
+        extrinsic[:3, 3] /= scale  # tsdf_utils.py:85-86
+        prepared = self.volume.prepare_depth(
+            depth, w, h, final_T=final_T, mask=mask,
+            min_depth=float(self._arg("TSDF_min_depth_baselines", 4)) * baseline,  # :83
+            depth_scale=scale, depth_trunc=baseline * float(self._arg("TSDF_max_depth_baselines", 20)) / scale)  # :92
+        self.volume.integrate(prepared, rgb, w, h, left_camera["fx"], left_camera["fy"], left_camera["cx"],
+                              left_camera["cy"], np.linalg.inv(extrinsic))  # :106-107
+
+    def run(self, visualize=False, views: Optional[Sequence[int]] = None):
+        """tsdf_utils.py:39-110.  `views` restricts the loop (used for view sharding across ranks)."""
+        self.volume = self._make_volume()
+        for camera_number, left_camera in enumerate(self.renderer.left_cameras):
+            if views is not None and camera_number not in views:
+                continue
+            if not self._selected(camera_number):
+                continue
+            rgb, depth, obj_mask, occ_mask = self._load_view(camera_number)
+            mask = None
+            if obj_mask is not None or occ_mask is not None:
+                mask = np.ones(np.asarray(obj_mask if obj_mask is not None else occ_mask).shape, dtype=bool)
+                if obj_mask is not None:
+                    mask &= obj_mask
+                if occ_mask is not None:
+                    mask &= occ_mask
+                mask = mask.astype(np.uint8)
+            self.integrate(depth, rgb, left_camera, mask=mask)
+        self.mesh = None
+        return self.volume
+
+    def extract_mesh(self):
+        """`volume.extract_triangle_mesh()` + scale + vertex normals (tsdf_utils.py:108-110)."""
+        from .mesh import extract_triangle_mesh
+
+        if self.volume is None:
+            raise RuntimeError("TSDF.extract_mesh() called before run()/integrate()")
+        self.mesh = extract_triangle_mesh(self.volume)
+        self.mesh.scale(float(self._arg("TSDF_scale", 1.0)), (0, 0, 0))
+        self.mesh.compute_vertex_normals()
+        return self.mesh
+
+    def save_mesh(self):
+        """tsdf_utils.py:112-120"""
+        if self.mesh is None:
+            self.extract_mesh()
+        path = os.path.join(self.renderer.output_dir_root, f"{self.out_name}_mesh.ply")
+        self.mesh.write_ply(path)
+        print("SAVED MESH")
+        return path
+
+    def clean_mesh(self):
+        """tsdf_utils.py:122-142 (the reference overwrites this method with the cleaned mesh on first
+        call; here the result is kept in `.cleaned_mesh` and returned)."""
+        if self.mesh is None:
+            self.extract_mesh()
+        thres = float(self._arg("TSDF_cleaning_threshold", 100000)) / float(self._arg("TSDF_scale", 1.0))
+        self.cleaned_mesh = self.mesh.remove_small_clusters(thres)
+        path = os.path.join(self.renderer.output_dir_root, f"{self.out_name}_cleaned_mesh.ply")
+        self.cleaned_mesh.write_ply(path)
+        print("SAVED CLEANED MESH")
+        return path

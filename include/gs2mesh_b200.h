@@ -1,0 +1,193 @@
+/*
+ * gs2mesh_b200 -- C ABI of the B200-native gs2mesh hot path.
+ *
+ * Plain C boundary (pointers + sizes, no torch / Open3D types) for the two halves of
+ * the path BASELINE.json's north_star names:
+ *
+ *   1. forward Gaussian-splat rasterizer  -- replaces the reference's pybind seam
+ *        `_C.rasterize_gaussians(...)`            DGR/ext.cpp:16, DGR/rasterize_points.h:19-39
+ *        -> CudaRasterizer::Rasterizer::forward   DGR/cuda_rasterizer/rasterizer.h:30-53
+ *        `_C.mark_visible(...)`                   DGR/ext.cpp:18, rasterizer.h:23-28
+ *   2. TSDF voxel integration -- replaces the Open3D (0.17.0) calls the reference makes in
+ *        gs2mesh_utils/tsdf_utils.py:53-56  ScalableTSDFVolume(voxel_length, sdf_trunc, RGB8)
+ *        gs2mesh_utils/tsdf_utils.py:88-93  RGBDImage.create_from_color_and_depth(...)
+ *        gs2mesh_utils/tsdf_utils.py:107    volume.integrate(rgbd, intrinsic, extrinsic)
+ *        gs2mesh_utils/tsdf_utils.py:108    volume.extract_triangle_mesh()
+ *   (DGR = third_party/gaussian-splatting/submodules/diff-gaussian-rasterization)
+ *
+ * Conventions
+ *   - every pointer named *_dev / documented "device" is a CUDA device pointer owned by the
+ *     CALLER; the library never allocates result or scratch memory (no hidden cudaMalloc on
+ *     the hot path) -- query the size, allocate, pass it in;
+ *   - every entry point takes the CUDA stream to enqueue on (`void*` = cudaStream_t) and never
+ *     synchronises the device unless its comment says so;
+ *   - return value 0 = success, anything else is a GSB_ERR_* code; gsb_last_error() gives text;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     GSB_ERR_CUDA.
+ */
+#ifndef GS2MESH_B200_H_
+#define GS2MESH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_VERSION 100
+
+enum {
+  GSB_OK = 0,
+  GSB_ERR_INVALID = 1,    /* bad argument combination (mirrors the Python Exceptions in
+                             DGR/diff_gaussian_rasterization/__init__.py:191-195 and
+                             AT_ERROR in rasterize_points.cu:57-59)                        */
+  GSB_ERR_WORKSPACE = 2,  /* caller workspace too small; see gsb_raster_required_instances */
+  GSB_ERR_CUDA = 3,       /* CUDA runtime / launch error                                  */
+  GSB_ERR_ALIGNMENT = 4   /* a device pointer is not 16-byte aligned                       */
+};
+
+const char* gsb_last_error(void);
+int gsb_version(void);
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+uint64_t gsb_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Rasterizer
+ * ------------------------------------------------------------------------------------------ */
+
+/* flags for GsbRasterArgs.flags */
+#define GSB_RASTER_EXACT_TILE_CULL 1u /* drop (Gaussian,tile) pairs that provably contribute to no
+                                         pixel of the tile; image is bit-identical, num_rendered
+                                         shrinks.  Off = reference rectangle binning
+                                         (rasterizer_impl.cu:88-107).                          */
+#define GSB_RASTER_NO_TMA 2u          /* stage parameters with plain loads (debug / A-B only)  */
+#define GSB_RASTER_DEBUG_SYNC 4u      /* synchronise + check after every stage, like debug=True
+                                         (auxiliary.h:166-173)                                 */
+#define GSB_RASTER_CUB_SORT 8u        /* use cub::DeviceRadixSort instead of the in-library sort
+                                         (validation only)                                     */
+
+/* One forward rasterization.  Field-for-field the argument list of
+ * CudaRasterizer::Rasterizer::forward (rasterizer.h:30-53) / RasterizeGaussiansCUDA
+ * (rasterize_points.h:19-39); tensors are raw device pointers in the reference layouts. */
+typedef struct GsbRasterArgs {
+  int32_t P;              /* number of Gaussians                                   */
+  int32_t sh_degree;      /* active SH degree D (0..3)                             */
+  int32_t sh_coeffs;      /* M = coefficients stored per Gaussian (0 if shs==NULL) */
+  int32_t width, height;
+  const float* background;     /* device [3]                                        */
+  const float* means3D;        /* device [P,3]                                      */
+  const float* shs;            /* device [P,M,3] or NULL                            */
+  const float* colors_precomp; /* device [P,3] or NULL   (exactly one of shs/colors) */
+  const float* opacities;      /* device [P] (post-sigmoid)                         */
+  const float* scales;         /* device [P,3] or NULL                              */
+  const float* rotations;      /* device [P,4] (w first, normalised) or NULL        */
+  const float* cov3D_precomp;  /* device [P,6] or NULL (exactly one of scales+rotations/cov3D) */
+  float scale_modifier;
+  const float* viewmatrix;     /* device [16]: world_view_transform as stored by cameras.py:54 */
+  const float* projmatrix;     /* device [16]: full_proj_transform (cameras.py:56)   */
+  const float* cam_pos;        /* device [3]                                        */
+  float tan_fovx, tan_fovy;
+  int32_t prefiltered;         /* accepted for signature parity; culled points never trap */
+  uint32_t flags;              /* GSB_RASTER_*                                      */
+  /* outputs (device).  out_color is required, the rest may be NULL. */
+  float* out_color;            /* [3,H,W]                                           */
+  float* out_depth;            /* [H,W]  NEW: sum_i z_i alpha_i T_i (no reference counterpart) */
+  float* out_final_T;          /* [H,W]  final transmittance (ImageState.accum_alpha) */
+  int32_t* radii;              /* [P]                                               */
+  /* num_rendered: written asynchronously on `stream` (device or pinned-mapped host memory);
+     [0] = instances actually binned, [1] = reference-equivalent count (sum of tile rectangles,
+     what rasterize_points.cu:114 returns).  May be NULL.                                 */
+  int64_t* num_rendered;
+  /* caller-owned scratch */
+  void* workspace;             /* device, >= gsb_raster_workspace_bytes(...)        */
+  size_t workspace_bytes;
+  int64_t max_instances;       /* binning capacity the workspace was sized for      */
+} GsbRasterArgs;
+
+/* Scratch size for P Gaussians, a width x height frame and room for `max_instances`
+ * (Gaussian,tile) pairs.  Replaces the three resizable byte tensors geomBuffer /
+ * binningBuffer / imgBuffer of rasterize_points.cu:68-75. */
+size_t gsb_raster_workspace_bytes(int32_t P, int32_t width, int32_t height, int64_t max_instances);
+
+/* Enqueue one forward pass.  If the frame needs more than args->max_instances pairs the call
+ * returns GSB_ERR_WORKSPACE and gsb_raster_required_instances() tells how many are needed
+ * (outputs are then undefined).  This entry point performs ONE small device->host read of the
+ * instance count (as the reference does, rasterizer_impl.cu:281) unless the in-library
+ * sync-free pipeline is selected at build time. */
+int gsb_raster_forward(const GsbRasterArgs* args, void* stream);
+int64_t gsb_raster_required_instances(void);
+
+/* Frustum test only (rasterizer.h:23-28 markVisible): present[i] = z_view > 0.2. */
+int gsb_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                            uint8_t* present, void* stream);
+
+/* Post step of Renderer.render_image_pair (renderer_utils.py:389-390) on the GPU:
+ * CHW float [0,1] -> HWC uint8 with cv2's saturate_cast<uchar>(x*255) (round-half-even). */
+int gsb_image_to_u8(const float* chw, int32_t width, int32_t height, uint8_t* hwc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * TSDF volume
+ * ------------------------------------------------------------------------------------------ */
+
+#define GSB_BRICK 16               /* Open3D volume_unit_resolution default               */
+#define GSB_BRICK_VOXELS 4096
+
+/* A bounded window of Open3D's ScalableTSDFVolume lattice: bricks (= Open3D "volume units",
+ * 16^3 voxels, unit_length = 16*voxel_length) with integer indices brick_origin + [0, brick_count)
+ * per axis.  Voxel (bx,by,bz | x,y,z) has its centre at
+ *     (brick_index * 16 + xyz + 0.5) * voxel_length
+ * i.e. exactly on Open3D's lattice.  Storage ("brick layout"): bricks row-major over
+ * (bx,by,bz); inside a brick voxels at x*256 + y*16 + z (UniformTSDFVolume::IndexOf).
+ * All arrays are caller-allocated device memory, zero-initialised by the caller. */
+typedef struct GsbVolumeDesc {
+  int32_t brick_origin[3];
+  int32_t brick_count[3];
+  double voxel_length;
+  double sdf_trunc;
+  float* tsdf_weight;     /* device [n_bricks*4096*2]  (tsdf, weight) interleaved            */
+  float* color;           /* device [n_bricks*4096*4]  (r,g,b,unused) running mean, or NULL  */
+  uint32_t* brick_stamp;  /* device [n_bricks]   last frame id that touched the brick        */
+  uint32_t* brick_list;   /* device [n_bricks]   scratch: bricks touched by the current frame */
+  uint32_t* counters;     /* device [8]          scratch counters                            */
+} GsbVolumeDesc;
+
+typedef struct GsbVolume GsbVolume; /* opaque; owns no device memory */
+
+GsbVolume* gsb_tsdf_create(const GsbVolumeDesc* desc);
+void gsb_tsdf_destroy(GsbVolume* vol);
+
+/* Per-view depth preparation, fused T0/T0b (tsdf_utils.py:78-93 + Open3D ConvertDepthToFloatImage):
+ *   d = depth_in;                       (if alpha != NULL: d = alpha > alpha_min ? d / alpha : 0
+ *                                        -- expected depth from the rasterizer's sum z*alpha*T)
+ *   if (mask != NULL) d *= mask;        (object / occlusion masks, uint8 0/1)
+ *   if (d < min_depth) d = 0;           (tsdf_utils.py:83)
+ *   d /= (float)depth_scale; if ((double)d >= depth_trunc) d = 0;   (T0b)
+ * final_T is the rasterizer's transmittance (alpha = 1 - final_T) or NULL. */
+int gsb_tsdf_prepare_depth(const float* depth_in, const float* final_T, const uint8_t* mask, int32_t width, int32_t height,
+                           float alpha_min, float min_depth, double depth_scale, double depth_trunc, float* depth_out,
+                           void* stream);
+
+/* volume.integrate(rgbd, intrinsic, extrinsic): depth = prepared float depth [H,W] (device),
+ * rgb = uint8 [H,W,3] (device) or NULL, extrinsic_w2c = row-major double[16] on the HOST
+ * (what tsdf_utils.py:107 passes: inv(left_camera['extrinsic'])). */
+int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, int32_t width, int32_t height, double fx,
+                       double fy, double cx, double cy, const double* extrinsic_w2c, void* stream);
+
+/* Cross-rank merge support (view-sharded multi-GPU): convert (mean, weight) -> (sum, weight)
+ * before an NCCL SUM reduce of tsdf_weight (and color), and back afterwards. */
+int gsb_tsdf_to_sums(GsbVolume* vol, void* stream);
+int gsb_tsdf_from_sums(GsbVolume* vol, void* stream);
+
+/* Brick layout -> dense x*N^2... linear grids (dims = brick_count*16), for consumers that want
+ * Open3D UniformTSDFVolume indexing.  tsdf / weight: device float [nx*ny*nz]. */
+int gsb_tsdf_export_dense(const GsbVolume* vol, float* tsdf, float* weight, void* stream);
+
+/* Statistics of the last integrate call, read back asynchronously into `out` (device or pinned
+ * host, uint32[4]): [0] bricks touched, [1] bricks outside the window, [2] frame id. */
+int gsb_tsdf_last_stats(const GsbVolume* vol, uint32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS2MESH_B200_H_ */
