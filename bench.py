@@ -1,0 +1,484 @@
+#!/usr/bin/env python
+"""bench.py -- stereo pairs rendered + TSDF-fused per second (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C1] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One STEP = one stereo pair of the synthetic scene: render the left and the right view
+(forward rasterizer x2, float->u8 frames), then fuse the left view's depth + colour into the
+TSDF volume.  With N > 1 GPUs the N*K views are sharded round-robin over the ranks (weak scaling:
+K pairs per rank) and the timed region ends with the single NCCL sum-reduce of the volume.
+
+`value`  : pairs/s with everything resident in HBM (Gaussians, camera table, volume).
+`e2e`    : same metric through the public classes with HOST buffers: Renderer.render_image_pair()
+           copies both uint8 frames and the left depth to pinned host memory, TSDF.integrate() takes
+           host depth + host rgb and uploads them -- every step.
+`--impl reference`: the reference's own implementation of the path on this box: the UNMODIFIED
+           reference rasterizer built for sm_100a (oracle/_ref) called the way
+           renderer_utils.py:378-390 calls it (float frame D2H, x255 -> uint8 on the host) and the
+           Open3D-0.17-equivalent CPU TSDF (oracle port, all host threads).  PNG encoding and the
+           stereo network are left out (both would only slow the reference arm down).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "stereo_pairs_per_sec_rendered_and_tsdf_fused"
+UNIT = "stereo-pairs/s"
+
+
+class BenchArgs:
+    """Reference defaults of the flags the hot path reads (argument_utils.py:29-42,74-90)."""
+
+    GS_white_background = False
+    TSDF_scale = 1.0
+    TSDF_sdf_trunc = 0.04
+    TSDF_dilate = 1
+    TSDF_valid = None
+    TSDF_skip = None
+    TSDF_use_mask = False
+    TSDF_use_occlusion_mask = False
+
+    def __init__(self, cfg):
+        self.TSDF_voxel = 2.0 * 512 / cfg["tsdf_res"]  # voxel_length = TSDF_voxel/512 = 2/tsdf_res
+        self.TSDF_min_depth_baselines = cfg["min_db"]
+        self.TSDF_max_depth_baselines = cfg["max_db"]
+        self.TSDF_sdf_trunc = max(0.04, 3 * 2.0 / cfg["tsdf_res"])
+
+
+def measured_peak_gbs():
+    for p in (os.path.join(ROOT, "MEASURED_PEAKS.json"), "/root/repo/MEASURED_PEAKS.json"):
+        try:
+            with open(p) as f:
+                v = json.load(f).get("hbm_gbs")
+            if v:
+                return float(v), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="gsb_clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for k, name in enumerate(names):
+                    if c[5 + k].lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def setup_dist(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    if n_gpus != world:
+        if rank == 0:
+            print(f"[bench] --gpus {n_gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    return rank, local, world
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def build_scene(cfg, total_views, seed=1):
+    from gs2mesh_b200 import scene
+
+    cloud = scene.make_gaussians(cfg["num_points"], seed=seed)
+    rigs, baseline = scene.make_stereo_cameras(total_views, cfg["width"], cfg["height"], layout=cfg["layout"],
+                                               principal_point=cfg.get("principal_point"))
+    return cloud, rigs, baseline
+
+
+def workload_name(name, cfg, total_views):
+    return (f"{name}: synthetic {cfg['num_points']}-Gaussian {'360' if cfg['layout'] == 'ring' else 'frontal-cap'} scene, "
+            f"{total_views} stereo pairs @{cfg['width']}x{cfg['height']}, {cfg['tsdf_res']}^3 TSDF lattice (voxel 2/{cfg['tsdf_res']})")
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args, cfg, rank, local, world):
+    from gs2mesh_b200 import _lib
+    from gs2mesh_b200.renderer import Renderer
+    from gs2mesh_b200.tsdf import TSDF, shard_views
+
+    K, Wm = args.steps, args.warmup
+    total_views = K * world
+    cloud, rigs, baseline = build_scene(cfg, total_views)
+    bargs = BenchArgs(cfg)
+    dev = f"cuda:{local}"
+    renderer = Renderer.from_scene(rigs, baseline, cloud, output_dir_root=None, args=bargs, device=dev)
+    renderer.prepare_renderer()
+    stage = TSDF(renderer, None, bargs, "bench", window_resolution=cfg["tsdf_res"], device=dev)
+    stage.volume = stage._make_volume()
+    vol = stage.volume
+    mine = shard_views(total_views, rank, world)
+    assert len(mine) == K
+    W, H = cfg["width"], cfg["height"]
+
+    def step(i):
+        out = renderer.render_image_pair(i, to_host=False)
+        stage.integrate(out["depth"], out["left_u8"], rigs[i]["left"], final_T=out["final_T"])
+
+    # ---- calibration (untimed): per-view workload statistics for the roofline formulas
+    stats = dict(Pv=[], R=[], R_ref=[], bricks=[], V_upd=[])
+    for i in mine[:3]:
+        o = renderer.render_view(i, 0, want_depth=True, want_counts=True)
+        rr = renderer.render_view(i, 0, want_counts=True)
+        cnt = o["counts"].cpu().numpy()
+        stats["R"].append(int(cnt[0]))
+        stats["R_ref"].append(int(cnt[1]))
+        from gs2mesh_b200 import rasterizer as rast
+
+        rad = rast.rasterize_forward(means3D=renderer.means3D, opacities=renderer.opacity, viewmatrix=renderer._camera_table[i, 0, 0:16],
+                                     projmatrix=renderer._camera_table[i, 0, 16:32], campos=renderer._camera_table[i, 0, 32:35],
+                                     bg=renderer.background, width=W, height=H, tan_fovx=renderer._views[i][0].tan_fovx,
+                                     tan_fovy=renderer._views[i][0].tan_fovy, shs=renderer.shs, scales=renderer.scales,
+                                     rotations=renderer.rotations, sh_degree=renderer.sh_degree, want_depth=False, want_final_T=False)["radii"]
+        stats["Pv"].append(int((rad > 0).sum().item()))
+        del rad, rr
+        w_before = float(vol.tsdf_weight.view(-1, 2)[:, 1].sum(dtype=torch.float64).item())
+        step(i)
+        stats["bricks"].append(vol.last_stats()[0])
+        stats["V_upd"].append(float(vol.tsdf_weight.view(-1, 2)[:, 1].sum(dtype=torch.float64).item()) - w_before)
+    outside = vol.last_stats()[1]
+    vol.reset()
+    mean = {k: float(np.mean(v)) for k, v in stats.items()}
+
+    # ---- warm-up
+    for i in (mine * ((Wm // max(len(mine), 1)) + 1))[:Wm]:
+        step(i)
+    vol.reset()
+    barrier(world)
+
+    # ---- timed region: K steps (+ the one volume reduce when sharded)
+    sampler = ClockSampler(local)
+    _lib.profile_collect()
+    _lib.profile_enable(True)
+    launches0 = _lib.lib().gsb_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier(world)
+    ev0.record()
+    for i in mine:
+        step(i)
+    if world > 1:
+        vol.reduce_across_ranks(dst=0)
+    ev1.record()
+    barrier(world)
+    clocks = sampler.stop()
+    _lib.profile_enable(False)
+    launches = int(_lib.lib().gsb_kernel_launch_count() - launches0)
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1), world)
+    prof = _lib.profile_collect()
+    value = world * K / (elapsed_ms / 1e3)
+
+    # ---- e2e: public classes with host buffers, H2D + D2H every step
+    vol.reset()
+    host_depth = torch.empty(H, W, dtype=torch.float32).pin_memory()
+    dev_depth = torch.empty(H, W, dtype=torch.float32, device=dev)
+    K_e2e = K
+    barrier(world)
+    t0 = time.perf_counter()
+    for i in mine[:K_e2e]:
+        out = renderer.render_image_pair(i, to_host=True)  # both uint8 frames -> pinned host
+        vol.prepare_depth(out["depth"], W, H, final_T=out["final_T"], out=dev_depth)  # expected depth of the left view
+        host_depth.copy_(dev_depth, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        # what a host-side stereo stage would hand back: float depth + the uint8 left frame, both on the host
+        stage.integrate(host_depth, out["host_left_u8"], rigs[i]["left"])
+    if world > 1:
+        vol.reduce_across_ranks(dst=0)
+    barrier(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    e2e_value = world * K_e2e / e2e_s
+    h2d = 4 * W * H + 3 * W * H + 16 * 8
+    d2h = 2 * 3 * W * H + 4 * W * H
+
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel
+    peak, peak_kind = measured_peak_gbs()
+    P = cfg["num_points"]
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    bytes_per_launch = {  # algorithmic bytes per launch, SURVEY.md 8(d) / DESIGN.md
+        "preprocess": 12 * P + 224 * mean["Pv"] + 8 * P + 40 * mean["Pv"],
+        "scan": 8 * P,
+        "emit_instances": 12 * mean["R"] + 36 * mean["Pv"],
+        "radix_sort": 24 * mean["R"],
+        "tile_ranges": 8 * mean["R"] + 8 * tiles,
+        "render": 40 * mean["R"] + 16 * W * H,
+        "to_u8": 15 * W * H,
+        "prepare_depth": 12 * W * H,
+        "mark_bricks": 4 * W * H / 16,
+        "integrate": 8 * 4096 * mean["bricks"] + 8 * mean["V_upd"] + 32 * mean["V_upd"] + 7 * W * H,
+    }
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+    kernels = {}
+    for name, (ms, n) in prof.items():
+        if n == 0:
+            continue
+        avg = ms / n
+        gbs = bytes_per_launch[name] / (avg * 1e-3) / 1e9
+        kernels[name] = {"avg_ms": round(avg, 5), "launches": n, "share": round(ms / elapsed_ms, 4), "achieved_gbs": round(gbs, 1),
+                         "frac": round(gbs / peak, 4)}
+    dom = max(kernels, key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "peak_kind": f"of {peak_kind}",
+                "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic.get(dom),
+                "algorithmic_bytes_per_launch": int(bytes_per_launch[dom]), "avg_ms": kernels[dom]["avg_ms"]}
+
+    # ---- CPU baseline: Open3D-0.17-equivalent TSDF (oracle port) on a bounded sample, all host threads
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_tsdf_baseline(renderer, vol, stage, rigs, mine, cfg, bargs, baseline, budget_s=args.cpu_budget)
+
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": round(elapsed_ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, cfg, total_views), "pairs_per_rank": K, "sharding": f"views round-robin x{world}",
+                   "l2": "inputs larger than L2: 236 MB of Gaussian parameters re-read per view + brick volume window per view",
+                   "tsdf_colour": "fused (float4 running mean)", "exact_tile_cull": True,
+                   "per_view": {k: round(v, 1) for k, v in mean.items()}, "points_outside_tsdf_window": int(outside)},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": K_e2e},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu_baseline,
+    }
+    return line
+
+
+def cpu_tsdf_baseline(renderer, vol, stage, rigs, mine, cfg, bargs, baseline, budget_s=20.0):
+    """The reference's CPU-path TSDF (Open3D ScalableTSDFVolume restated, oracle/tsdf_oracle.cpp) on the
+    first few depth frames of the same workload; the oracle is only timed here, never used as a result."""
+    from oracle import oracle as orc
+
+    W, H = cfg["width"], cfg["height"]
+    cores = os.cpu_count() or 1
+    frames = []
+    for i in mine[:8]:
+        out = renderer.render_image_pair(i, to_host=True)
+        d = vol.prepare_depth(out["depth"], W, H, final_T=out["final_T"], min_depth=bargs.TSDF_min_depth_baselines * baseline)
+        frames.append((d.cpu().numpy(), out["host_left_u8"].numpy().copy(), rigs[i]["left"]))
+    ovol = orc.OracleTSDFVolume(vol.voxel_length, vol.sdf_trunc, with_color=True)
+    n, t0 = 0, time.perf_counter()
+    for d, rgb, cam_ in frames:
+        ovol.integrate(d, rgb, W, H, cam_["fx"], cam_["fy"], cam_["cx"], cam_["cy"], np.linalg.inv(cam_["extrinsic"]),
+                       depth_scale=1.0, depth_trunc=baseline * bargs.TSDF_max_depth_baselines, threads=cores)
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": round(n / dt, 4), "unit": "stereo-pairs/s (TSDF fuse only, CPU)", "cores": cores, "kind": "port",
+            "sample": f"first {n} left depth frames of the workload, Open3D-0.17-equivalent ScalableTSDFVolume restatement, {cores} OpenMP threads"}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, cfg, rank, local, world):
+    if rank != 0:
+        return None
+    from oracle import oracle as orc
+
+    K, Wm = args.steps, args.warmup
+    total_views = K * world
+    cloud, rigs, baseline = build_scene(cfg, total_views)
+    bargs = BenchArgs(cfg)
+    W, H = cfg["width"], cfg["height"]
+    cores = os.cpu_count() or 1
+    dev = torch.device("cuda", local)
+    have_ref = orc.ref_available()
+    if not have_ref:
+        return {"impl": "reference", "unavailable": "oracle/_ref/libref_dgr.so (reference rasterizer built for sm_100a) is missing"}
+
+    from gs2mesh_b200 import camera as cam
+
+    up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    g = dict(xyz=up(cloud.xyz), sh=up(cloud.features), op=up(cloud.opacity).reshape(-1), sc=up(cloud.scaling), ro=up(cloud.rotation))
+    bg = torch.zeros(3, device=dev)
+
+    # Setup only (untimed): depth frames standing in for the stereo network's output.
+    from gs2mesh_b200.renderer import Renderer
+    from gs2mesh_b200.tsdf import TSDFVolume
+
+    n_sample = min(K + Wm, total_views)
+    helper = Renderer.from_scene(rigs, baseline, cloud, output_dir_root=None, args=bargs, device=str(dev))
+    helper.prepare_renderer()
+    hv = TSDFVolume(2.0 / cfg["tsdf_res"], bargs.TSDF_sdf_trunc, (0, 0, 0), (1, 1, 1), with_color=False, device=dev)
+    depth_frames = {}
+    for i in range(n_sample):
+        out = helper.render_image_pair(i, to_host=False)
+        depth_frames[i] = hv.prepare_depth(out["depth"], W, H, final_T=out["final_T"],
+                                           min_depth=bargs.TSDF_min_depth_baselines * baseline).cpu().numpy()
+    del helper, hv
+    torch.cuda.empty_cache()
+
+    ovol = orc.OracleTSDFVolume(2.0 / cfg["tsdf_res"], bargs.TSDF_sdf_trunc, with_color=True)
+
+    def step(i):
+        frames = []
+        for side in ("left", "right"):  # renderer_utils.py:378-390
+            c = rigs[i][side]
+            vt = cam.view_transforms_from_camera(c)
+            view, proj, pos = up(vt.world_view), up(vt.full_proj), up(vt.cam_center)  # cameras.py:54-57 uploads per view
+            res = orc.ref_forward_torch(g["xyz"], g["op"], view, proj, pos, W, H, vt.tan_fovx, vt.tan_fovy, bg, shs=g["sh"],
+                                        scales=g["sc"], rotations=g["ro"], sh_degree=3)
+            rendering = (res["color"].permute(1, 2, 0) * 255).cpu().numpy()  # :389
+            frames.append(np.clip(np.rint(rendering), 0, 255).astype(np.uint8))  # imwrite's float->u8
+        c = rigs[i]["left"]
+        ovol.integrate(depth_frames[i], frames[0], W, H, c["fx"], c["fy"], c["cx"], c["cy"], np.linalg.inv(c["extrinsic"]),
+                       depth_scale=1.0, depth_trunc=baseline * bargs.TSDF_max_depth_baselines, threads=cores)
+
+    order = list(range(n_sample))
+    for i in order[:Wm]:
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    done = 0
+    for i in order[Wm:Wm + K] if n_sample >= Wm + K else order[:K]:
+        step(i)
+        done += 1
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    value = done / dt
+    return {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": done, "warmup": Wm,
+        "ms_per_step": round(1e3 * dt / max(done, 1), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, cfg, total_views),
+                   "note": "reference rasterizer (oracle/_ref, sm_100a build of the unmodified sources) x2 per pair as called by "
+                           "renderer_utils.py:378-390 + Open3D-0.17-equivalent CPU TSDF; rank 0 only; PNG encode and DLNR excluded"},
+        "clocks": clocks,
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "reference+port",
+                         "sample": f"{done} stereo pairs: GPU reference rasterizer + CPU TSDF port on {cores} threads"},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="C1")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    from gs2mesh_b200 import scene
+
+    cfg = scene.CONFIGS[args.config]
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gs2mesh_b200 has no CPU fallback")
+    rank, local, world = setup_dist(args.gpus)
+    import __graft_entry__ as ge
+
+    if rank == 0:
+        ge.build()
+    barrier(world)
+    if args.impl == "reference":
+        args.steps = min(args.steps, 200)  # bounded: ~0.25 s of CPU TSDF per step at C1
+        line = run_reference(args, cfg, rank, local, world)
+    else:
+        line = run_ours(args, cfg, rank, local, world)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,10 @@ SIGNATURES = {
     "gsb_last_error": (C.c_char_p, []),
     "gsb_version": (C.c_int, []),
     "gsb_kernel_launch_count": (C.c_uint64, []),
+    "gsb_profile_num_stages": (C.c_int, []),
+    "gsb_profile_stage_name": (C.c_char_p, [C.c_int]),
+    "gsb_profile_enable": (C.c_int, [C.c_int]),
+    "gsb_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "gsb_raster_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
     "gsb_raster_forward": (C.c_int, [C.POINTER(GsbRasterArgs), _vp]),
     "gsb_raster_required_instances": (C.c_int64, []),
@@ -96,3 +100,17 @@ def check(code: int) -> None:
 def ptr(t):
     """torch tensor (or None) -> c_void_p of its storage start."""
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().gsb_profile_enable(1 if on else 0))
+
+
+def profile_collect():
+    """{stage name: (total ms, samples)} since the last collect; synchronises the device."""
+    L = lib()
+    n = L.gsb_profile_num_stages()
+    ms = (C.c_double * n)()
+    cnt = (C.c_uint64 * n)()
+    check(L.gsb_profile_collect(ms, cnt, n))
+    return {L.gsb_profile_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}

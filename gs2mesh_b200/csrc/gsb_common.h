@@ -7,6 +7,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "gs2mesh_b200.h"
 
@@ -47,6 +49,65 @@ inline int check_launch(const char* what, cudaStream_t s, bool sync) {
   }
   return GSB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Optional per-stage device timing (bench.py's roofline numbers): CUDA events recorded on the
+// launching stream around each stage when enabled; read back with gsb_profile_collect().
+// ---------------------------------------------------------------------------------------------
+enum Stage {
+  kStPreprocess = 0,
+  kStScan,
+  kStEmit,
+  kStSort,
+  kStRanges,
+  kStRender,
+  kStToU8,
+  kStDepthPrep,
+  kStMarkBricks,
+  kStIntegrate,
+  kStCount
+};
+
+struct Profiler {
+  std::atomic<bool> enabled{false};
+  struct Rec {
+    int stage;
+    cudaEvent_t a, b;
+  };
+  std::mutex mu;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+extern Profiler g_prof;
+
+struct StageTimer {
+  cudaStream_t s;
+  int stage;
+  cudaEvent_t a = nullptr, b = nullptr;
+  StageTimer(int stage_, cudaStream_t s_) : s(s_), stage(stage_) {
+    if (!g_prof.enabled.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    a = g_prof.get();
+    b = g_prof.get();
+    cudaEventRecord(a, s);
+  }
+  ~StageTimer() {
+    if (!a) return;
+    cudaEventRecord(b, s);
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.recs.push_back({stage, a, b});
+  }
+};
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -30,6 +30,9 @@ namespace gsb {
 
 thread_local char g_error[512] = {0};
 std::atomic<uint64_t> g_launches{0};
+Profiler g_prof;
+static const char* kStageNames[kStCount] = {"preprocess", "scan", "emit_instances", "radix_sort", "tile_ranges",
+                                            "render",     "to_u8", "prepare_depth", "mark_bricks", "integrate"};
 static thread_local int64_t g_required_instances = 0;
 
 namespace {
@@ -50,18 +53,23 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// Bounded wait: a bulk copy that never lands (bad pointer / size) traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 22)) __trap();
 }
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -641,6 +649,33 @@ int gsb_version(void) { return GSB_VERSION; }
 uint64_t gsb_kernel_launch_count(void) { return g_launches.load(); }
 int64_t gsb_raster_required_instances(void) { return g_required_instances; }
 
+int gsb_profile_num_stages(void) { return kStCount; }
+const char* gsb_profile_stage_name(int stage) { return stage >= 0 && stage < kStCount ? kStageNames[stage] : ""; }
+int gsb_profile_enable(int on) {
+  g_prof.enabled.store(on != 0);
+  return GSB_OK;
+}
+int gsb_profile_collect(double* total_ms, uint64_t* samples, int n_stages) {
+  if (!total_ms || !samples || n_stages < kStCount) return fail(GSB_ERR_INVALID, "profile_collect: need %d stages", (int)kStCount);
+  GSB_CUDA_OK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  for (int i = 0; i < n_stages; ++i) {
+    total_ms[i] = 0.0;
+    samples[i] = 0;
+  }
+  for (const Profiler::Rec& r : g_prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      total_ms[r.stage] += ms;
+      samples[r.stage] += 1;
+    }
+    g_prof.pool.push_back(r.a);
+    g_prof.pool.push_back(r.b);
+  }
+  g_prof.recs.clear();
+  return GSB_OK;
+}
+
 size_t gsb_raster_workspace_bytes(int32_t P, int32_t width, int32_t height, int64_t max_instances) {
   return carve(nullptr, P, width, height, max_instances).total;
 }
@@ -717,11 +752,17 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
 
   GSB_CUDA_OK(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream));
   const int pre_blocks = (P + kPreThreads - 1) / kPreThreads;
-  preprocess_kernel<<<pre_blocks, kPreThreads, 0, stream>>>(pp);
+  {
+    StageTimer tm(kStPreprocess, stream);
+    preprocess_kernel<<<pre_blocks, kPreThreads, 0, stream>>>(pp);
+  }
   count_launch();
   if ((rc = check_launch("preprocess_kernel", stream, dbg))) return rc;
 
-  GSB_CUDA_OK(cub::DeviceScan::InclusiveSum(ws.scan_temp, ws.scan_temp_bytes, ws.tiles, ws.offsets, P, stream));
+  {
+    StageTimer tm(kStScan, stream);
+    GSB_CUDA_OK(cub::DeviceScan::InclusiveSum(ws.scan_temp, ws.scan_temp_bytes, ws.tiles, ws.offsets, P, stream));
+  }
   if (a->num_rendered) {
     write_counts_kernel<<<1, 1, 0, stream>>>(ws.offsets, P, ws.counters, a->num_rendered);
     count_launch();
@@ -736,23 +777,35 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   if (R > cap) return fail(GSB_ERR_WORKSPACE, "frame needs %lld instances, workspace sized for %lld", (long long)R, (long long)cap);
 
   if (R > 0) {
-    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ws.recA, ws.recB, ws.tiles, ws.offsets, pp.radii, gx, gy,
-                                                               a->flags, cap, ws.keys_in, ws.vals_in);
+    {
+      StageTimer tm(kStEmit, stream);
+      emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ws.recA, ws.recB, ws.tiles, ws.offsets, pp.radii, gx, gy,
+                                                                 a->flags, cap, ws.keys_in, ws.vals_in);
+    }
     count_launch();
     if ((rc = check_launch("emit_instances_kernel", stream, dbg))) return rc;
     const int bit = (int)higher_msb(gx * gy);
-    GSB_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.sort_temp, ws.sort_temp_bytes, ws.keys_in, ws.keys_out, ws.vals_in,
-                                                ws.vals_out, R, 0, 32 + bit, stream));
+    {
+      StageTimer tm(kStSort, stream);
+      GSB_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.sort_temp, ws.sort_temp_bytes, ws.keys_in, ws.keys_out, ws.vals_in,
+                                                  ws.vals_out, R, 0, 32 + bit, stream));
+    }
     if ((rc = check_launch("radix sort", stream, dbg))) return rc;
   }
   GSB_CUDA_OK(cudaMemsetAsync(ws.ranges, 0, (size_t)gx * gy * sizeof(uint2), stream));
   if (R > 0) {
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, ws.keys_out, ws.ranges);
+    {
+      StageTimer tm(kStRanges, stream);
+      tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, ws.keys_out, ws.ranges);
+    }
     count_launch();
     if ((rc = check_launch("tile_ranges_kernel", stream, dbg))) return rc;
   }
-  render_kernel<<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, ws.vals_out, W, H, ws.recA, ws.recB, ws.recC,
-                                                         a->background, a->out_color, a->out_depth, a->out_final_T);
+  {
+    StageTimer tm(kStRender, stream);
+    render_kernel<<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, ws.vals_out, W, H, ws.recA, ws.recB, ws.recC,
+                                                           a->background, a->out_color, a->out_depth, a->out_final_T);
+  }
   count_launch();
   if ((rc = check_launch("render_kernel", stream, dbg))) return rc;
   return GSB_OK;
@@ -773,7 +826,10 @@ int gsb_image_to_u8(const float* chw, int32_t width, int32_t height, uint8_t* hw
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!chw || !hwc || width <= 0 || height <= 0) return fail(GSB_ERR_INVALID, "image_to_u8: bad arguments");
   const size_t n = (size_t)width * height;
-  to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(chw, width, height, hwc);
+  {
+    StageTimer tm(kStToU8, stream);
+    to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(chw, width, height, hwc);
+  }
   count_launch();
   return check_launch("to_u8_kernel", stream, false);
 }

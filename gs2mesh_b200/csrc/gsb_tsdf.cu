@@ -347,8 +347,11 @@ int gsb_tsdf_prepare_depth(const float* depth_in, const float* final_T, const ui
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!depth_in || !depth_out || width <= 0 || height <= 0) return fail(GSB_ERR_INVALID, "prepare_depth: bad arguments");
   const size_t n = (size_t)width * height;
-  prepare_depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(depth_in, final_T, mask, n, alpha_min, min_depth,
-                                                                        (float)depth_scale, depth_trunc, depth_out);
+  {
+    StageTimer tm(kStDepthPrep, stream);
+    prepare_depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(depth_in, final_T, mask, n, alpha_min, min_depth,
+                                                                          (float)depth_scale, depth_trunc, depth_out);
+  }
   count_launch();
   return check_launch("prepare_depth_kernel", stream, false);
 }
@@ -384,7 +387,10 @@ int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, i
     m.nb[k] = d.brick_count[k];
   }
   const int ns = m.nsx * m.nsy;
-  mark_bricks_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(m, depth, d.brick_stamp, d.brick_list, d.counters, vol->frame);
+  {
+    StageTimer tm(kStMarkBricks, stream);
+    mark_bricks_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(m, depth, d.brick_stamp, d.brick_list, d.counters, vol->frame);
+  }
   count_launch();
   int rc;
   if ((rc = check_launch("mark_bricks_kernel", stream, false))) return rc;
@@ -414,8 +420,11 @@ int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, i
     f.nb[k] = d.brick_count[k];
   }
   const int grid = (int)((size_t)num_sms() * 8 < vol->n_bricks ? (size_t)num_sms() * 8 : vol->n_bricks);
-  integrate_kernel<<<grid, kIntThreads, 0, stream>>>(f, depth, rgb, reinterpret_cast<float4*>(d.tsdf_weight),
-                                                     reinterpret_cast<float4*>(d.color), d.brick_list, d.counters);
+  {
+    StageTimer tm(kStIntegrate, stream);
+    integrate_kernel<<<grid, kIntThreads, 0, stream>>>(f, depth, rgb, reinterpret_cast<float4*>(d.tsdf_weight),
+                                                       reinterpret_cast<float4*>(d.color), d.brick_list, d.counters);
+  }
   count_launch();
   return check_launch("integrate_kernel", stream, false);
 }

@@ -82,6 +82,12 @@ def rasterize_forward(*, means3D, opacities, viewmatrix, projmatrix, campos, bg,
     device = means3D.device
     if not means3D.is_cuda:
         raise RuntimeError("means3D must live on a CUDA device (gs2mesh_b200 has no CPU path)")
+    if means3D.shape[0] == 0:
+        # rasterize_points.cu:68-77: with no points the zero-filled outputs are returned untouched
+        W, H = int(width), int(height)
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
+        return dict(color=z(3, H, W), depth=z(H, W) if want_depth else None, final_T=z(H, W) if want_final_T else None,
+                    radii=z(0, dt=torch.int32) if want_radii else None, counts=z(2, dt=torch.int64) if want_counts else None)
     means3D = _dev_f32(means3D, "means3D", device)
     opacities = _dev_f32(opacities, "opacities", device)
     shs = _dev_f32(shs, "shs", device)

@@ -168,16 +168,7 @@ class TSDFVolume:
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return
         self.to_sums()
-        for buf in (self.tsdf_weight, self.color):
-            if buf is None:
-                continue
-            step = max(1, chunk_bytes // 4)
-            for s in range(0, buf.numel(), step):
-                piece = buf[s:s + step]
-                if dst is None:
-                    dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group)
-                else:
-                    dist.reduce(piece, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        reduce_sum_chunked([self.tsdf_weight, self.color], group=group, dst=dst, chunk_bytes=chunk_bytes)
         self.from_sums()
 
     # ------------------------------------------------------------------ read-back
@@ -200,6 +191,25 @@ class TSDFVolume:
             self.color.zero_()
         self._stamp.zero_()
         self.frames_integrated = 0
+
+
+def reduce_sum_chunked(buffers, group=None, dst: Optional[int] = None, chunk_bytes: int = 256 << 20):
+    """The one collective of the multi-GPU path: an in-place SUM reduce (all-reduce when dst is None)
+    of each flat fp32 buffer, issued in `chunk_bytes` pieces so a 1024^3 volume (8.6 GB) does not
+    need one giant NCCL launch and the tail of integration can overlap the first chunks."""
+    import torch.distributed as dist
+
+    for buf in buffers:
+        if buf is None:
+            continue
+        flat = buf.view(-1)
+        step = max(1, chunk_bytes // flat.element_size())
+        for s in range(0, flat.numel(), step):
+            piece = flat[s:s + step]
+            if dst is None:
+                dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group)
+            else:
+                dist.reduce(piece, dst=dst, op=dist.ReduceOp.SUM, group=group)
 
 
 def merge_bricks_reference(volumes_tw):

@@ -52,6 +52,15 @@ int gsb_version(void);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 uint64_t gsb_kernel_launch_count(void);
 
+/* Optional per-stage device timing: when enabled every stage of the two pipelines is bracketed by
+ * CUDA events on the launching stream.  gsb_profile_collect() synchronises the device, writes the
+ * accumulated milliseconds and sample counts per stage (arrays of gsb_profile_num_stages()) and
+ * resets the accumulators. */
+int gsb_profile_num_stages(void);
+const char* gsb_profile_stage_name(int stage);
+int gsb_profile_enable(int on);
+int gsb_profile_collect(double* total_ms, uint64_t* samples, int n_stages);
+
 /* ------------------------------------------------------------------------------------------
  * Rasterizer
  * ------------------------------------------------------------------------------------------ */

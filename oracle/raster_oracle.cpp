@@ -293,6 +293,14 @@ int64_t orc_forward(int P, int D, int M, const float* background, int W, int H, 
                     const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
                     float tan_fovy, float* out_color, float* out_depth, float* final_T, uint32_t* n_contrib,
                     int* radii, uint32_t* point_list, int64_t list_cap, uint32_t* ranges) {
+  if (P == 0) {  // rasterize_points.cu:68-77: outputs stay zero-filled when there are no points
+    const size_t n = (size_t)W * H;
+    if (out_color) std::memset(out_color, 0, 3 * n * sizeof(float));
+    if (out_depth) std::memset(out_depth, 0, n * sizeof(float));
+    if (final_T) std::memset(final_T, 0, n * sizeof(float));
+    if (n_contrib) std::memset(n_contrib, 0, n * sizeof(uint32_t));
+    return 0;
+  }
   std::vector<int> rad(P);
   std::vector<float> xy(2 * (size_t)P), depth(P), rgb(3 * (size_t)P), co(4 * (size_t)P);
   std::vector<uint32_t> touched(P);

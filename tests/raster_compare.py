@@ -1,0 +1,31 @@
+"""Shared parity metric for rasterizer images (north_star: 1e-4 relative fp32).
+
+A pixel is "bad" if |a-b| > 1e-4 * max(1, |b|).  The pipeline has hard thresholds
+(alpha < 1/255, T < 1e-4, power > 0, ceil / floor in the tile rectangle) that a 1-ulp
+difference in expf or an FMA contraction can flip for isolated pixels (SURVEY.md section 7,
+"Branch-boundary parity"), so comparisons carry an explicit outlier budget instead of a max.
+"""
+import numpy as np
+
+TOL = 1e-4
+
+
+def compare_images(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    bad = err > TOL
+    return dict(frac_bad=float(bad.mean()), max_err=float(err.max()) if err.size else 0.0, n_bad=int(bad.sum()),
+                median=float(np.median(err)) if err.size else 0.0)
+
+
+def load_golden_case(path):
+    z = np.load(path)
+    inputs = dict(means3D=z["means3D"], opacities=z["opacities"], view=z["view"], proj=z["proj"], campos=z["campos"],
+                  W=int(z["W"]), H=int(z["H"]), tan_fovx=float(z["tan_fovx"]), tan_fovy=float(z["tan_fovy"]), bg=z["bg"],
+                  sh_degree=int(z["sh_degree"]), scale_modifier=float(z["scale_modifier"]))
+    for k_npz, k_arg in (("shs", "shs"), ("colors_precomp", "colors_precomp"), ("scales", "scales"), ("rotations", "rotations"),
+                         ("cov3D_precomp", "cov3D_precomp")):
+        if k_npz in z.files:
+            inputs[k_arg] = z[k_npz]
+    return dict(inputs=inputs, color=z["color"], radii=z["radii"], num_rendered=int(z["num_rendered"]), final_T=z["final_T"])

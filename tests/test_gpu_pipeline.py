@@ -1,0 +1,162 @@
+"""End-to-end GPU tests through the reference-shaped stage classes (Renderer / TSDF), plus
+size-independent properties at BASELINE.json's full C1 size."""
+import os
+
+import numpy as np
+import pytest
+
+from gs2mesh_b200 import camera as cam
+from gs2mesh_b200 import scene
+
+pytestmark = pytest.mark.gpu
+
+
+class Args:
+    GS_white_background = False
+    TSDF_voxel = 8  # voxel_length 1/64 -> a 128^3 window covers [-1,1]^3
+    TSDF_sdf_trunc = 0.06
+    TSDF_scale = 1.0
+    TSDF_min_depth_baselines = 4
+    TSDF_max_depth_baselines = 20
+    TSDF_dilate = 1
+    TSDF_valid = None
+    TSDF_skip = [2]
+    TSDF_use_mask = False
+    TSDF_use_occlusion_mask = True
+
+
+class StereoStub:
+    model_name = "unit"
+
+
+W, H, NPTS, NPAIRS = 320, 240, 6000, 4
+
+
+@pytest.fixture(scope="module")
+def small_scene():
+    cloud = scene.make_gaussians(NPTS, seed=7)
+    rigs, baseline = scene.make_stereo_cameras(NPAIRS, W, H)
+    return cloud, rigs, baseline
+
+
+def test_renderer_pair_matches_oracle_and_writes_reference_artifacts(oracle, gsb_lib, cuda_device, small_scene, tmp_path):
+    import cv2
+
+    from gs2mesh_b200.renderer import Renderer
+
+    cloud, rigs, baseline = small_scene
+    r = Renderer.from_scene(rigs, baseline, cloud, output_dir_root=str(tmp_path), args=Args(), device=str(cuda_device))
+    assert len(r) == NPAIRS and r.left_cameras[1] is rigs[1]["left"] and r.baseline == baseline
+    r.prepare_renderer()
+    out = r.render(1)  # north_star alias of render_image_pair
+    for side, key in (("left", "left"), ("right", "right")):
+        vt = cam.view_transforms_from_camera(rigs[1][side])
+        ref = oracle.forward(cloud.xyz, cloud.opacity, vt.world_view, vt.full_proj, vt.cam_center, W, H, vt.tan_fovx, vt.tan_fovy,
+                             shs=cloud.features, scales=cloud.scaling, rotations=cloud.rotation)
+        err = np.abs(out[key].cpu().numpy() - ref["color"])
+        assert (err > 1e-4).mean() <= 2e-4
+        png = cv2.cvtColor(cv2.imread(os.path.join(r.render_folder_name(1), f"{side}.png")), cv2.COLOR_BGR2RGB)
+        want = np.clip(np.rint(np.transpose(ref["color"], (1, 2, 0)) * np.float32(255)), 0, 255).astype(np.uint8)
+        assert (png != want).mean() < 2e-3  # .5 rounding ties can differ by one level
+        assert np.abs(png.astype(int) - want.astype(int)).max() <= 1 or (np.abs(png.astype(int) - want.astype(int)) > 1).mean() < 2e-4
+    assert os.path.basename(r.render_folder_name(1)) == "001"
+    assert out["host_left_u8"].is_pinned()
+
+
+def test_tsdf_stage_in_memory_equals_files_equals_oracle(oracle, gsb_lib, cuda_device, small_scene, tmp_path):
+    import torch
+
+    from gs2mesh_b200.renderer import Renderer
+    from gs2mesh_b200.tsdf import TSDF
+
+    cloud, rigs, baseline = small_scene
+    args = Args()
+    r = Renderer.from_scene(rigs, baseline, cloud, output_dir_root=str(tmp_path), args=args, device=str(cuda_device))
+    r.prepare_renderer()
+    r.keep_frames = True
+    frames = {}
+    for i in range(NPAIRS):
+        out = r.render_image_pair(i)
+        depth = r.expected_depth(out["depth"], out["final_T"]).cpu().numpy()
+        frames[i] = (out["host_left_u8"].numpy().copy(), depth)
+        d = os.path.join(r.render_folder_name(i), f"out_{StereoStub.model_name}")
+        os.makedirs(d, exist_ok=True)
+        np.save(os.path.join(d, "depth.npy"), depth)
+        occ = np.ones((H, W), bool)
+        occ[:, : W // 8] = False  # an occlusion mask that removes the left band
+        np.save(os.path.join(d, "occlusion_mask.npy"), occ)
+
+    # (a) from the files the reference stages exchange
+    r.keep_frames = False
+    r._frames = {}
+    stage = TSDF(r, StereoStub(), args, "unit", window_resolution=128)
+    vol = stage.run()
+    torch.cuda.synchronize()
+    from_files = vol.bricks().cpu().numpy().copy()
+    assert vol.frames_integrated == NPAIRS - 1  # TSDF_skip = [2]
+
+    # (b) oracle on the same frames, reference filter order (tsdf_utils.py:78-93)
+    ovol = oracle.OracleTSDFVolume(8.0 / 512, args.TSDF_sdf_trunc, with_color=True)
+    for i in range(NPAIRS):
+        if i in args.TSDF_skip:
+            continue
+        rgb, depth = frames[i]
+        occ = np.ones((H, W), bool)
+        occ[:, : W // 8] = False
+        d = depth * occ
+        d = np.where(d < np.float32(args.TSDF_min_depth_baselines * baseline), 0, d).astype(np.float32)
+        c = rigs[i]["left"]
+        ovol.integrate(d, rgb, W, H, c["fx"], c["fy"], c["cx"], c["cy"], np.linalg.inv(c["extrinsic"]), depth_scale=1.0,
+                       depth_trunc=baseline * args.TSDF_max_depth_baselines)
+    tw, alloc, outside = ovol.export_bricks(vol.brick_origin, vol.brick_count)
+    assert outside == 0
+    np.testing.assert_array_equal(from_files[..., 1], tw[..., 1])
+    np.testing.assert_array_equal(from_files[..., 0], tw[..., 0])
+    assert (tw[..., 1] > 0).sum() > 5000
+
+
+def test_full_size_properties(gsb_lib, cuda_device):
+    """BASELINE config C1 shapes (1M Gaussians, 1600x1200, 512^3 lattice): properties that need no oracle."""
+    import torch
+
+    from gs2mesh_b200 import _lib
+    from gs2mesh_b200.renderer import Renderer
+    from gs2mesh_b200.tsdf import TSDF
+
+    cfg = scene.CONFIGS["C1"]
+    cloud = scene.make_gaussians(cfg["num_points"], seed=1)
+    rigs, baseline = scene.make_stereo_cameras(8, cfg["width"], cfg["height"])
+
+    class A(Args):
+        TSDF_voxel = 2
+        TSDF_sdf_trunc = 0.04
+        TSDF_skip = None
+
+    r = Renderer.from_scene(rigs, baseline, cloud, args=A(), device=str(cuda_device))
+    r.prepare_renderer()
+    exact = r.render_view(0, 0, want_depth=True, want_counts=True)
+    img_e, dep_e, T_e, cnt_e = (exact[k].clone() for k in ("color", "depth", "final_T", "counts"))
+    rect = r.render_view(0, 0, want_depth=True, want_counts=True, flags=0)
+    assert torch.equal(img_e, rect["color"]) and torch.equal(dep_e, rect["depth"]) and torch.equal(T_e, rect["final_T"])
+    assert cnt_e[0] < rect["counts"][0] and cnt_e[1] == rect["counts"][0]
+    assert torch.isfinite(img_e).all() and float((1 - T_e).mean()) > 0.2
+    # the two eyes see the same scene: a horizontal shift, similar coverage
+    pair = r.render_image_pair(0, to_host=False)
+    cov_l = float((1 - pair["final_T"]).mean())
+    assert abs(float(pair["left"].mean()) - float(pair["right"].mean())) < 0.02 and cov_l > 0.2
+
+    stage = TSDF(r, None, A(), "c1", window_resolution=512)
+    for _ in range(2):
+        stage.integrate(pair["depth"], pair["left_u8"], rigs[0]["left"], final_T=pair["final_T"])
+    vol = stage.volume
+    touched, outside, frame = vol.last_stats()
+    assert outside == 0 and touched > 500 and frame == 2
+    tw = vol.tsdf_weight.view(-1, 2)
+    w = tw[:, 1]
+    assert set(torch.unique(w).tolist()) <= {0.0, 2.0}  # same frame twice: weight 2 wherever touched
+    once = TSDF(r, None, A(), "c1b", window_resolution=512)
+    once.integrate(pair["depth"], pair["left_u8"], rigs[0]["left"], final_T=pair["final_T"])
+    t1 = once.volume.tsdf_weight.view(-1, 2)
+    assert torch.equal(t1[:, 1] * 2, w)
+    assert float((t1[:, 0] - tw[:, 0]).abs().max()) <= 1e-6  # running mean of identical samples
+    assert float(tw[:, 0].abs().max()) <= 1.0 and float(tw[:, 0].min()) < -0.5  # truncated to [-1, 1], surface crossed

@@ -1,0 +1,124 @@
+"""Known-answer tests of the TSDF oracle (Open3D-0.17 restatement; parity unpinned, see
+oracle/tsdf_oracle.cpp header).  KATs 6-9 of SURVEY.md section 8(c)."""
+import numpy as np
+import pytest
+
+W, H, FX, FY, CX, CY = 64, 48, 60.0, 60.0, 32.0, 24.0
+VL, TRUNC = 1.0 / 64, 0.05
+
+
+def _plane(d0):
+    return np.full((H, W), d0, np.float32)
+
+
+def _lookup(vol, p):
+    """(tsdf, weight) of the voxel containing world point p, or None if its unit is not allocated."""
+    idx = np.floor(np.asarray(p) / (16 * VL)).astype(int)
+    units = vol.unit_indices()
+    hit = np.where((units == idx).all(axis=1))[0]
+    if len(hit) == 0:
+        return None
+    t, w, _ = vol.unit_data(int(hit[0]))
+    loc = np.floor(np.asarray(p) / VL).astype(int) - idx * 16
+    k = (loc[0] * 16 + loc[1]) * 16 + loc[2]
+    return float(t[k]), float(w[k])
+
+
+def test_fronto_parallel_plane_closed_form(oracle):
+    d0 = 1.0
+    vol = oracle.OracleTSDFVolume(VL, TRUNC, with_color=False)
+    n = vol.integrate(_plane(d0), None, W, H, FX, FY, CX, CY, np.eye(4))
+    assert n == vol.num_units and n > 0
+    rng = np.random.default_rng(0)
+    checked = 0
+    for _ in range(400):
+        z = rng.uniform(d0 - 0.06, d0 + 0.06)
+        x, y = rng.uniform(-0.2, 0.2, 2) * z
+        # voxel centre containing (x,y,z)
+        c = (np.floor(np.array([x, y, z]) / VL) + 0.5) * VL
+        got = _lookup(vol, c)
+        if got is None:
+            continue
+        u = int(c[0] * FX / c[2] + CX + 0.5)
+        v = int(c[1] * FY / c[2] + CY + 0.5)
+        mult = np.sqrt(((u - CX) / FX) ** 2 + ((v - CY) / FY) ** 2 + 1)
+        sdf = (d0 - c[2]) * mult
+        if sdf > -TRUNC:
+            assert got[1] == 1.0
+            assert got[0] == pytest.approx(min(1.0, sdf / TRUNC), abs=2e-5)
+            checked += 1
+        else:
+            assert got == (0.0, 0.0)
+    assert checked > 50
+
+
+def test_repeated_integration_keeps_tsdf_and_counts_weight(oracle):
+    vol = oracle.OracleTSDFVolume(VL, TRUNC, with_color=True)
+    rgb = np.full((H, W, 3), 200, np.uint8)
+    for _ in range(3):
+        vol.integrate(_plane(1.0), rgb, W, H, FX, FY, CX, CY, np.eye(4))
+    t1 = oracle.OracleTSDFVolume(VL, TRUNC, with_color=False)
+    t1.integrate(_plane(1.0), None, W, H, FX, FY, CX, CY, np.eye(4))
+    for i in range(vol.num_units):
+        t, w, c = vol.unit_data(i)
+        t0, w0, _ = t1.unit_data(i)
+        np.testing.assert_array_equal(w, 3 * w0)
+        np.testing.assert_allclose(t, t0, atol=1e-6)
+        np.testing.assert_allclose(c[w > 0], 200.0, atol=1e-9)
+
+
+def test_depth_convert_scale_and_trunc(oracle):
+    d = np.array([[0.5, 1.0, 2.0, 4.0]], np.float32)
+    out = oracle.depth_convert(d, depth_scale=2.0, depth_trunc=1.0)
+    np.testing.assert_array_equal(out, [[0.25, 0.5, 0.0, 0.0]])  # d/scale >= trunc -> 0 (>=, not >)
+
+
+def test_zero_and_truncated_depth_contribute_nothing(oracle):
+    vol = oracle.OracleTSDFVolume(VL, TRUNC, with_color=False)
+    assert vol.integrate(np.zeros((H, W), np.float32), None, W, H, FX, FY, CX, CY, np.eye(4)) == 0
+    assert vol.integrate(_plane(5.0), None, W, H, FX, FY, CX, CY, np.eye(4), depth_trunc=3.0) == 0
+    assert vol.num_units == 0
+
+
+def test_stride4_sampling_drives_allocation(oracle):
+    """Only pixels with i,j = 0 mod 4 open volume units (depth_sampling_stride=4)."""
+    d = np.zeros((H, W), np.float32)
+    d[5, 7] = 1.0  # not on the stride-4 lattice
+    vol = oracle.OracleTSDFVolume(VL, TRUNC, with_color=False)
+    assert vol.integrate(d, None, W, H, FX, FY, CX, CY, np.eye(4)) == 0
+    d[8, 12] = 1.0
+    assert vol.integrate(d, None, W, H, FX, FY, CX, CY, np.eye(4)) > 0
+
+
+def _rot_y(deg):
+    a = np.radians(deg)
+    e = np.eye(4)
+    e[0, 0], e[0, 2], e[2, 0], e[2, 2] = np.cos(a), np.sin(a), -np.sin(a), np.cos(a)
+    return e
+
+
+def test_view_order_independence_and_sharded_merge(oracle):
+    from gs2mesh_b200.tsdf import merge_bricks_reference
+
+    views = []
+    for k, ang in enumerate([-8, -3, 4, 9]):
+        e = _rot_y(ang)
+        e[2, 3] = 0.1 * k
+        views.append((_plane(1.0 + 0.01 * k), e))
+    b0, nb = (-4, -4, -2), (8, 8, 8)
+
+    def fuse(order):
+        vol = oracle.OracleTSDFVolume(VL, TRUNC, with_color=False)
+        for i in order:
+            vol.integrate(views[i][0], None, W, H, FX, FY, CX, CY, views[i][1])
+        tw, alloc, outside = vol.export_bricks(b0, nb)
+        assert outside == 0
+        return tw
+
+    seq = fuse([0, 1, 2, 3])
+    perm = fuse([2, 0, 3, 1])
+    np.testing.assert_array_equal(seq[..., 1], perm[..., 1])
+    np.testing.assert_allclose(seq[..., 0], perm[..., 0], atol=1e-6)
+    merged = merge_bricks_reference([fuse([0, 2]), fuse([1, 3])])
+    np.testing.assert_array_equal(merged[..., 1], seq[..., 1])
+    np.testing.assert_allclose(merged[..., 0], seq[..., 0], atol=1e-6)
