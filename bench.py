@@ -243,6 +243,7 @@ def run_ours(args, cfg, rank, local, world):
         vol.reduce_across_ranks(dst=0)
     ev1.record()
     barrier(world)
+    renderer.check_status(mine)  # no asynchronously rendered frame overflowed its scratch
     clocks = sampler.stop()
     _lib.profile_enable(False)
     launches = int(_lib.lib().gsb_kernel_launch_count() - launches0)
@@ -281,9 +282,9 @@ def run_ours(args, cfg, rank, local, world):
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     bytes_per_launch = {  # algorithmic bytes per launch, SURVEY.md 8(d) / DESIGN.md
         "preprocess": 12 * P + 224 * mean["Pv"] + 8 * P + 40 * mean["Pv"],
-        "scan": 8 * P,
-        "emit_instances": 12 * mean["R"] + 36 * mean["Pv"],
-        "radix_sort": 24 * mean["R"],
+        "scan": 16 * tiles,
+        "bin_scatter": 8 * mean["R"] + 36 * mean["Pv"] + 4 * P,
+        "sort": 12 * mean["R"],
         "tile_ranges": 8 * mean["R"] + 8 * tiles,
         "render": 40 * mean["R"] + 16 * W * H,
         "to_u8": 15 * W * H,

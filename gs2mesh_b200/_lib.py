@@ -17,6 +17,7 @@ RASTER_EXACT_TILE_CULL = 1
 RASTER_NO_TMA = 2
 RASTER_DEBUG_SYNC = 4
 RASTER_CUB_SORT = 8
+RASTER_ASYNC = 16
 
 BRICK = 16
 BRICK_VOXELS = 4096

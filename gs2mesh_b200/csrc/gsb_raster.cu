@@ -31,7 +31,7 @@ namespace gsb {
 thread_local char g_error[512] = {0};
 std::atomic<uint64_t> g_launches{0};
 Profiler g_prof;
-static const char* kStageNames[kStCount] = {"preprocess", "scan", "emit_instances", "radix_sort", "tile_ranges",
+static const char* kStageNames[kStCount] = {"preprocess", "scan", "bin_scatter", "sort", "tile_ranges",
                                             "render",     "to_u8", "prepare_depth", "mark_bricks", "integrate"};
 static thread_local int64_t g_required_instances = 0;
 
@@ -144,6 +144,63 @@ __device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, 
   return qmin <= two_tau + margin;
 }
 
+// Enumerates the tiles a Gaussian is binned into.  All 32 lanes of the warp must call this
+// together (`active` false for idle lanes).  Small rectangles are walked by their own lane; large
+// ones are processed by the whole warp, one Gaussian at a time, so a few huge splats do not
+// serialise behind a single lane.  f(tile_id, payload0, payload1) is invoked once per kept tile;
+// the return value is the number of kept tiles of THIS lane's Gaussian.
+constexpr uint32_t kCoopTiles = 24;
+template <typename F>
+__device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, float py, float ca, float cb, float cc,
+                                                         float opacity, int radius, uint32_t gx, uint32_t gy, bool exact,
+                                                         uint32_t pay0, uint32_t pay1, F&& f) {
+  const int lane = threadIdx.x & 31;
+  TileRect rc{0, 0, 0, 0};
+  uint32_t w = 0, area = 0, kept = 0;
+  float two_tau = 0.f;
+  if (active) {
+    rc = tile_rect(px, py, radius, gx, gy);
+    w = rc.x1 - rc.x0;
+    area = w * (rc.y1 - rc.y0);
+    two_tau = exact ? 2.f * logf(255.f * opacity) : 0.f;
+  }
+  const bool big = active && area > kCoopTiles;
+  if (active && !big) {
+    for (uint32_t ty = rc.y0; ty < rc.y1; ++ty)
+      for (uint32_t tx = rc.x0; tx < rc.x1; ++tx)
+        if (!exact || tile_can_contribute(px, py, ca, cb, cc, two_tau, tx, ty)) {
+          f(ty * gx + tx, pay0, pay1);
+          ++kept;
+        }
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, big);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const float spx = __shfl_sync(0xffffffffu, px, src), spy = __shfl_sync(0xffffffffu, py, src);
+    const float sa = __shfl_sync(0xffffffffu, ca, src), sb = __shfl_sync(0xffffffffu, cb, src);
+    const float sc = __shfl_sync(0xffffffffu, cc, src), st = __shfl_sync(0xffffffffu, two_tau, src);
+    const uint32_t sx0 = __shfl_sync(0xffffffffu, rc.x0, src), sy0 = __shfl_sync(0xffffffffu, rc.y0, src);
+    const uint32_t sw = __shfl_sync(0xffffffffu, w, src), sarea = __shfl_sync(0xffffffffu, area, src);
+    const uint32_t sp0 = __shfl_sync(0xffffffffu, pay0, src), sp1 = __shfl_sync(0xffffffffu, pay1, src);
+    uint32_t cnt = 0;
+    for (uint32_t base = 0; base < sarea; base += 32) {
+      const uint32_t k = base + lane;
+      bool keep = false;
+      uint32_t tile = 0;
+      if (k < sarea) {
+        const uint32_t ty = sy0 + k / sw, tx = sx0 + k % sw;
+        tile = ty * gx + tx;
+        keep = !exact || tile_can_contribute(spx, spy, sa, sb, sc, st, tx, ty);
+      }
+      if (keep) f(tile, sp0, sp1);
+      cnt += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (lane == src) kept = cnt;
+  }
+  return kept;
+}
+
 struct PreParams {
   int P, D, M, W, H;
   const float* means3D;
@@ -167,6 +224,7 @@ struct PreParams {
   uint32_t* tiles;
   int* radii;
   unsigned long long* ref_count;  // sum of reference tile rectangles
+  uint32_t* tile_count;           // per-tile instance counters (NULL on the validation path)
 };
 
 struct WarpStage {  // one warp's staged parameter block; every member offset is a multiple of 128 B
@@ -333,17 +391,18 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
           visible = true;
           radius = (int)my_radius;
           opacity = st.opac[lane];
-          if (p.flags & GSB_RASTER_EXACT_TILE_CULL) {
-            const float two_tau = 2.f * logf(255.f * opacity);
-            for (uint32_t ty = rc.y0; ty < rc.y1; ++ty)
-              for (uint32_t tx = rc.x0; tx < rc.x1; ++tx)
-                ntiles += tile_can_contribute(px, py, ca, cb, cc, two_tau, tx, ty) ? 1u : 0u;
-          } else {
-            ntiles = nref;
-          }
         }
       }
     }
+  }
+  // binning, pass 1: count this Gaussian's tiles (and the per-tile totals the scatter pass needs)
+  {
+    uint32_t* tc = p.tile_count;
+    ntiles = for_each_binned_tile(visible, px, py, ca, cb, cc, opacity, radius, p.gx, p.gy,
+                                  (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, 0u, 0u,
+                                  [tc](uint32_t tile, uint32_t, uint32_t) {
+                                    if (tc) atomicAdd(tc + tile, 1u);
+                                  });
   }
 
   // ---- stage 2: colour.  The 6 KB SH block is fetched only if some lane needs it -------------
@@ -462,6 +521,190 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const float4
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Binned pipeline (default): per-tile counts -> exclusive scan -> scatter into per-tile segments
+// -> per-tile sort by (depth bits, Gaussian index).  Equivalent to the reference's global stable
+// radix sort on (tile, depth) of keys emitted in Gaussian order (rasterizer_impl.cu:88-107,303),
+// without sorting the tile bits, without a P-sized scan and without a host round trip.
+// ---------------------------------------------------------------------------------------------
+// counters layout (unsigned long long[8]): [0] reference instance count  [1] binned instances
+// [2] overflow flag  [3] big-tile count
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t ntiles,
+                                                         uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
+                                                         unsigned long long* __restrict__ counters, int64_t capacity) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < ntiles; base += 1024) {
+    const uint32_t t = base + threadIdx.x;
+    const uint32_t c = t < ntiles ? tile_count[t] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t ws = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += v;
+      }
+      warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    const uint32_t start = carry + (warp ? warp_sums[warp - 1] : 0u) + incl - c;
+    if (t < ntiles) {
+      ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);  // untouched tiles stay (0,0)
+      cursor[t] = start;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = start + c;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counters[1] = carry;
+    if ((int64_t)carry > capacity) counters[2] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const float4* __restrict__ recA,
+                                                                const float4* __restrict__ recB,
+                                                                const uint32_t* __restrict__ tiles,
+                                                                const int* __restrict__ radii, uint32_t gx, uint32_t gy,
+                                                                uint32_t flags, int64_t capacity,
+                                                                uint32_t* __restrict__ cursor,
+                                                                uint64_t* __restrict__ keys) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < P && tiles[idx] != 0;
+  float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+  int radius = 0;
+  if (active) {
+    A = recA[idx];
+    B = recB[idx];
+    radius = radii[idx];
+  }
+  for_each_binned_tile(active, A.x, A.y, B.x, B.y, B.z, A.w, radius, gx, gy, (flags & GSB_RASTER_EXACT_TILE_CULL) != 0,
+                       __float_as_uint(A.z), (uint32_t)idx, [=](uint32_t tile, uint32_t depth_bits, uint32_t gid) {
+                         const uint32_t pos = atomicAdd(cursor + tile, 1u);
+                         if ((int64_t)pos < capacity) keys[pos] = ((uint64_t)depth_bits << 32) | gid;
+                       });
+}
+
+constexpr int kSortThreads = 256;
+constexpr uint32_t kSortSmall = 4096;  // keys sorted in static shared memory (32 KB)
+
+// In-place bitonic sort of n2 (power of two) 64-bit keys in shared memory by the whole CTA.
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, uint32_t n2, int tid, int nthreads) {
+  for (uint32_t k = 2; k <= n2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < (n2 >> 1); i += nthreads) {
+        const uint32_t a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        const uint32_t b = a | j;
+        const uint64_t ka = s[a], kb = s[b];
+        const bool up = (a & k) == 0;
+        if ((ka > kb) == up) {
+          s[a] = kb;
+          s[b] = ka;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One CTA per tile: sort the tile's (depth bits << 32 | gaussian) keys, emit the Gaussian ids.
+// Tiles with more than kSortSmall instances are queued for tile_sort_big_kernel.
+__global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint2* __restrict__ ranges,
+                                                                const uint64_t* __restrict__ keys, int64_t capacity,
+                                                                uint32_t* __restrict__ point_list,
+                                                                uint32_t* __restrict__ big_tiles,
+                                                                unsigned long long* __restrict__ counters) {
+  __shared__ uint64_t s[kSortSmall];
+  const uint32_t tile = blockIdx.x;
+  const uint2 r = ranges[tile];
+  if (r.y <= r.x || (int64_t)r.y > capacity) return;
+  const uint32_t n = r.y - r.x;
+  if (n > kSortSmall) {
+    if (threadIdx.x == 0) big_tiles[atomicAdd(&counters[3], 1ull)] = tile;
+    return;
+  }
+  uint32_t n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (uint32_t i = threadIdx.x; i < n2; i += kSortThreads) s[i] = i < n ? keys[r.x + i] : ~0ull;
+  __syncthreads();
+  bitonic_sort_smem(s, n2, threadIdx.x, kSortThreads);
+  for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) point_list[r.x + i] = (uint32_t)s[i];
+}
+
+constexpr int kBigThreads = 1024;
+constexpr uint32_t kBigChunk = 16384;  // keys per shared-memory chunk (128 KB dynamic)
+
+// Rare path: tiles with more instances than fit the small sorter.  Chunks are bitonic-sorted in
+// shared memory, then merged pairwise in global memory (rank by binary search; keys are unique).
+__global__ void __launch_bounds__(kBigThreads) tile_sort_big_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ keys,
+                                                                   uint64_t* __restrict__ tmp, uint32_t* __restrict__ point_list,
+                                                                   const uint32_t* __restrict__ big_tiles,
+                                                                   const unsigned long long* __restrict__ counters) {
+  extern __shared__ uint64_t sbig[];
+  const uint32_t nbig = (uint32_t)counters[3];
+  for (uint32_t bt = blockIdx.x; bt < nbig; bt += gridDim.x) {
+    const uint2 r = ranges[big_tiles[bt]];
+    const uint32_t n = r.y - r.x;
+    uint64_t* in = keys + r.x;
+    uint64_t* out = tmp + r.x;
+    for (uint32_t c0 = 0; c0 < n; c0 += kBigChunk) {
+      const uint32_t len = min(kBigChunk, n - c0);
+      uint32_t n2 = 1;
+      while (n2 < len) n2 <<= 1;
+      for (uint32_t i = threadIdx.x; i < n2; i += kBigThreads) sbig[i] = i < len ? in[c0 + i] : ~0ull;
+      __syncthreads();
+      bitonic_sort_smem(sbig, n2, threadIdx.x, kBigThreads);
+      for (uint32_t i = threadIdx.x; i < len; i += kBigThreads) in[c0 + i] = sbig[i];
+      __syncthreads();
+    }
+    for (uint32_t width = kBigChunk; width < n; width <<= 1) {
+      for (uint32_t i = threadIdx.x; i < n; i += kBigThreads) {
+        const uint32_t pair0 = i / (2 * width) * (2 * width);
+        const uint32_t mid = min(pair0 + width, n), end = min(pair0 + 2 * width, n);
+        const uint64_t key = in[i];
+        // rank of `key` inside the other run of its pair
+        uint32_t lo, hi, self_off;
+        if (i < mid) {
+          lo = mid;
+          hi = end;
+          self_off = i - pair0;
+        } else {
+          lo = pair0;
+          hi = mid;
+          self_off = i - mid;
+        }
+        const uint32_t lo0 = lo;
+        while (lo < hi) {
+          const uint32_t m = (lo + hi) >> 1;
+          if (in[m] < key)
+            lo = m + 1;
+          else
+            hi = m;
+        }
+        out[pair0 + self_off + (lo - lo0)] = key;
+      }
+      __syncthreads();
+      uint64_t* t = in;
+      in = out;
+      out = t;
+      __threadfence_block();
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += kBigThreads) point_list[r.x + i] = (uint32_t)in[i];
+    __syncthreads();
+  }
+}
+
 // rasterizer_impl.cu:116-138
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const uint64_t* __restrict__ keys,
                                                           uint2* __restrict__ ranges) {
@@ -488,7 +731,8 @@ __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __rest
                                                             const float4* __restrict__ recB,
                                                             const float2* __restrict__ recC,
                                                             const float* __restrict__ bg, float* __restrict__ out_color,
-                                                            float* __restrict__ out_depth, float* __restrict__ out_T) {
+                                                            float* __restrict__ out_depth, float* __restrict__ out_T,
+                                                            int64_t capacity) {
   __shared__ float4 sA[kTilePixels];
   __shared__ float4 sB[kTilePixels];
   __shared__ float2 sC[kTilePixels];
@@ -497,7 +741,8 @@ __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __rest
   const uint32_t pix_x = blockIdx.x * kTile + lx, pix_y = blockIdx.y * kTile + ly;
   const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
   const float pfx = (float)pix_x, pfy = (float)pix_y;
-  const uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
+  uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
+  if ((int64_t)range.y > capacity) range = make_uint2(0u, 0u);  // undersized workspace: frame is reported invalid
   const int rounds = (range.y - range.x + kTilePixels - 1) / kTilePixels;
   int todo = range.y - range.x;
   bool done = !inside;
@@ -546,10 +791,13 @@ __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __rest
   }
 }
 
-__global__ void write_counts_kernel(const uint32_t* __restrict__ offsets, int P, const unsigned long long* ref_count,
+__global__ void write_counts_kernel(const uint32_t* __restrict__ offsets, int P, const unsigned long long* counters,
                                     int64_t* out) {
-  out[0] = P > 0 ? (int64_t)offsets[P - 1] : 0;
-  out[1] = (int64_t)*ref_count;
+  // offsets != NULL: validation path (instance total = last element of the per-Gaussian scan)
+  out[0] = offsets ? (P > 0 ? (int64_t)offsets[P - 1] : 0) : (int64_t)counters[1];
+  out[1] = (int64_t)counters[0];
+  out[2] = (int64_t)counters[2];
+  out[3] = (int64_t)counters[3];
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means,
@@ -598,6 +846,9 @@ struct Workspace {
   int* radii;
   unsigned long long* counters;  // [0] reference instance count
   uint2* ranges;
+  uint32_t* tile_count;
+  uint32_t* cursor;
+  uint32_t* big_tiles;
   uint64_t* keys_in;
   uint64_t* keys_out;
   uint32_t* vals_in;
@@ -622,6 +873,9 @@ Workspace carve(void* base, int32_t P, int32_t W, int32_t H, int64_t R) {
   w.radii = c.take<int>(Pn);
   w.counters = c.take<unsigned long long>(8);
   w.ranges = c.take<uint2>(ntiles);
+  w.tile_count = c.take<uint32_t>(ntiles);
+  w.cursor = c.take<uint32_t>(ntiles);
+  w.big_tiles = c.take<uint32_t>(ntiles);
   w.keys_in = c.take<uint64_t>(Rn);
   w.keys_out = c.take<uint64_t>(Rn);
   w.vals_in = c.take<uint32_t>(Rn);
@@ -713,7 +967,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     GSB_CUDA_OK(cudaMemsetAsync(a->out_color, 0, 3 * npix * sizeof(float), stream));
     if (a->out_depth) GSB_CUDA_OK(cudaMemsetAsync(a->out_depth, 0, npix * sizeof(float), stream));
     if (a->out_final_T) GSB_CUDA_OK(cudaMemsetAsync(a->out_final_T, 0, npix * sizeof(float), stream));
-    if (a->num_rendered) GSB_CUDA_OK(cudaMemsetAsync(a->num_rendered, 0, 2 * sizeof(int64_t), stream));
+    if (a->num_rendered) GSB_CUDA_OK(cudaMemsetAsync(a->num_rendered, 0, 4 * sizeof(int64_t), stream));
     return GSB_OK;
   }
 
@@ -750,7 +1004,11 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   pp.radii = a->radii ? a->radii : ws.radii;
   pp.ref_count = ws.counters;
 
+  const bool use_cub = (a->flags & GSB_RASTER_CUB_SORT) != 0;
+  const size_t ntiles = (size_t)gx * gy;
+  pp.tile_count = use_cub ? nullptr : ws.tile_count;
   GSB_CUDA_OK(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream));
+  if (!use_cub) GSB_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, ntiles * sizeof(uint32_t), stream));
   const int pre_blocks = (P + kPreThreads - 1) / kPreThreads;
   {
     StageTimer tm(kStPreprocess, stream);
@@ -759,55 +1017,106 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   count_launch();
   if ((rc = check_launch("preprocess_kernel", stream, dbg))) return rc;
 
-  {
-    StageTimer tm(kStScan, stream);
-    GSB_CUDA_OK(cub::DeviceScan::InclusiveSum(ws.scan_temp, ws.scan_temp_bytes, ws.tiles, ws.offsets, P, stream));
-  }
-  if (a->num_rendered) {
-    write_counts_kernel<<<1, 1, 0, stream>>>(ws.offsets, P, ws.counters, a->num_rendered);
+  const uint32_t* point_list = nullptr;
+  if (use_cub) {
+    // ---- validation path: the reference's own pipeline shape (P-sized scan, emit in Gaussian order,
+    //      global radix sort of (tile | depth) keys, boundary detection), incl. its host round trip
+    {
+      StageTimer tm(kStScan, stream);
+      GSB_CUDA_OK(cub::DeviceScan::InclusiveSum(ws.scan_temp, ws.scan_temp_bytes, ws.tiles, ws.offsets, P, stream));
+    }
+    if (a->num_rendered) {
+      write_counts_kernel<<<1, 1, 0, stream>>>(ws.offsets, P, ws.counters, a->num_rendered);
+      count_launch();
+    }
+    uint32_t R32 = 0;
+    GSB_CUDA_OK(cudaMemcpyAsync(&R32, ws.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GSB_CUDA_OK(cudaStreamSynchronize(stream));
+    const int64_t R = (int64_t)R32;
+    g_required_instances = R;
+    if (R > cap)
+      return fail(GSB_ERR_WORKSPACE, "frame needs %lld instances, workspace sized for %lld", (long long)R, (long long)cap);
+    if (R > 0) {
+      {
+        StageTimer tm(kStEmit, stream);
+        emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ws.recA, ws.recB, ws.tiles, ws.offsets, pp.radii, gx, gy,
+                                                                   a->flags, cap, ws.keys_in, ws.vals_in);
+      }
+      count_launch();
+      if ((rc = check_launch("emit_instances_kernel", stream, dbg))) return rc;
+      const int bit = (int)higher_msb(gx * gy);
+      {
+        StageTimer tm(kStSort, stream);
+        GSB_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.sort_temp, ws.sort_temp_bytes, ws.keys_in, ws.keys_out, ws.vals_in,
+                                                    ws.vals_out, R, 0, 32 + bit, stream));
+      }
+      if ((rc = check_launch("radix sort", stream, dbg))) return rc;
+    }
+    GSB_CUDA_OK(cudaMemsetAsync(ws.ranges, 0, ntiles * sizeof(uint2), stream));
+    if (R > 0) {
+      {
+        StageTimer tm(kStRanges, stream);
+        tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, ws.keys_out, ws.ranges);
+      }
+      count_launch();
+      if ((rc = check_launch("tile_ranges_kernel", stream, dbg))) return rc;
+    }
+    point_list = ws.vals_out;
+  } else {
+    // ---- binned pipeline: no P-sized scan, no tile bits in the sort, no host round trip
+    {
+      StageTimer tm(kStScan, stream);
+      tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, (uint32_t)ntiles, ws.ranges, ws.cursor, ws.counters, cap);
+    }
     count_launch();
-  }
-
-  // Instance count -> host (the reference does the same blocking read, rasterizer_impl.cu:281).
-  uint32_t R32 = 0;
-  GSB_CUDA_OK(cudaMemcpyAsync(&R32, ws.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-  GSB_CUDA_OK(cudaStreamSynchronize(stream));
-  const int64_t R = (int64_t)R32;
-  g_required_instances = R;
-  if (R > cap) return fail(GSB_ERR_WORKSPACE, "frame needs %lld instances, workspace sized for %lld", (long long)R, (long long)cap);
-
-  if (R > 0) {
+    if ((rc = check_launch("tile_scan_kernel", stream, dbg))) return rc;
     {
       StageTimer tm(kStEmit, stream);
-      emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ws.recA, ws.recB, ws.tiles, ws.offsets, pp.radii, gx, gy,
-                                                                 a->flags, cap, ws.keys_in, ws.vals_in);
+      scatter_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ws.recA, ws.recB, ws.tiles, pp.radii, gx, gy, a->flags,
+                                                                    cap, ws.cursor, ws.keys_in);
     }
     count_launch();
-    if ((rc = check_launch("emit_instances_kernel", stream, dbg))) return rc;
-    const int bit = (int)higher_msb(gx * gy);
+    if ((rc = check_launch("scatter_instances_kernel", stream, dbg))) return rc;
     {
       StageTimer tm(kStSort, stream);
-      GSB_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.sort_temp, ws.sort_temp_bytes, ws.keys_in, ws.keys_out, ws.vals_in,
-                                                  ws.vals_out, R, 0, 32 + bit, stream));
+      tile_sort_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(ws.ranges, ws.keys_in, cap, ws.vals_out, ws.big_tiles,
+                                                                     ws.counters);
+      static bool big_attr_set = false;
+      if (!big_attr_set) {
+        GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kBigChunk * sizeof(uint64_t))));
+        big_attr_set = true;
+      }
+      tile_sort_big_kernel<<<64, kBigThreads, kBigChunk * sizeof(uint64_t), stream>>>(ws.ranges, ws.keys_in, ws.keys_out,
+                                                                                     ws.vals_out, ws.big_tiles, ws.counters);
     }
-    if ((rc = check_launch("radix sort", stream, dbg))) return rc;
-  }
-  GSB_CUDA_OK(cudaMemsetAsync(ws.ranges, 0, (size_t)gx * gy * sizeof(uint2), stream));
-  if (R > 0) {
-    {
-      StageTimer tm(kStRanges, stream);
-      tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, ws.keys_out, ws.ranges);
+    count_launch(2);
+    if ((rc = check_launch("tile_sort_kernel", stream, dbg))) return rc;
+    if (a->num_rendered) {
+      write_counts_kernel<<<1, 1, 0, stream>>>(nullptr, P, ws.counters, a->num_rendered);
+      count_launch();
     }
-    count_launch();
-    if ((rc = check_launch("tile_ranges_kernel", stream, dbg))) return rc;
+    point_list = ws.vals_out;
   }
   {
     StageTimer tm(kStRender, stream);
-    render_kernel<<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, ws.vals_out, W, H, ws.recA, ws.recB, ws.recC,
-                                                           a->background, a->out_color, a->out_depth, a->out_final_T);
+    render_kernel<<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC,
+                                                           a->background, a->out_color, a->out_depth, a->out_final_T, cap);
   }
   count_launch();
   if ((rc = check_launch("render_kernel", stream, dbg))) return rc;
+
+  if (!use_cub && !(a->flags & GSB_RASTER_ASYNC)) {
+    // synchronous contract: report an undersized workspace now (one wait at the END of the frame;
+    // GSB_RASTER_ASYNC callers read num_rendered[2] themselves after their own synchronisation)
+    unsigned long long host_counters[4] = {0, 0, 0, 0};
+    GSB_CUDA_OK(cudaMemcpyAsync(host_counters, ws.counters, sizeof(host_counters), cudaMemcpyDeviceToHost, stream));
+    GSB_CUDA_OK(cudaStreamSynchronize(stream));
+    g_required_instances = (int64_t)host_counters[1];
+    if (host_counters[2])
+      return fail(GSB_ERR_WORKSPACE, "frame needs %lld instances, workspace sized for %lld", (long long)host_counters[1],
+                  (long long)cap);
+  }
   return GSB_OK;
 }
 

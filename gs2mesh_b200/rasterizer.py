@@ -71,11 +71,17 @@ def _dev_f32(t, name, device):
 def rasterize_forward(*, means3D, opacities, viewmatrix, projmatrix, campos, bg, width, height, tan_fovx, tan_fovy,
                       shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, sh_degree=0,
                       scale_modifier=1.0, prefiltered=False, flags=DEFAULT_FLAGS, want_depth=True, want_final_T=True,
-                      want_radii=True, want_counts=False, out_color=None, out_depth=None, out_final_T=None):
+                      want_radii=True, want_counts=False, out_color=None, out_depth=None, out_final_T=None,
+                      async_mode=False, counts_out=None, min_instances=0):
     """One forward rasterization on the current CUDA stream.
 
     Returns dict(color[3,H,W], depth[H,W]|None, final_T[H,W]|None, radii[P]|None,
-    counts (int64[2] CUDA tensor: binned, reference-equivalent)|None).
+    counts (int64[4]: binned instances, reference-equivalent instances, overflow flag, large tiles)|None).
+
+    async_mode=False (default): the call waits for the stream once at the end of the frame so that an
+    undersized scratch block can be grown and the frame redone transparently.
+    async_mode=True: nothing waits; pass `counts_out` (int64[4], device or pinned host memory) and check
+    counts_out[2] == 0 after your own synchronisation (see Renderer.check_status()).
     """
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
@@ -87,7 +93,7 @@ def rasterize_forward(*, means3D, opacities, viewmatrix, projmatrix, campos, bg,
         W, H = int(width), int(height)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
         return dict(color=z(3, H, W), depth=z(H, W) if want_depth else None, final_T=z(H, W) if want_final_T else None,
-                    radii=z(0, dt=torch.int32) if want_radii else None, counts=z(2, dt=torch.int64) if want_counts else None)
+                    radii=z(0, dt=torch.int32) if want_radii else None, counts=z(4, dt=torch.int64) if want_counts else None)
     means3D = _dev_f32(means3D, "means3D", device)
     opacities = _dev_f32(opacities, "opacities", device)
     shs = _dev_f32(shs, "shs", device)
@@ -109,12 +115,14 @@ def rasterize_forward(*, means3D, opacities, viewmatrix, projmatrix, campos, bg,
         depth = (out_depth if out_depth is not None else torch.empty(H, W, **f32)) if want_depth else None
         final_T = (out_final_T if out_final_T is not None else torch.empty(H, W, **f32)) if want_final_T else None
         radii = torch.empty(P, dtype=torch.int32, device=device) if want_radii else None
-        counts = torch.zeros(2, dtype=torch.int64, device=device) if want_counts else None
+        counts = counts_out if counts_out is not None else (torch.zeros(4, dtype=torch.int64, device=device) if want_counts else None)
         scratch = _scratch_for(device)
-        guess = max(scratch.max_instances if scratch.key == (P, W, H) else 0, 4 * P, 1 << 20)
+        guess = max(scratch.max_instances if scratch.key == (P, W, H) else 0, 4 * P, 1 << 20, int(min_instances))
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         L = _lib.lib()
-        for attempt in range(3):
+        if async_mode:
+            flags = int(flags) | _lib.RASTER_ASYNC
+        for attempt in range(1 if async_mode else 3):
             ws = scratch.ensure(P, W, H, guess)
             args = GsbRasterArgs(
                 P=P, sh_degree=int(sh_degree), sh_coeffs=M, width=W, height=H, background=ptr(bg), means3D=ptr(means3D),
@@ -125,7 +133,7 @@ def rasterize_forward(*, means3D, opacities, viewmatrix, projmatrix, campos, bg,
                 out_depth=ptr(depth), out_final_T=ptr(final_T), radii=ptr(radii), num_rendered=ptr(counts),
                 workspace=ptr(ws), workspace_bytes=ws.numel(), max_instances=scratch.max_instances)
             rc = L.gsb_raster_forward(C.byref(args), stream)
-            if rc == _lib.GSB_ERR_WORKSPACE and attempt < 2:
+            if rc == _lib.GSB_ERR_WORKSPACE and attempt < 2 and not async_mode:
                 need = int(L.gsb_raster_required_instances())
                 guess = max(int(need * 1.25) + 1024, guess)
                 continue

@@ -116,7 +116,33 @@ class Renderer:
             self._views.append(vts)
         self._camera_table = torch.as_tensor(recs).to(dev)
         self._bufs = {}
+        # per-(view, side) rasterizer status words, written by the GPU straight into pinned host memory
+        self._status = torch.zeros(len(self.cameras), 2, 4, dtype=torch.int64).pin_memory()
+        self._min_instances = 0
         self._ready = True
+        self.calibrate_capacity()
+
+    def calibrate_capacity(self, sample_views=3, slack=1.5):
+        """Size the binning scratch once from a few synchronous renders so that the hot loop can run
+        without ever waiting for the GPU (the reference re-sizes -- and blocks -- inside every frame,
+        rasterizer_impl.cu:281-285)."""
+        n = len(self.cameras)
+        worst = 0
+        for i in sorted(set(int(round(k * (n - 1) / max(sample_views - 1, 1))) for k in range(sample_views))):
+            for s in range(2):
+                out = self.render_view(i, s, want_counts=True)
+                worst = max(worst, int(out["counts"][0].item()))
+        self._min_instances = int(worst * slack) + 4096
+
+    def check_status(self, views=None):
+        """After a synchronisation: raise if any asynchronously rendered frame overflowed the scratch."""
+        st = self._status if views is None else self._status[list(views)]
+        bad = (st[..., 2] != 0).nonzero()
+        if len(bad):
+            need = int(st[..., 0].max().item())
+            self._min_instances = max(self._min_instances, int(need * 1.5))
+            raise RuntimeError(f"{len(bad)} frame(s) needed more binning scratch than calibrated ({need} instances); "
+                               "capacity has been raised, render them again")
 
     def _buffers(self, w, h):
         key = (w, h)
@@ -133,7 +159,7 @@ class Renderer:
         return self._bufs[key]
 
     def render_view(self, camera_number, side, *, want_depth=False, out_color=None, out_depth=None, out_final_T=None,
-                    flags=rast.DEFAULT_FLAGS, want_counts=False):
+                    flags=rast.DEFAULT_FLAGS, want_counts=False, async_mode=False):
         """One forward rasterization of view `camera_number`, side 0 (left) / 1 (right)."""
         if not self._ready:
             raise RuntimeError("call prepare_renderer() first")
@@ -144,7 +170,8 @@ class Renderer:
             bg=self.background, width=vt.width, height=vt.height, tan_fovx=vt.tan_fovx, tan_fovy=vt.tan_fovy, shs=self.shs,
             scales=self.scales, rotations=self.rotations, sh_degree=self.sh_degree, scale_modifier=1.0, flags=flags,
             want_depth=want_depth, want_final_T=want_depth, want_radii=False, want_counts=want_counts,
-            out_color=out_color, out_depth=out_depth, out_final_T=out_final_T)
+            out_color=out_color, out_depth=out_depth, out_final_T=out_final_T, async_mode=async_mode,
+            counts_out=self._status[camera_number, side] if async_mode else None, min_instances=self._min_instances)
 
     def render_image_pair(self, camera_number, visualize=False, *, to_host: Optional[bool] = None):
         """Render the stereo-aligned left/right pair of view `camera_number`
@@ -157,7 +184,8 @@ class Renderer:
             b = self._buffers(vt.width, vt.height)
             for s in range(2):
                 self.render_view(camera_number, s, want_depth=(s == 0), out_color=b["color"][s],
-                                 out_depth=b["depth"] if s == 0 else None, out_final_T=b["final_T"] if s == 0 else None)
+                                 out_depth=b["depth"] if s == 0 else None, out_final_T=b["final_T"] if s == 0 else None,
+                                 async_mode=True)
                 rast.image_to_u8(b["color"][s], out=b["u8"][s])
             result = dict(left=b["color"][0], right=b["color"][1], left_u8=b["u8"][0], right_u8=b["u8"][1],
                           depth=b["depth"], final_T=b["final_T"])
@@ -166,6 +194,7 @@ class Renderer:
                 for s in range(2):
                     b["host_u8"][s].copy_(b["u8"][s], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
+                self.check_status([camera_number])
                 result["host_left_u8"], result["host_right_u8"] = b["host_u8"]
             if self.write_images:
                 import cv2

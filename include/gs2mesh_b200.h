@@ -73,8 +73,12 @@ int gsb_profile_collect(double* total_ms, uint64_t* samples, int n_stages);
 #define GSB_RASTER_NO_TMA 2u          /* stage parameters with plain loads (debug / A-B only)  */
 #define GSB_RASTER_DEBUG_SYNC 4u      /* synchronise + check after every stage, like debug=True
                                          (auxiliary.h:166-173)                                 */
-#define GSB_RASTER_CUB_SORT 8u        /* use cub::DeviceRadixSort instead of the in-library sort
-                                         (validation only)                                     */
+#define GSB_RASTER_CUB_SORT 8u        /* validation only: the reference's pipeline shape (P-sized scan,
+                                         cub::DeviceRadixSort on tile|depth keys, host read of the
+                                         instance count) instead of the in-library binned sort     */
+#define GSB_RASTER_ASYNC 16u          /* never wait for the stream: an undersized workspace is then
+                                         reported through num_rendered[2] instead of the return
+                                         value                                                 */
 
 /* One forward rasterization.  Field-for-field the argument list of
  * CudaRasterizer::Rasterizer::forward (rasterizer.h:30-53) / RasterizeGaussiansCUDA
@@ -104,9 +108,10 @@ typedef struct GsbRasterArgs {
   float* out_depth;            /* [H,W]  NEW: sum_i z_i alpha_i T_i (no reference counterpart) */
   float* out_final_T;          /* [H,W]  final transmittance (ImageState.accum_alpha) */
   int32_t* radii;              /* [P]                                               */
-  /* num_rendered: written asynchronously on `stream` (device or pinned-mapped host memory);
+  /* num_rendered: int64[4] written asynchronously on `stream` (device or pinned host memory);
      [0] = instances actually binned, [1] = reference-equivalent count (sum of tile rectangles,
-     what rasterize_points.cu:114 returns).  May be NULL.                                 */
+     what rasterize_points.cu:114 returns), [2] = 1 if the frame needed more than max_instances
+     (outputs invalid), [3] = tiles that took the large-tile sort path.  May be NULL.       */
   int64_t* num_rendered;
   /* caller-owned scratch */
   void* workspace;             /* device, >= gsb_raster_workspace_bytes(...)        */
@@ -121,9 +126,9 @@ size_t gsb_raster_workspace_bytes(int32_t P, int32_t width, int32_t height, int6
 
 /* Enqueue one forward pass.  If the frame needs more than args->max_instances pairs the call
  * returns GSB_ERR_WORKSPACE and gsb_raster_required_instances() tells how many are needed
- * (outputs are then undefined).  This entry point performs ONE small device->host read of the
- * instance count (as the reference does, rasterizer_impl.cu:281) unless the in-library
- * sync-free pipeline is selected at build time. */
+ * (outputs are then undefined).  Without GSB_RASTER_ASYNC the call waits for the stream ONCE, at
+ * the end of the frame, to be able to report that; the reference blocks in the middle of the
+ * frame instead (rasterizer_impl.cu:281).  With GSB_RASTER_ASYNC nothing waits. */
 int gsb_raster_forward(const GsbRasterArgs* args, void* stream);
 int64_t gsb_raster_required_instances(void);
 

@@ -145,6 +145,84 @@ def test_exact_tile_cull_is_bit_identical_to_rectangle_binning(gsb_lib, cuda_dev
         assert exact["counts"][1] == rect["counts"][1] == rect["counts"][0]
 
 
+def test_binned_sort_equals_reference_shaped_sort(gsb_lib, cuda_device):
+    """Default pipeline (per-tile counts, scatter, per-tile bitonic sort on (depth, index)) against the
+    validation path that keeps the reference's shape (global stable radix sort on (tile, depth) of keys
+    emitted in Gaussian order): identical blend order => bit-identical images.  The dense cases push
+    single tiles past the shared-memory sorter (4096) and past one merge chunk (16384)."""
+    from gs2mesh_b200 import _lib
+
+    for n, W, H, seed, expect_big in [(6000, 320, 240, 60, False), (20000, 96, 64, 61, True), (60000, 64, 48, 62, True)]:
+        g, vt = _case(n, W, H, seed=seed)
+        inp = _np_inputs(g, vt)
+        for cull in (0, _lib.RASTER_EXACT_TILE_CULL):
+            ref = _ours(cuda_device, inp, flags=cull | _lib.RASTER_CUB_SORT)
+            new = _ours(cuda_device, inp, flags=cull)
+            for k in ("color", "depth", "final_T", "radii"):
+                np.testing.assert_array_equal(ref[k], new[k], err_msg=f"{k} n={n} cull={cull}")
+            np.testing.assert_array_equal(ref["counts"][:2], new["counts"][:2])
+            assert new["counts"][2] == 0
+            assert (new["counts"][3] > 0) == expect_big, new["counts"]
+
+
+def test_async_mode_reports_overflow_in_status_word(gsb_lib, cuda_device):
+    import torch
+
+    from gs2mesh_b200 import rasterizer as rast
+
+    g, vt = _case(3000, 320, 240, seed=0)
+    dev = cuda_device
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    status = torch.zeros(4, dtype=torch.int64).pin_memory()
+    kw = dict(means3D=t(g.xyz), opacities=t(g.opacity).reshape(-1), viewmatrix=t(vt.world_view), projmatrix=t(vt.full_proj),
+              campos=t(vt.cam_center), bg=torch.zeros(3, device=dev), width=320, height=240, tan_fovx=vt.tan_fovx,
+              tan_fovy=vt.tan_fovy, shs=t(g.features), scales=t(g.scaling), rotations=t(g.rotation), sh_degree=3)
+    sync = rast.rasterize_forward(**kw, want_counts=True)
+    torch.cuda.synchronize()
+    out = rast.rasterize_forward(**kw, async_mode=True, counts_out=status)
+    torch.cuda.synchronize()
+    assert status[2] == 0 and status[0] == sync["counts"][0].item() and status[1] == sync["counts"][1].item()
+    assert torch.equal(out["color"], sync["color"])
+
+
+def _raw_call(gsb_lib, dev, g, vt, cap, flags, status=None):
+    """Direct C-ABI call with an explicit binning capacity."""
+    import torch
+
+    from gs2mesh_b200 import _lib
+
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    P, W, H = g.xyz.shape[0], vt.width, vt.height
+    ten = dict(m=t(g.xyz), o=t(g.opacity).reshape(-1), sh=t(g.features), s=t(g.scaling), r=t(g.rotation), v=t(vt.world_view),
+               p=t(vt.full_proj), c=t(vt.cam_center), bg=torch.zeros(3, device=dev), col=torch.zeros(3, H, W, device=dev))
+    ws = torch.empty(gsb_lib.gsb_raster_workspace_bytes(P, W, H, cap), dtype=torch.uint8, device=dev)
+    a = _lib.GsbRasterArgs(P=P, sh_degree=3, sh_coeffs=16, width=W, height=H, background=_lib.ptr(ten["bg"]),
+                           means3D=_lib.ptr(ten["m"]), shs=_lib.ptr(ten["sh"]), opacities=_lib.ptr(ten["o"]), scales=_lib.ptr(ten["s"]),
+                           rotations=_lib.ptr(ten["r"]), scale_modifier=1.0, viewmatrix=_lib.ptr(ten["v"]), projmatrix=_lib.ptr(ten["p"]),
+                           cam_pos=_lib.ptr(ten["c"]), tan_fovx=vt.tan_fovx, tan_fovy=vt.tan_fovy, flags=flags, out_color=_lib.ptr(ten["col"]),
+                           num_rendered=_lib.ptr(status), workspace=_lib.ptr(ws), workspace_bytes=ws.numel(), max_instances=cap)
+    rc = gsb_lib.gsb_raster_forward(C.byref(a), None)
+    torch.cuda.synchronize()
+    return rc, ten["col"], (ten, ws)
+
+
+def test_undersized_workspace_async_flags_frame_and_stays_in_bounds(gsb_lib, cuda_device):
+    import torch
+
+    from gs2mesh_b200 import _lib
+
+    g, vt = _case(3000, 320, 240, seed=0)
+    status = torch.zeros(4, dtype=torch.int64).pin_memory()
+    rc, _, _ = _raw_call(gsb_lib, cuda_device, g, vt, 1000, _lib.RASTER_ASYNC, status)
+    assert rc == _lib.GSB_OK and status[2] == 1 and status[0] > 1000
+    need = int(status[0])
+    status.zero_()
+    rc, col, _ = _raw_call(gsb_lib, cuda_device, g, vt, need, _lib.RASTER_ASYNC, status)
+    assert rc == _lib.GSB_OK and status[2] == 0 and status[0] == need
+    rc2, col2, _ = _raw_call(gsb_lib, cuda_device, g, vt, need + 12345, 0, None)
+    assert rc2 == _lib.GSB_OK and torch.equal(col, col2)
+
+
 def test_tma_staging_equals_plain_loads(gsb_lib, cuda_device):
     from gs2mesh_b200 import _lib
 
@@ -210,26 +288,13 @@ def test_workspace_too_small_is_reported(gsb_lib, cuda_device):
     from gs2mesh_b200 import _lib
 
     g, vt = _case(3000, 320, 240, seed=0)
-    dev = cuda_device
-    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
-    ten = dict(m=t(g.xyz), o=t(g.opacity).reshape(-1), sh=t(g.features), s=t(g.scaling), r=t(g.rotation), v=t(vt.world_view),
-               p=t(vt.full_proj), c=t(vt.cam_center), bg=torch.zeros(3, device=dev), col=torch.empty(3, 240, 320, device=dev))
-    cap = 1000
-    ws = torch.empty(gsb_lib.gsb_raster_workspace_bytes(3000, 320, 240, cap), dtype=torch.uint8, device=dev)
-    a = _lib.GsbRasterArgs(P=3000, sh_degree=3, sh_coeffs=16, width=320, height=240, background=_lib.ptr(ten["bg"]),
-                           means3D=_lib.ptr(ten["m"]), shs=_lib.ptr(ten["sh"]), opacities=_lib.ptr(ten["o"]), scales=_lib.ptr(ten["s"]),
-                           rotations=_lib.ptr(ten["r"]), scale_modifier=1.0, viewmatrix=_lib.ptr(ten["v"]), projmatrix=_lib.ptr(ten["p"]),
-                           cam_pos=_lib.ptr(ten["c"]), tan_fovx=vt.tan_fovx, tan_fovy=vt.tan_fovy, flags=0, out_color=_lib.ptr(ten["col"]),
-                           workspace=_lib.ptr(ws), workspace_bytes=ws.numel(), max_instances=cap)
-    rc = gsb_lib.gsb_raster_forward(C.byref(a), None)
-    assert rc == _lib.GSB_ERR_WORKSPACE
-    need = gsb_lib.gsb_raster_required_instances()
-    assert need > cap
-    ws = torch.empty(gsb_lib.gsb_raster_workspace_bytes(3000, 320, 240, need), dtype=torch.uint8, device=dev)
-    a.workspace, a.workspace_bytes, a.max_instances = _lib.ptr(ws), ws.numel(), need
-    assert gsb_lib.gsb_raster_forward(C.byref(a), None) == _lib.GSB_OK
-    torch.cuda.synchronize()
-    assert torch.isfinite(ten["col"]).all()
+    for flags in (0, _lib.RASTER_CUB_SORT):
+        rc, _, _ = _raw_call(gsb_lib, cuda_device, g, vt, 1000, flags)
+        assert rc == _lib.GSB_ERR_WORKSPACE
+        need = gsb_lib.gsb_raster_required_instances()
+        assert need > 1000 and b"instances" in gsb_lib.gsb_last_error()
+        rc, col, _ = _raw_call(gsb_lib, cuda_device, g, vt, need, flags)
+        assert rc == _lib.GSB_OK and torch.isfinite(col).all() and float(col.mean()) > 0.01
 
 
 def test_invalid_argument_combinations(gsb_lib, cuda_device):
