@@ -115,19 +115,18 @@ __device__ __forceinline__ TileRect tile_rect(float px, float py, int radius, ui
   return r;
 }
 
-// Exact tile test.  A pixel of tile (tx,ty) can only be blended if
+// Exact footprint test.  A pixel of the box [x0,x1] x [y0,y1] (pixel centres) can only be blended if
 //   power = -0.5*(a dx^2 + c dy^2) - b dx dy <= 0  and  opacity*exp(power) >= 1/255
 // (forward.cu:336-346), i.e. q(d) = a dx^2 + 2b dx dy + c dy^2 <= 2 ln(255*opacity).  q is convex,
 // so its minimum over the tile's pixel box is 0 if the centre lies inside and otherwise sits on
 // one of the four box edges.  A safety margin covers fp32 rounding of both evaluations; pairs
 // inside the margin are kept, so no contributing pair is ever dropped.
 // __noinline__: the counting and the emitting kernel must execute the same instructions.
-__device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, float b, float c, float two_tau,
-                                                 uint32_t tx, uint32_t ty) {
+__device__ __forceinline__ bool rect_can_contribute(float gxp, float gyp, float a, float b, float c, float two_tau,
+                                                    float x0, float y0, float x1, float y1) {
   if (!(a > 0.f && c > 0.f && a * c - b * b > 0.f)) return true;  // degenerate conic: stay conservative
-  const float x0 = (float)(tx * kTile), y0 = (float)(ty * kTile);
-  const float dx_lo = gxp - (x0 + (kTile - 1)), dx_hi = gxp - x0;
-  const float dy_lo = gyp - (y0 + (kTile - 1)), dy_hi = gyp - y0;
+  const float dx_lo = gxp - x1, dx_hi = gxp - x0;
+  const float dy_lo = gyp - y1, dy_hi = gyp - y0;
   if (dx_lo <= 0.f && dx_hi >= 0.f && dy_lo <= 0.f && dy_hi >= 0.f) return true;
   const float DX = fmaxf(fabsf(dx_lo), fabsf(dx_hi)), DY = fmaxf(fabsf(dy_lo), fabsf(dy_hi));
   const float margin = 1e-3f + 8e-6f * (a * DX * DX + c * DY * DY + 2.f * fabsf(b) * DX * DY);
@@ -142,6 +141,11 @@ __device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, 
     qmin = fminf(qmin, a * ex * ex + 2.f * b * ex * ey + c * ey * ey);
   }
   return qmin <= two_tau + margin;
+}
+__device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, float b, float c, float two_tau,
+                                                 uint32_t tx, uint32_t ty) {
+  const float x0 = (float)(tx * kTile), y0 = (float)(ty * kTile);
+  return rect_can_contribute(gxp, gyp, a, b, c, two_tau, x0, y0, x0 + (kTile - 1), y0 + (kTile - 1));
 }
 
 // Enumerates the tiles a Gaussian is binned into.  All 32 lanes of the warp must call this
@@ -723,8 +727,14 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const uint6
   if (idx == L - 1) ranges[cur].y = (uint32_t)L;
 }
 
-// forward.cu:261-374, with colour + depth carried in the shared-memory batch and an
-// expected-depth accumulator next to the colour.
+// forward.cu:261-374, re-organised:
+//  * the batch staged in shared memory carries colour and depth, so the blend loop touches no
+//    global memory, and the NEXT batch is already in flight (registers) while this one is blended;
+//  * each warp owns an 8x4 pixel block of the 16x16 tile and first asks, 32 Gaussians at a time
+//    (one per lane, exact footprint test), which ones can reach alpha >= 1/255 anywhere in its
+//    block; only those are evaluated per pixel.  Skipped Gaussians are exactly the ones every pixel
+//    of the block would `continue` past in the reference loop, so the result is bit-identical;
+//  * an expected-depth accumulator (sum z*alpha*T) runs next to the colour.
 __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __restrict__ ranges,
                                                             const uint32_t* __restrict__ point_list, int W, int H,
                                                             const float4* __restrict__ recA,
@@ -737,47 +747,78 @@ __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __rest
   __shared__ float4 sB[kTilePixels];
   __shared__ float2 sC[kTilePixels];
   const uint32_t tiles_x = (W + kTile - 1) / kTile;
-  const uint32_t lx = threadIdx.x & (kTile - 1), ly = threadIdx.x >> 4;
-  const uint32_t pix_x = blockIdx.x * kTile + lx, pix_y = blockIdx.y * kTile + ly;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // warp -> 8x4 block inside the tile: 2 blocks across, 4 down
+  const uint32_t blk_x = blockIdx.x * kTile + (warp & 1) * 8, blk_y = blockIdx.y * kTile + (warp >> 1) * 4;
+  const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
   const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
   const float pfx = (float)pix_x, pfy = (float)pix_y;
+  const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 3);
   uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
   if ((int64_t)range.y > capacity) range = make_uint2(0u, 0u);  // undersized workspace: frame is reported invalid
-  const int rounds = (range.y - range.x + kTilePixels - 1) / kTilePixels;
-  int todo = range.y - range.x;
+  const int total = range.y - range.x;
+  const int rounds = (total + kTilePixels - 1) / kTilePixels;
   bool done = !inside;
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
 
-  for (int i = 0; i < rounds; ++i, todo -= kTilePixels) {
+  // software pipeline: registers hold the next batch's records while the current one is blended
+  float4 nA = make_float4(0.f, 0.f, 0.f, 0.f), nB = nA;
+  float2 nC = make_float2(0.f, 0.f);
+  if ((int)threadIdx.x < total) {
+    const uint32_t g = point_list[range.x + threadIdx.x];
+    nA = recA[g];
+    nB = recB[g];
+    nC = recC[g];
+  }
+  for (int i = 0; i < rounds; ++i) {
+    // everyone is past the previous batch; stop if the whole tile is saturated
     if (__syncthreads_count(done) == kTilePixels) break;
-    const uint32_t slot = range.x + i * kTilePixels + threadIdx.x;
-    if (slot < range.y) {
-      const uint32_t g = point_list[slot];
-      sA[threadIdx.x] = recA[g];
-      sB[threadIdx.x] = recB[g];
-      sC[threadIdx.x] = recC[g];
-    }
+    sA[threadIdx.x] = nA;
+    sB[threadIdx.x] = nB;
+    sC[threadIdx.x] = nC;
     __syncthreads();
-    const int batch = min(kTilePixels, todo);
-    for (int j = 0; !done && j < batch; ++j) {
-      const float4 A = sA[j];
-      const float4 B = sB[j];
-      const float dx = A.x - pfx, dy = A.y - pfy;
-      const float power = -0.5f * (B.x * dx * dx + B.z * dy * dy) - B.y * dx * dy;
-      if (power > 0.0f) continue;
-      const float alpha = min(0.99f, A.w * exp(power));
-      if (alpha < 1.0f / 255.0f) continue;
-      const float test_T = T * (1 - alpha);
-      if (test_T < 0.0001f) {
-        done = true;
-        continue;
+    const int next = (i + 1) * kTilePixels + (int)threadIdx.x;
+    if (next < total) {
+      const uint32_t g = point_list[range.x + next];
+      nA = recA[g];
+      nB = recB[g];
+      nC = recC[g];
+    }
+    const int batch = min(kTilePixels, total - i * kTilePixels);
+    bool warp_done = __all_sync(0xffffffffu, done);
+    for (int c0 = 0; c0 < batch && !warp_done; c0 += 32) {
+      const int jt = c0 + lane;
+      bool hit = false;
+      if (jt < batch) {
+        const float4 A = sA[jt];
+        const float4 B = sB[jt];
+        hit = rect_can_contribute(A.x, A.y, B.x, B.y, B.z, 2.f * __logf(255.f * A.w) + 1e-3f, bx0, by0, bx1, by1);
       }
-      const float2 gb = sC[j];
-      C0 += B.w * alpha * T;
-      C1 += gb.x * alpha * T;
-      C2 += gb.y * alpha * T;
-      Dz += A.z * alpha * T;
-      T = test_T;
+      unsigned todo = __ballot_sync(0xffffffffu, hit);
+      while (todo) {
+        const int j = c0 + __ffs(todo) - 1;
+        todo &= todo - 1;
+        if (done) continue;
+        const float4 A = sA[j];
+        const float4 B = sB[j];
+        const float dx = A.x - pfx, dy = A.y - pfy;
+        const float power = -0.5f * (B.x * dx * dx + B.z * dy * dy) - B.y * dx * dy;
+        if (power > 0.0f) continue;
+        const float alpha = min(0.99f, A.w * exp(power));
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = T * (1 - alpha);
+        if (test_T < 0.0001f) {
+          done = true;
+          continue;
+        }
+        const float2 gb = sC[j];
+        C0 += B.w * alpha * T;
+        C1 += gb.x * alpha * T;
+        C2 += gb.y * alpha * T;
+        Dz += A.z * alpha * T;
+        T = test_T;
+      }
+      warp_done = __all_sync(0xffffffffu, done);
     }
   }
   if (inside) {
