@@ -282,9 +282,9 @@ def run_ours(args, cfg, rank, local, world):
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     bytes_per_launch = {  # algorithmic bytes per launch, SURVEY.md 8(d) / DESIGN.md
         "preprocess": 12 * P + 224 * mean["Pv"] + 8 * P + 40 * mean["Pv"],
-        "scan": 16 * tiles,
-        "bin_scatter": 8 * mean["R"] + 36 * mean["Pv"] + 4 * P,
-        "sort": 12 * mean["R"],
+        "depth_sort": 16 * P + 8 * P,
+        "emit": 8 * mean["R"] + 36 * mean["Pv"] + 8 * P,
+        "tile_sort": 16 * mean["R"],
         "tile_ranges": 8 * mean["R"] + 8 * tiles,
         "render": 40 * mean["R"] + 16 * W * H,
         "to_u8": 15 * W * H,

@@ -22,16 +22,19 @@
 //                expected-depth channel (sum z*alpha*T) the TSDF stage consumes.
 //
 // All kernels run on the caller's stream.
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 #include "gsb_common.h"
+#include "gsb_radix.cuh"
 
 namespace gsb {
 
 thread_local char g_error[512] = {0};
 std::atomic<uint64_t> g_launches{0};
 Profiler g_prof;
-static const char* kStageNames[kStCount] = {"preprocess", "scan", "bin_scatter", "sort", "tile_ranges",
+static const char* kStageNames[kStCount] = {"preprocess", "depth_sort", "emit", "tile_sort", "tile_ranges",
                                             "render",     "to_u8", "prepare_depth", "mark_bricks", "integrate"};
 static thread_local int64_t g_required_instances = 0;
 
@@ -148,17 +151,18 @@ __device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, 
   return rect_can_contribute(gxp, gyp, a, b, c, two_tau, x0, y0, x0 + (kTile - 1), y0 + (kTile - 1));
 }
 
-// Enumerates the tiles a Gaussian is binned into.  All 32 lanes of the warp must call this
-// together (`active` false for idle lanes).  Small rectangles are walked by their own lane; large
-// ones are processed by the whole warp, one Gaussian at a time, so a few huge splats do not
-// serialise behind a single lane.  f(tile_id, payload0, payload1) is invoked once per kept tile;
-// the return value is the number of kept tiles of THIS lane's Gaussian.
+// Enumerates the tiles a Gaussian is binned into, in ascending tile order.  All 32 lanes of the
+// warp must call this together (`active` false for idle lanes).  Small rectangles are walked by
+// their own lane; large ones are processed by the whole warp, one Gaussian at a time, so a few
+// huge splats do not serialise behind a single lane.  f(tile_id, ordinal, payload0, payload1) is
+// invoked once per kept tile (ordinal = 0,1,2.. in tile order); returns this lane's kept count.
 constexpr uint32_t kCoopTiles = 24;
 template <typename F>
 __device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, float py, float ca, float cb, float cc,
                                                          float opacity, int radius, uint32_t gx, uint32_t gy, bool exact,
                                                          uint32_t pay0, uint32_t pay1, F&& f) {
   const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   TileRect rc{0, 0, 0, 0};
   uint32_t w = 0, area = 0, kept = 0;
   float two_tau = 0.f;
@@ -173,7 +177,7 @@ __device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, 
     for (uint32_t ty = rc.y0; ty < rc.y1; ++ty)
       for (uint32_t tx = rc.x0; tx < rc.x1; ++tx)
         if (!exact || tile_can_contribute(px, py, ca, cb, cc, two_tau, tx, ty)) {
-          f(ty * gx + tx, pay0, pay1);
+          f(ty * gx + tx, kept, pay0, pay1);
           ++kept;
         }
   }
@@ -197,8 +201,9 @@ __device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, 
         tile = ty * gx + tx;
         keep = !exact || tile_can_contribute(spx, spy, sa, sb, sc, st, tx, ty);
       }
-      if (keep) f(tile, sp0, sp1);
-      cnt += __popc(__ballot_sync(0xffffffffu, keep));
+      const unsigned votes = __ballot_sync(0xffffffffu, keep);
+      if (keep) f(tile, cnt + __popc(votes & lt_mask), sp0, sp1);
+      cnt += __popc(votes);
     }
     if (lane == src) kept = cnt;
   }
@@ -228,7 +233,8 @@ struct PreParams {
   uint32_t* tiles;
   int* radii;
   unsigned long long* ref_count;  // sum of reference tile rectangles
-  uint32_t* tile_count;           // per-tile instance counters (NULL on the validation path)
+  uint32_t* depth_keys;           // view-depth sort key per Gaussian (0xffffffff = not binned)
+  uint32_t* ids;                  // identity permutation, the sort's payload
 };
 
 struct WarpStage {  // one warp's staged parameter block; every member offset is a multiple of 128 B
@@ -399,15 +405,10 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
       }
     }
   }
-  // binning, pass 1: count this Gaussian's tiles (and the per-tile totals the scatter pass needs)
-  {
-    uint32_t* tc = p.tile_count;
-    ntiles = for_each_binned_tile(visible, px, py, ca, cb, cc, opacity, radius, p.gx, p.gy,
-                                  (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, 0u, 0u,
-                                  [tc](uint32_t tile, uint32_t, uint32_t) {
-                                    if (tc) atomicAdd(tc + tile, 1u);
-                                  });
-  }
+  // binning, pass 1: how many tiles this Gaussian is binned into
+  ntiles = for_each_binned_tile(visible, px, py, ca, cb, cc, opacity, radius, p.gx, p.gy,
+                                (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, 0u, 0u,
+                                [](uint32_t, uint32_t, uint32_t, uint32_t) {});
 
   // ---- stage 2: colour.  The 6 KB SH block is fetched only if some lane needs it -------------
   float cr = 0.f, cg = 0.f, cbl = 0.f;
@@ -485,6 +486,10 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
     }
     p.tiles[idx] = ntiles;
     p.radii[idx] = radius;
+    if (p.depth_keys) {
+      p.depth_keys[idx] = ntiles ? __float_as_uint(zv) : 0xffffffffu;  // z_view > 0.2: bit order == float order
+      p.ids[idx] = (uint32_t)idx;
+    }
   }
   unsigned long long wsum = nref;
 #pragma unroll
@@ -526,187 +531,131 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const float4
 }
 
 // ---------------------------------------------------------------------------------------------
-// Binned pipeline (default): per-tile counts -> exclusive scan -> scatter into per-tile segments
-// -> per-tile sort by (depth bits, Gaussian index).  Equivalent to the reference's global stable
-// radix sort on (tile, depth) of keys emitted in Gaussian order (rasterizer_impl.cu:88-107,303),
-// without sorting the tile bits, without a P-sized scan and without a host round trip.
+// Default binning pipeline: depth-sort the P Gaussians, emit their (tile, id) instances in that
+// order, then split the instance stream by tile with a STABLE sort on the tile id alone.  Inside
+// every tile the order is (depth bits, Gaussian index) ascending -- exactly what the reference's
+// global stable radix sort on tile|depth keys emitted in Gaussian order produces
+// (rasterizer_impl.cu:88-107,303) -- but the R-sized stream is sorted on <= 16 bits instead of 45,
+// and nothing waits for the host.
+// counters (unsigned long long[8]): [0] reference instance count  [1] binned instances R
+//                                   [2] overflow flag (R > capacity)
 // ---------------------------------------------------------------------------------------------
-// counters layout (unsigned long long[8]): [0] reference instance count  [1] binned instances
-// [2] overflow flag  [3] big-tile count
-__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ tile_count, uint32_t ntiles,
-                                                         uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
-                                                         unsigned long long* __restrict__ counters, int64_t capacity) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 8;
+constexpr int kScanBlock = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_reduce_sum_1024(uint32_t v, uint32_t* smem32) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) smem32[threadIdx.x >> 5] = v;
   __syncthreads();
-  for (uint32_t base = 0; base < ntiles; base += 1024) {
-    const uint32_t t = base + threadIdx.x;
-    const uint32_t c = t < ntiles ? tile_count[t] : 0u;
-    uint32_t incl = c;
+  uint32_t t = smem32[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  return t;  // every thread holds the block total
+}
+
+// tiles-per-Gaussian in depth-sorted order: per-block sums
+__global__ void __launch_bounds__(kScanThreads) sorted_block_sums_kernel(int P, const uint32_t* __restrict__ ids_sorted,
+                                                                        const uint32_t* __restrict__ tiles,
+                                                                        uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t red[32];
+  uint32_t sum = 0;
+  const int base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (base + k < P) sum += tiles[ids_sorted[base + k]];
+  sum = block_reduce_sum_1024(sum, red);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = sum;
+}
+
+// exclusive offsets in depth-sorted order; the last block publishes R and the overflow flag
+__global__ void __launch_bounds__(kScanThreads) sorted_offsets_kernel(int P, const uint32_t* __restrict__ ids_sorted,
+                                                                     const uint32_t* __restrict__ tiles,
+                                                                     const uint32_t* __restrict__ block_sums,
+                                                                     uint32_t* __restrict__ offsets,
+                                                                     unsigned long long* __restrict__ counters,
+                                                                     int64_t capacity) {
+  __shared__ uint32_t red[32];
+  __shared__ uint32_t warp_sums[32];
+  uint32_t prev = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += kScanThreads) prev += block_sums[b];
+  const uint32_t block_base = block_reduce_sum_1024(prev, red);
+  const int base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t tsum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = base + k < P ? tiles[ids_sorted[base + k]] : 0u;
+    tsum += v[k];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t ws = warp_sums[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+      const uint32_t u = __shfl_up_sync(0xffffffffu, ws, o);
+      if (lane >= o) ws += u;
     }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t ws = warp_sums[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, ws, o);
-        if (lane >= o) ws += v;
-      }
-      warp_sums[lane] = ws;
-    }
-    __syncthreads();
-    const uint32_t start = carry + (warp ? warp_sums[warp - 1] : 0u) + incl - c;
-    if (t < ntiles) {
-      ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);  // untouched tiles stay (0,0)
-      cursor[t] = start;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = start + c;
-    __syncthreads();
+    warp_sums[lane] = ws;
   }
-  if (threadIdx.x == 0) {
-    counters[1] = carry;
-    if ((int64_t)carry > capacity) counters[2] = 1;
+  __syncthreads();
+  uint32_t run = block_base + (warp ? warp_sums[warp - 1] : 0u) + incl - tsum;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < P) offsets[base + k] = run;
+    run += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) {
+    counters[1] = run;
+    if ((int64_t)run > capacity) counters[2] = 1;
   }
 }
 
-__global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const float4* __restrict__ recA,
-                                                                const float4* __restrict__ recB,
-                                                                const uint32_t* __restrict__ tiles,
-                                                                const int* __restrict__ radii, uint32_t gx, uint32_t gy,
-                                                                uint32_t flags, int64_t capacity,
-                                                                uint32_t* __restrict__ cursor,
-                                                                uint64_t* __restrict__ keys) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = idx < P && tiles[idx] != 0;
+// thread k = k-th Gaussian in depth order; writes its (tile id, Gaussian id) instances at its offset
+__global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t* __restrict__ ids_sorted,
+                                                          const uint32_t* __restrict__ offsets,
+                                                          const float4* __restrict__ recA, const float4* __restrict__ recB,
+                                                          const uint32_t* __restrict__ tiles, const int* __restrict__ radii,
+                                                          uint32_t gx, uint32_t gy, uint32_t flags, int64_t capacity,
+                                                          const unsigned long long* __restrict__ counters,
+                                                          uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool fits = counters[2] == 0;
+  uint32_t gid = 0, off = 0;
+  bool active = false;
+  if (k < P && fits) {
+    gid = ids_sorted[k];
+    active = tiles[gid] != 0;
+    off = offsets[k];
+  }
   float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
   int radius = 0;
   if (active) {
-    A = recA[idx];
-    B = recB[idx];
-    radius = radii[idx];
+    A = recA[gid];
+    B = recB[gid];
+    radius = radii[gid];
   }
-  for_each_binned_tile(active, A.x, A.y, B.x, B.y, B.z, A.w, radius, gx, gy, (flags & GSB_RASTER_EXACT_TILE_CULL) != 0,
-                       __float_as_uint(A.z), (uint32_t)idx, [=](uint32_t tile, uint32_t depth_bits, uint32_t gid) {
-                         const uint32_t pos = atomicAdd(cursor + tile, 1u);
-                         if ((int64_t)pos < capacity) keys[pos] = ((uint64_t)depth_bits << 32) | gid;
+  (void)capacity;
+  for_each_binned_tile(active, A.x, A.y, B.x, B.y, B.z, A.w, radius, gx, gy, (flags & GSB_RASTER_EXACT_TILE_CULL) != 0, off,
+                       gid, [=](uint32_t tile, uint32_t ordinal, uint32_t base_off, uint32_t g) {
+                         tile_keys[base_off + ordinal] = tile;
+                         tile_vals[base_off + ordinal] = g;
                        });
 }
 
-constexpr int kSortThreads = 256;
-constexpr uint32_t kSortSmall = 4096;  // keys sorted in static shared memory (32 KB)
-
-// In-place bitonic sort of n2 (power of two) 64-bit keys in shared memory by the whole CTA.
-__device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, uint32_t n2, int tid, int nthreads) {
-  for (uint32_t k = 2; k <= n2; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = tid; i < (n2 >> 1); i += nthreads) {
-        const uint32_t a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-        const uint32_t b = a | j;
-        const uint64_t ka = s[a], kb = s[b];
-        const bool up = (a & k) == 0;
-        if ((ka > kb) == up) {
-          s[a] = kb;
-          s[b] = ka;
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// One CTA per tile: sort the tile's (depth bits << 32 | gaussian) keys, emit the Gaussian ids.
-// Tiles with more than kSortSmall instances are queued for tile_sort_big_kernel.
-__global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint2* __restrict__ ranges,
-                                                                const uint64_t* __restrict__ keys, int64_t capacity,
-                                                                uint32_t* __restrict__ point_list,
-                                                                uint32_t* __restrict__ big_tiles,
-                                                                unsigned long long* __restrict__ counters) {
-  __shared__ uint64_t s[kSortSmall];
-  const uint32_t tile = blockIdx.x;
-  const uint2 r = ranges[tile];
-  if (r.y <= r.x || (int64_t)r.y > capacity) return;
-  const uint32_t n = r.y - r.x;
-  if (n > kSortSmall) {
-    if (threadIdx.x == 0) big_tiles[atomicAdd(&counters[3], 1ull)] = tile;
-    return;
-  }
-  uint32_t n2 = 1;
-  while (n2 < n) n2 <<= 1;
-  for (uint32_t i = threadIdx.x; i < n2; i += kSortThreads) s[i] = i < n ? keys[r.x + i] : ~0ull;
-  __syncthreads();
-  bitonic_sort_smem(s, n2, threadIdx.x, kSortThreads);
-  for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) point_list[r.x + i] = (uint32_t)s[i];
-}
-
-constexpr int kBigThreads = 1024;
-constexpr uint32_t kBigChunk = 16384;  // keys per shared-memory chunk (128 KB dynamic)
-
-// Rare path: tiles with more instances than fit the small sorter.  Chunks are bitonic-sorted in
-// shared memory, then merged pairwise in global memory (rank by binary search; keys are unique).
-__global__ void __launch_bounds__(kBigThreads) tile_sort_big_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ keys,
-                                                                   uint64_t* __restrict__ tmp, uint32_t* __restrict__ point_list,
-                                                                   const uint32_t* __restrict__ big_tiles,
-                                                                   const unsigned long long* __restrict__ counters) {
-  extern __shared__ uint64_t sbig[];
-  const uint32_t nbig = (uint32_t)counters[3];
-  for (uint32_t bt = blockIdx.x; bt < nbig; bt += gridDim.x) {
-    const uint2 r = ranges[big_tiles[bt]];
-    const uint32_t n = r.y - r.x;
-    uint64_t* in = keys + r.x;
-    uint64_t* out = tmp + r.x;
-    for (uint32_t c0 = 0; c0 < n; c0 += kBigChunk) {
-      const uint32_t len = min(kBigChunk, n - c0);
-      uint32_t n2 = 1;
-      while (n2 < len) n2 <<= 1;
-      for (uint32_t i = threadIdx.x; i < n2; i += kBigThreads) sbig[i] = i < len ? in[c0 + i] : ~0ull;
-      __syncthreads();
-      bitonic_sort_smem(sbig, n2, threadIdx.x, kBigThreads);
-      for (uint32_t i = threadIdx.x; i < len; i += kBigThreads) in[c0 + i] = sbig[i];
-      __syncthreads();
-    }
-    for (uint32_t width = kBigChunk; width < n; width <<= 1) {
-      for (uint32_t i = threadIdx.x; i < n; i += kBigThreads) {
-        const uint32_t pair0 = i / (2 * width) * (2 * width);
-        const uint32_t mid = min(pair0 + width, n), end = min(pair0 + 2 * width, n);
-        const uint64_t key = in[i];
-        // rank of `key` inside the other run of its pair
-        uint32_t lo, hi, self_off;
-        if (i < mid) {
-          lo = mid;
-          hi = end;
-          self_off = i - pair0;
-        } else {
-          lo = pair0;
-          hi = mid;
-          self_off = i - mid;
-        }
-        const uint32_t lo0 = lo;
-        while (lo < hi) {
-          const uint32_t m = (lo + hi) >> 1;
-          if (in[m] < key)
-            lo = m + 1;
-          else
-            hi = m;
-        }
-        out[pair0 + self_off + (lo - lo0)] = key;
-      }
-      __syncthreads();
-      uint64_t* t = in;
-      in = out;
-      out = t;
-      __threadfence_block();
-    }
-    for (uint32_t i = threadIdx.x; i < n; i += kBigThreads) point_list[r.x + i] = (uint32_t)in[i];
-    __syncthreads();
-  }
+__global__ void __launch_bounds__(256) init_ranges_kernel(uint2* __restrict__ ranges, uint32_t ntiles) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ntiles) ranges[t] = make_uint2(0xffffffffu, 0u);  // atomicMin / atomicMax targets; y <= x means empty
 }
 
 // rasterizer_impl.cu:116-138
@@ -755,7 +704,7 @@ __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __rest
   const float pfx = (float)pix_x, pfy = (float)pix_y;
   const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 3);
   uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
-  if ((int64_t)range.y > capacity) range = make_uint2(0u, 0u);  // undersized workspace: frame is reported invalid
+  if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);  // empty tile / invalid frame
   const int total = range.y - range.x;
   const int rounds = (total + kTilePixels - 1) / kTilePixels;
   bool done = !inside;
@@ -838,7 +787,7 @@ __global__ void write_counts_kernel(const uint32_t* __restrict__ offsets, int P,
   out[0] = offsets ? (P > 0 ? (int64_t)offsets[P - 1] : 0) : (int64_t)counters[1];
   out[1] = (int64_t)counters[0];
   out[2] = (int64_t)counters[2];
-  out[3] = (int64_t)counters[3];
+  out[3] = 0;
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means,
@@ -887,9 +836,14 @@ struct Workspace {
   int* radii;
   unsigned long long* counters;  // [0] reference instance count
   uint2* ranges;
-  uint32_t* tile_count;
-  uint32_t* cursor;
-  uint32_t* big_tiles;
+  uint32_t* depth_a;
+  uint32_t* depth_b;
+  uint32_t* ids_a;
+  uint32_t* ids_b;
+  uint32_t* sorted_offsets;
+  uint32_t* block_sums;
+  uint32_t* radix_table;
+  uint32_t* radix_totals;
   uint64_t* keys_in;
   uint64_t* keys_out;
   uint32_t* vals_in;
@@ -914,9 +868,17 @@ Workspace carve(void* base, int32_t P, int32_t W, int32_t H, int64_t R) {
   w.radii = c.take<int>(Pn);
   w.counters = c.take<unsigned long long>(8);
   w.ranges = c.take<uint2>(ntiles);
-  w.tile_count = c.take<uint32_t>(ntiles);
-  w.cursor = c.take<uint32_t>(ntiles);
-  w.big_tiles = c.take<uint32_t>(ntiles);
+  w.depth_a = c.take<uint32_t>(Pn);
+  w.depth_b = c.take<uint32_t>(Pn);
+  w.ids_a = c.take<uint32_t>(Pn);
+  w.ids_b = c.take<uint32_t>(Pn);
+  w.sorted_offsets = c.take<uint32_t>(Pn);
+  w.block_sums = c.take<uint32_t>((Pn + kScanBlock - 1) / kScanBlock + 1);
+  {
+    const size_t nb = (std::max(Pn, Rn) + kRdxBlock - 1) / kRdxBlock;
+    w.radix_table = c.take<uint32_t>((size_t)kRdxBins * nb);
+    w.radix_totals = c.take<uint32_t>(kRdxBins);
+  }
   w.keys_in = c.take<uint64_t>(Rn);
   w.keys_out = c.take<uint64_t>(Rn);
   w.vals_in = c.take<uint32_t>(Rn);
@@ -1047,9 +1009,9 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
 
   const bool use_cub = (a->flags & GSB_RASTER_CUB_SORT) != 0;
   const size_t ntiles = (size_t)gx * gy;
-  pp.tile_count = use_cub ? nullptr : ws.tile_count;
+  pp.depth_keys = use_cub ? nullptr : ws.depth_a;
+  pp.ids = use_cub ? nullptr : ws.ids_a;
   GSB_CUDA_OK(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream));
-  if (!use_cub) GSB_CUDA_OK(cudaMemsetAsync(ws.tile_count, 0, ntiles * sizeof(uint32_t), stream));
   const int pre_blocks = (P + kPreThreads - 1) / kPreThreads;
   {
     StageTimer tm(kStPreprocess, stream);
@@ -1104,40 +1066,47 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     }
     point_list = ws.vals_out;
   } else {
-    // ---- binned pipeline: no P-sized scan, no tile bits in the sort, no host round trip
+    // ---- default pipeline: depth-sort P, emit in that order, stable split by tile; nothing waits
+    const RadixScratch rs{ws.radix_table, ws.radix_totals};
+    uint64_t nl = 0;
+    const uint32_t* ids_sorted;
     {
       StageTimer tm(kStScan, stream);
-      tile_scan_kernel<<<1, 1024, 0, stream>>>(ws.tile_count, (uint32_t)ntiles, ws.ranges, ws.cursor, ws.counters, cap);
+      const int which = radix_sort_pairs(ws.depth_a, ws.ids_a, ws.depth_b, ws.ids_b, (uint32_t)P, nullptr, 0, (size_t)P, 32, rs,
+                                         nullptr, stream, &nl);
+      ids_sorted = which ? ws.ids_b : ws.ids_a;
+      const int sblocks = (P + kScanBlock - 1) / kScanBlock;
+      sorted_block_sums_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, ids_sorted, ws.tiles, ws.block_sums);
+      sorted_offsets_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, ids_sorted, ws.tiles, ws.block_sums, ws.sorted_offsets,
+                                                                 ws.counters, cap);
+      nl += 2;
     }
-    count_launch();
-    if ((rc = check_launch("tile_scan_kernel", stream, dbg))) return rc;
+    if ((rc = check_launch("depth sort / offsets", stream, dbg))) return rc;
+    // tile-id sort buffers alias the 64-bit key arrays of the validation path
+    uint32_t* tk_a = reinterpret_cast<uint32_t*>(ws.keys_in);
+    uint32_t* tv_a = tk_a + cap;
+    uint32_t* tk_b = reinterpret_cast<uint32_t*>(ws.keys_out);
+    uint32_t* tv_b = tk_b + cap;
     {
       StageTimer tm(kStEmit, stream);
-      scatter_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ws.recA, ws.recB, ws.tiles, pp.radii, gx, gy, a->flags,
-                                                                    cap, ws.cursor, ws.keys_in);
+      emit_sorted_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ids_sorted, ws.sorted_offsets, ws.recA, ws.recB, ws.tiles,
+                                                              pp.radii, gx, gy, a->flags, cap, ws.counters, tk_a, tv_a);
+      init_ranges_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream>>>(ws.ranges, (uint32_t)ntiles);
+      nl += 2;
     }
-    count_launch();
-    if ((rc = check_launch("scatter_instances_kernel", stream, dbg))) return rc;
+    if ((rc = check_launch("emit_sorted_kernel", stream, dbg))) return rc;
     {
       StageTimer tm(kStSort, stream);
-      tile_sort_kernel<<<(unsigned)ntiles, kSortThreads, 0, stream>>>(ws.ranges, ws.keys_in, cap, ws.vals_out, ws.big_tiles,
-                                                                     ws.counters);
-      static bool big_attr_set = false;
-      if (!big_attr_set) {
-        GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(kBigChunk * sizeof(uint64_t))));
-        big_attr_set = true;
-      }
-      tile_sort_big_kernel<<<64, kBigThreads, kBigChunk * sizeof(uint64_t), stream>>>(ws.ranges, ws.keys_in, ws.keys_out,
-                                                                                     ws.vals_out, ws.big_tiles, ws.counters);
+      const int bits = (int)higher_msb((uint32_t)ntiles);
+      const int which = radix_sort_pairs(tk_a, tv_a, tk_b, tv_b, 0u, ws.counters, cap, (size_t)cap, bits, rs, ws.ranges, stream, &nl);
+      point_list = which ? tv_b : tv_a;
     }
-    count_launch(2);
-    if ((rc = check_launch("tile_sort_kernel", stream, dbg))) return rc;
+    count_launch(nl);
+    if ((rc = check_launch("tile sort", stream, dbg))) return rc;
     if (a->num_rendered) {
       write_counts_kernel<<<1, 1, 0, stream>>>(nullptr, P, ws.counters, a->num_rendered);
       count_launch();
     }
-    point_list = ws.vals_out;
   }
   {
     StageTimer tm(kStRender, stream);

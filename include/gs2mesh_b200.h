@@ -75,7 +75,8 @@ int gsb_profile_collect(double* total_ms, uint64_t* samples, int n_stages);
                                          (auxiliary.h:166-173)                                 */
 #define GSB_RASTER_CUB_SORT 8u        /* validation only: the reference's pipeline shape (P-sized scan,
                                          cub::DeviceRadixSort on tile|depth keys, host read of the
-                                         instance count) instead of the in-library binned sort     */
+                                         instance count) instead of the in-library depth-presort +
+                                         stable tile split                                      */
 #define GSB_RASTER_ASYNC 16u          /* never wait for the stream: an undersized workspace is then
                                          reported through num_rendered[2] instead of the return
                                          value                                                 */
@@ -111,7 +112,7 @@ typedef struct GsbRasterArgs {
   /* num_rendered: int64[4] written asynchronously on `stream` (device or pinned host memory);
      [0] = instances actually binned, [1] = reference-equivalent count (sum of tile rectangles,
      what rasterize_points.cu:114 returns), [2] = 1 if the frame needed more than max_instances
-     (outputs invalid), [3] = tiles that took the large-tile sort path.  May be NULL.       */
+     (outputs invalid), [3] = reserved (0).  May be NULL.                                  */
   int64_t* num_rendered;
   /* caller-owned scratch */
   void* workspace;             /* device, >= gsb_raster_workspace_bytes(...)        */

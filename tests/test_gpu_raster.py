@@ -146,13 +146,13 @@ def test_exact_tile_cull_is_bit_identical_to_rectangle_binning(gsb_lib, cuda_dev
 
 
 def test_binned_sort_equals_reference_shaped_sort(gsb_lib, cuda_device):
-    """Default pipeline (per-tile counts, scatter, per-tile bitonic sort on (depth, index)) against the
-    validation path that keeps the reference's shape (global stable radix sort on (tile, depth) of keys
-    emitted in Gaussian order): identical blend order => bit-identical images.  The dense cases push
-    single tiles past the shared-memory sorter (4096) and past one merge chunk (16384)."""
+    """Default pipeline (depth-sort the P Gaussians, emit instances in that order, stable radix split on
+    the tile id) against the validation path that keeps the reference's shape (global stable radix sort on
+    (tile, depth) of keys emitted in Gaussian order): identical blend order => bit-identical images.
+    The dense cases put tens of thousands of instances into single tiles."""
     from gs2mesh_b200 import _lib
 
-    for n, W, H, seed, expect_big in [(6000, 320, 240, 60, False), (20000, 96, 64, 61, True), (60000, 64, 48, 62, True)]:
+    for n, W, H, seed in [(6000, 320, 240, 60), (20000, 96, 64, 61), (60000, 64, 48, 62), (5, 40, 40, 63), (4097, 1000, 30, 64)]:
         g, vt = _case(n, W, H, seed=seed)
         inp = _np_inputs(g, vt)
         for cull in (0, _lib.RASTER_EXACT_TILE_CULL):
@@ -162,7 +162,6 @@ def test_binned_sort_equals_reference_shaped_sort(gsb_lib, cuda_device):
                 np.testing.assert_array_equal(ref[k], new[k], err_msg=f"{k} n={n} cull={cull}")
             np.testing.assert_array_equal(ref["counts"][:2], new["counts"][:2])
             assert new["counts"][2] == 0
-            assert (new["counts"][3] > 0) == expect_big, new["counts"]
 
 
 def test_async_mode_reports_overflow_in_status_word(gsb_lib, cuda_device):
