@@ -18,6 +18,7 @@ RASTER_NO_TMA = 2
 RASTER_DEBUG_SYNC = 4
 RASTER_CUB_SORT = 8
 RASTER_ASYNC = 16
+RASTER_FAST_EXP = 32
 
 BRICK = 16
 BRICK_VOXELS = 4096

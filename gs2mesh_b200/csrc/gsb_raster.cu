@@ -125,30 +125,56 @@ __device__ __forceinline__ TileRect tile_rect(float px, float py, int radius, ui
 // one of the four box edges.  A safety margin covers fp32 rounding of both evaluations; pairs
 // inside the margin are kept, so no contributing pair is ever dropped.
 // __noinline__: the counting and the emitting kernel must execute the same instructions.
-__device__ __forceinline__ bool rect_can_contribute(float gxp, float gyp, float a, float b, float c, float two_tau,
-                                                    float x0, float y0, float x1, float y1) {
-  if (!(a > 0.f && c > 0.f && a * c - b * b > 0.f)) return true;  // degenerate conic: stay conservative
+struct Footprint {  // per-Gaussian constants of the test
+  float a, b, c;      // conic
+  float nb_a, nb_c;   // -b/a, -b/c: minimiser slopes along horizontal / vertical box edges
+  float two_tau;      // 2 ln(255 * opacity)
+  bool degenerate;    // non positive-definite conic: never culled
+};
+__device__ __forceinline__ Footprint make_footprint(float a, float b, float c, float two_tau) {
+  Footprint f;
+  f.a = a;
+  f.b = b;
+  f.c = c;
+  f.degenerate = !(a > 0.f && c > 0.f && a * c - b * b > 0.f);
+  f.nb_a = f.degenerate ? 0.f : -b / a;
+  f.nb_c = f.degenerate ? 0.f : -b / c;
+  f.two_tau = two_tau;
+  return f;
+}
+__device__ __forceinline__ bool rect_can_contribute(float gxp, float gyp, const Footprint& f, float x0, float y0, float x1,
+                                                    float y1) {
+  if (f.degenerate) return true;
   const float dx_lo = gxp - x1, dx_hi = gxp - x0;
   const float dy_lo = gyp - y1, dy_hi = gyp - y0;
   if (dx_lo <= 0.f && dx_hi >= 0.f && dy_lo <= 0.f && dy_hi >= 0.f) return true;
   const float DX = fmaxf(fabsf(dx_lo), fabsf(dx_hi)), DY = fmaxf(fabsf(dy_lo), fabsf(dy_hi));
-  const float margin = 1e-3f + 8e-6f * (a * DX * DX + c * DY * DY + 2.f * fabsf(b) * DX * DY);
+  const float margin = 1e-3f + 8e-6f * (f.a * DX * DX + f.c * DY * DY + 2.f * fabsf(f.b) * DX * DY);
   float qmin = 3.0e38f;
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const float dx = e ? dx_hi : dx_lo;
-    const float dy = fminf(dy_hi, fmaxf(dy_lo, -b * dx / c));
-    qmin = fminf(qmin, a * dx * dx + 2.f * b * dx * dy + c * dy * dy);
+    const float dy = fminf(dy_hi, fmaxf(dy_lo, f.nb_c * dx));
+    qmin = fminf(qmin, f.a * dx * dx + 2.f * f.b * dx * dy + f.c * dy * dy);
     const float ey = e ? dy_hi : dy_lo;
-    const float ex = fminf(dx_hi, fmaxf(dx_lo, -b * ey / a));
-    qmin = fminf(qmin, a * ex * ex + 2.f * b * ex * ey + c * ey * ey);
+    const float ex = fminf(dx_hi, fmaxf(dx_lo, f.nb_a * ey));
+    qmin = fminf(qmin, f.a * ex * ex + 2.f * f.b * ex * ey + f.c * ey * ey);
   }
-  return qmin <= two_tau + margin;
+  return qmin <= f.two_tau + margin;
 }
-__device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, float b, float c, float two_tau,
-                                                 uint32_t tx, uint32_t ty) {
+// __noinline__: the counting and the emitting kernel must execute the same instructions.
+__device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, float b, float c, float nb_a, float nb_c,
+                                                 float two_tau, uint32_t tx, uint32_t ty) {
+  Footprint f;
+  f.a = a;
+  f.b = b;
+  f.c = c;
+  f.nb_a = nb_a;
+  f.nb_c = nb_c;
+  f.two_tau = two_tau;
+  f.degenerate = false;
   const float x0 = (float)(tx * kTile), y0 = (float)(ty * kTile);
-  return rect_can_contribute(gxp, gyp, a, b, c, two_tau, x0, y0, x0 + (kTile - 1), y0 + (kTile - 1));
+  return rect_can_contribute(gxp, gyp, f, x0, y0, x0 + (kTile - 1), y0 + (kTile - 1));
 }
 
 // Enumerates the tiles a Gaussian is binned into, in ascending tile order.  All 32 lanes of the
@@ -156,7 +182,7 @@ __device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, 
 // their own lane; large ones are processed by the whole warp, one Gaussian at a time, so a few
 // huge splats do not serialise behind a single lane.  f(tile_id, ordinal, payload0, payload1) is
 // invoked once per kept tile (ordinal = 0,1,2.. in tile order); returns this lane's kept count.
-constexpr uint32_t kCoopTiles = 24;
+constexpr uint32_t kCoopTiles = 12;
 template <typename F>
 __device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, float py, float ca, float cb, float cc,
                                                          float opacity, int radius, uint32_t gx, uint32_t gy, bool exact,
@@ -165,18 +191,22 @@ __device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, 
   const uint32_t lt_mask = (1u << lane) - 1u;
   TileRect rc{0, 0, 0, 0};
   uint32_t w = 0, area = 0, kept = 0;
-  float two_tau = 0.f;
+  Footprint fp = make_footprint(1.f, 0.f, 1.f, 0.f);
+  bool test = false;
   if (active) {
     rc = tile_rect(px, py, radius, gx, gy);
     w = rc.x1 - rc.x0;
     area = w * (rc.y1 - rc.y0);
-    two_tau = exact ? 2.f * logf(255.f * opacity) : 0.f;
+    if (exact) {
+      fp = make_footprint(ca, cb, cc, 2.f * logf(255.f * opacity));
+      test = !fp.degenerate;
+    }
   }
   const bool big = active && area > kCoopTiles;
   if (active && !big) {
     for (uint32_t ty = rc.y0; ty < rc.y1; ++ty)
       for (uint32_t tx = rc.x0; tx < rc.x1; ++tx)
-        if (!exact || tile_can_contribute(px, py, ca, cb, cc, two_tau, tx, ty)) {
+        if (!test || tile_can_contribute(px, py, fp.a, fp.b, fp.c, fp.nb_a, fp.nb_c, fp.two_tau, tx, ty)) {
           f(ty * gx + tx, kept, pay0, pay1);
           ++kept;
         }
@@ -186,8 +216,10 @@ __device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, 
     const int src = __ffs(todo) - 1;
     todo &= todo - 1;
     const float spx = __shfl_sync(0xffffffffu, px, src), spy = __shfl_sync(0xffffffffu, py, src);
-    const float sa = __shfl_sync(0xffffffffu, ca, src), sb = __shfl_sync(0xffffffffu, cb, src);
-    const float sc = __shfl_sync(0xffffffffu, cc, src), st = __shfl_sync(0xffffffffu, two_tau, src);
+    const float sa = __shfl_sync(0xffffffffu, fp.a, src), sb = __shfl_sync(0xffffffffu, fp.b, src);
+    const float sc = __shfl_sync(0xffffffffu, fp.c, src), st = __shfl_sync(0xffffffffu, fp.two_tau, src);
+    const float sna = __shfl_sync(0xffffffffu, fp.nb_a, src), snc = __shfl_sync(0xffffffffu, fp.nb_c, src);
+    const bool stest = __shfl_sync(0xffffffffu, (int)test, src) != 0;
     const uint32_t sx0 = __shfl_sync(0xffffffffu, rc.x0, src), sy0 = __shfl_sync(0xffffffffu, rc.y0, src);
     const uint32_t sw = __shfl_sync(0xffffffffu, w, src), sarea = __shfl_sync(0xffffffffu, area, src);
     const uint32_t sp0 = __shfl_sync(0xffffffffu, pay0, src), sp1 = __shfl_sync(0xffffffffu, pay1, src);
@@ -199,7 +231,7 @@ __device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, 
       if (k < sarea) {
         const uint32_t ty = sy0 + k / sw, tx = sx0 + k % sw;
         tile = ty * gx + tx;
-        keep = !exact || tile_can_contribute(spx, spy, sa, sb, sc, st, tx, ty);
+        keep = !stest || tile_can_contribute(spx, spy, sa, sb, sc, sna, snc, st, tx, ty);
       }
       const unsigned votes = __ballot_sync(0xffffffffu, keep);
       if (keep) f(tile, cnt + __popc(votes & lt_mask), sp0, sp1);
@@ -519,10 +551,11 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const float4
   const TileRect rc = tile_rect(A.x, A.y, radii[idx], gx, gy);
   const uint32_t depth_bits = __float_as_uint(A.z);
   const bool exact = flags & GSB_RASTER_EXACT_TILE_CULL;
-  const float two_tau = exact ? 2.f * logf(255.f * A.w) : 0.f;
+  const Footprint fp = make_footprint(B.x, B.y, B.z, exact ? 2.f * logf(255.f * A.w) : 0.f);
+  const bool test = exact && !fp.degenerate;
   for (uint32_t ty = rc.y0; ty < rc.y1; ++ty)
     for (uint32_t tx = rc.x0; tx < rc.x1; ++tx) {
-      if (exact && !tile_can_contribute(A.x, A.y, B.x, B.y, B.z, two_tau, tx, ty)) continue;
+      if (test && !tile_can_contribute(A.x, A.y, fp.a, fp.b, fp.c, fp.nb_a, fp.nb_c, fp.two_tau, tx, ty)) continue;
       if (off >= end) return;
       keys[off] = ((uint64_t)(ty * gx + tx) << 32) | depth_bits;
       vals[off] = (uint32_t)idx;
@@ -676,14 +709,36 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t L, const uint6
   if (idx == L - 1) ranges[cur].y = (uint32_t)L;
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, const float2& v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
 // forward.cu:261-374, re-organised:
-//  * the batch staged in shared memory carries colour and depth, so the blend loop touches no
-//    global memory, and the NEXT batch is already in flight (registers) while this one is blended;
+//  * batches of 256 records (position/depth/opacity, conic/red, green/blue) are staged in a
+//    DOUBLE-buffered shared-memory ring: while batch i is blended, batch i+1 is already in the other
+//    buffer and batch i+2 is in flight in registers -> one block barrier per batch, no global
+//    access inside the blend loop;
 //  * each warp owns an 8x4 pixel block of the 16x16 tile and first asks, 32 Gaussians at a time
 //    (one per lane, exact footprint test), which ones can reach alpha >= 1/255 anywhere in its
 //    block; only those are evaluated per pixel.  Skipped Gaussians are exactly the ones every pixel
 //    of the block would `continue` past in the reference loop, so the result is bit-identical;
 //  * an expected-depth accumulator (sum z*alpha*T) runs next to the colour.
+// kFastExp: alpha = opacity * ex2.approx(power * log2 e) instead of the reference's full-precision
+// expf (forward.cu:340): ~2e-7 relative on alpha, far inside the 1e-4 parity budget.
+template <bool kFastExp>
 __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __restrict__ ranges,
                                                             const uint32_t* __restrict__ point_list, int W, int H,
                                                             const float4* __restrict__ recA,
@@ -692,9 +747,11 @@ __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __rest
                                                             const float* __restrict__ bg, float* __restrict__ out_color,
                                                             float* __restrict__ out_depth, float* __restrict__ out_T,
                                                             int64_t capacity) {
-  __shared__ float4 sA[kTilePixels];
-  __shared__ float4 sB[kTilePixels];
-  __shared__ float2 sC[kTilePixels];
+  __shared__ __align__(16) float4 sA[2][kTilePixels];
+  __shared__ __align__(16) float4 sB[2][kTilePixels];
+  __shared__ __align__(16) float2 sC[2][kTilePixels];
+  const uint32_t aA = smem_u32(&sA[0][0]), aB = smem_u32(&sB[0][0]), aC = smem_u32(&sC[0][0]);
+  constexpr uint32_t kStrideAB = kTilePixels * 16, kStrideC = kTilePixels * 8;
   const uint32_t tiles_x = (W + kTile - 1) / kTile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // warp -> 8x4 block inside the tile: 2 blocks across, 4 down
@@ -710,57 +767,64 @@ __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __rest
   bool done = !inside;
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
 
-  // software pipeline: registers hold the next batch's records while the current one is blended
   float4 nA = make_float4(0.f, 0.f, 0.f, 0.f), nB = nA;
   float2 nC = make_float2(0.f, 0.f);
-  if ((int)threadIdx.x < total) {
-    const uint32_t g = point_list[range.x + threadIdx.x];
-    nA = recA[g];
-    nB = recB[g];
-    nC = recC[g];
-  }
-  for (int i = 0; i < rounds; ++i) {
-    // everyone is past the previous batch; stop if the whole tile is saturated
-    if (__syncthreads_count(done) == kTilePixels) break;
-    sA[threadIdx.x] = nA;
-    sB[threadIdx.x] = nB;
-    sC[threadIdx.x] = nC;
-    __syncthreads();
-    const int next = (i + 1) * kTilePixels + (int)threadIdx.x;
-    if (next < total) {
-      const uint32_t g = point_list[range.x + next];
+  auto fetch = [&](int batch_index) {
+    const int slot = batch_index * kTilePixels + (int)threadIdx.x;
+    if (slot < total) {
+      const uint32_t g = point_list[range.x + slot];
       nA = recA[g];
       nB = recB[g];
       nC = recC[g];
     }
+  };
+  auto stage = [&](int buf) {
+    sts128(aA + buf * kStrideAB + threadIdx.x * 16, nA);
+    sts128(aB + buf * kStrideAB + threadIdx.x * 16, nB);
+    sts64(aC + buf * kStrideC + threadIdx.x * 8, nC);
+  };
+  if (rounds > 0) {
+    fetch(0);
+    stage(0);
+    fetch(1);
+  }
+  __syncthreads();
+  for (int i = 0; i < rounds; ++i) {
+    const int cur = i & 1;
+    if (i + 1 < rounds) {  // buffer cur^1 was released by the barrier that ended iteration i-1
+      stage(cur ^ 1);
+      fetch(i + 2);
+    }
+    const uint32_t bA = aA + cur * kStrideAB, bB = aB + cur * kStrideAB, bC = aC + cur * kStrideC;
     const int batch = min(kTilePixels, total - i * kTilePixels);
     bool warp_done = __all_sync(0xffffffffu, done);
     for (int c0 = 0; c0 < batch && !warp_done; c0 += 32) {
       const int jt = c0 + lane;
       bool hit = false;
       if (jt < batch) {
-        const float4 A = sA[jt];
-        const float4 B = sB[jt];
-        hit = rect_can_contribute(A.x, A.y, B.x, B.y, B.z, 2.f * __logf(255.f * A.w) + 1e-3f, bx0, by0, bx1, by1);
+        const float4 A = lds128(bA + jt * 16);
+        const float4 B = lds128(bB + jt * 16);
+        const Footprint fp = make_footprint(B.x, B.y, B.z, 2.f * __logf(255.f * A.w) + 1e-3f);
+        hit = rect_can_contribute(A.x, A.y, fp, bx0, by0, bx1, by1);
       }
       unsigned todo = __ballot_sync(0xffffffffu, hit);
       while (todo) {
         const int j = c0 + __ffs(todo) - 1;
         todo &= todo - 1;
         if (done) continue;
-        const float4 A = sA[j];
-        const float4 B = sB[j];
+        const float4 A = lds128(bA + j * 16);
+        const float4 B = lds128(bB + j * 16);
         const float dx = A.x - pfx, dy = A.y - pfy;
         const float power = -0.5f * (B.x * dx * dx + B.z * dy * dy) - B.y * dx * dy;
         if (power > 0.0f) continue;
-        const float alpha = min(0.99f, A.w * exp(power));
+        const float alpha = min(0.99f, A.w * (kFastExp ? __expf(power) : exp(power)));
         if (alpha < 1.0f / 255.0f) continue;
         const float test_T = T * (1 - alpha);
         if (test_T < 0.0001f) {
           done = true;
           continue;
         }
-        const float2 gb = sC[j];
+        const float2 gb = lds64(bC + j * 8);
         C0 += B.w * alpha * T;
         C1 += gb.x * alpha * T;
         C2 += gb.y * alpha * T;
@@ -769,6 +833,9 @@ __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __rest
       }
       warp_done = __all_sync(0xffffffffu, done);
     }
+    // one barrier per batch: batch i+1 is now visible, buffer `cur` may be overwritten, and the
+    // tile stops as soon as every pixel is saturated
+    if (__syncthreads_count(done) == kTilePixels) break;
   }
   if (inside) {
     const size_t pid = (size_t)pix_y * W + pix_x;
@@ -1110,8 +1177,14 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   }
   {
     StageTimer tm(kStRender, stream);
-    render_kernel<<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC,
-                                                           a->background, a->out_color, a->out_depth, a->out_final_T, cap);
+    if (a->flags & GSB_RASTER_FAST_EXP)
+      render_kernel<true><<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC,
+                                                                   a->background, a->out_color, a->out_depth,
+                                                                   a->out_final_T, cap);
+    else
+      render_kernel<false><<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC,
+                                                                    a->background, a->out_color, a->out_depth,
+                                                                    a->out_final_T, cap);
   }
   count_launch();
   if ((rc = check_launch("render_kernel", stream, dbg))) return rc;

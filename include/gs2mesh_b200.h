@@ -77,6 +77,8 @@ int gsb_profile_collect(double* total_ms, uint64_t* samples, int n_stages);
                                          cub::DeviceRadixSort on tile|depth keys, host read of the
                                          instance count) instead of the in-library depth-presort +
                                          stable tile split                                      */
+#define GSB_RASTER_FAST_EXP 32u       /* blend with ex2.approx(power*log2e) instead of full-precision
+                                         expf: ~2e-7 relative on alpha (parity budget is 1e-4)   */
 #define GSB_RASTER_ASYNC 16u          /* never wait for the stream: an undersized workspace is then
                                          reported through num_rendered[2] instead of the return
                                          value                                                 */

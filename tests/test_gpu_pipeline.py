@@ -137,7 +137,7 @@ def test_full_size_properties(gsb_lib, cuda_device):
     r.prepare_renderer()
     exact = r.render_view(0, 0, want_depth=True, want_counts=True)
     img_e, dep_e, T_e, cnt_e = (exact[k].clone() for k in ("color", "depth", "final_T", "counts"))
-    rect = r.render_view(0, 0, want_depth=True, want_counts=True, flags=0)
+    rect = r.render_view(0, 0, want_depth=True, want_counts=True, flags=_lib.RASTER_FAST_EXP)
     assert torch.equal(img_e, rect["color"]) and torch.equal(dep_e, rect["depth"]) and torch.equal(T_e, rect["final_T"])
     assert cnt_e[0] < rect["counts"][0] and cnt_e[1] == rect["counts"][0]
     assert torch.isfinite(img_e).all() and float((1 - T_e).mean()) > 0.2

@@ -222,6 +222,26 @@ def test_undersized_workspace_async_flags_frame_and_stays_in_bounds(gsb_lib, cud
     assert rc2 == _lib.GSB_OK and torch.equal(col, col2)
 
 
+def test_fast_exp_stays_inside_parity_budget(oracle, gsb_lib, cuda_device):
+    """GSB_RASTER_FAST_EXP (ex2.approx in the blend loop, the Renderer's default) vs the reference
+    rasterizer / oracle: still within 1e-4 relative with the same outlier budget."""
+    from gs2mesh_b200 import _lib
+
+    for n, W, H, seed in [(10000, 640, 480, 1), (3000, 320, 240, 0)]:
+        g, vt = _case(n, W, H, seed)
+        inp = _np_inputs(g, vt)
+        fast = _ours(cuda_device, inp, flags=_lib.RASTER_EXACT_TILE_CULL | _lib.RASTER_FAST_EXP)
+        exact = _ours(cuda_device, inp, flags=_lib.RASTER_EXACT_TILE_CULL)
+        r = compare_images(fast["color"], exact["color"])
+        assert r["frac_bad"] <= BUDGET and r["median"] <= 1e-6, r
+        if oracle.ref_available():
+            ref = _ref(oracle, cuda_device, inp)
+            _assert_parity(fast["color"], ref["color"], "fast-exp color vs reference")
+            _assert_parity(fast["final_T"], ref["final_T"], "fast-exp final_T vs reference")
+        o = oracle.forward(**inp)
+        _assert_parity(fast["depth"], o["depth"], "fast-exp depth vs oracle")
+
+
 def test_tma_staging_equals_plain_loads(gsb_lib, cuda_device):
     from gs2mesh_b200 import _lib
 
