@@ -7,9 +7,10 @@
 //   2. instances are emitted in that order (tile id, Gaussian id);
 //   3. a stable sort on the tile id alone (2 passes for <= 65536 tiles) groups them per tile while
 //      preserving the (depth, index) order inside every tile.
-// One pass = three kernels: per-block digit histograms -> row scan -> stable scatter.  The scatter
-// ranks items with warp match-any votes (stable inside a warp's contiguous segment), combines
-// the per-warp counts, stages the block's items in digit order in shared memory and writes runs.
+// A sort = one histogram kernel (all digits of all passes in a single read of the keys) + ONE
+// kernel per pass: block-local stable ranking with warp match-any votes, block offsets by chained
+// (decoupled look-back) prefix over per-block status words, items staged in digit order in shared
+// memory and written out in runs.
 #pragma once
 
 #include "gsb_common.h"
@@ -22,8 +23,12 @@ constexpr int kRdxWarps = kRdxThreads / 32;
 constexpr int kRdxItems = 16;                          // items per thread
 constexpr int kRdxBlock = kRdxThreads * kRdxItems;     // 4096 items per CTA
 constexpr int kRdxBins = 256;
+constexpr int kRdxMaxPasses = 4;
 
-// Number of items the pass works on: host value, or a device counter clamped by `capacity`
+// status word of (block, digit): [31:30] 0 = not ready, 1 = block aggregate, 2 = inclusive prefix
+constexpr uint32_t kStAgg = 1u << 30, kStIncl = 2u << 30, kStVal = (1u << 30) - 1u;
+
+// Number of items the sort works on: host value, or a device counter clamped by `capacity`
 // (0 when the frame overflowed its workspace: counters[2] != 0).
 __device__ __forceinline__ uint32_t radix_count(uint32_t n_host, const unsigned long long* counters, int64_t capacity) {
   if (counters == nullptr) return n_host;
@@ -32,88 +37,74 @@ __device__ __forceinline__ uint32_t radix_count(uint32_t n_host, const unsigned 
   return (int64_t)n > capacity ? 0u : (uint32_t)n;
 }
 
-__global__ void __launch_bounds__(kRdxThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n_host,
-                                                                const unsigned long long* __restrict__ counters,
-                                                                int64_t capacity, int shift, uint32_t nblocks,
-                                                                uint32_t* __restrict__ table) {
-  __shared__ uint32_t hist[kRdxBins];
+// Digit histograms of every pass in one read of the keys: ghist[pass][digit].
+__global__ void __launch_bounds__(kRdxThreads) radix_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n_host,
+                                                                     const unsigned long long* __restrict__ counters,
+                                                                     int64_t capacity, int passes,
+                                                                     uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t hist[kRdxMaxPasses][kRdxBins];
   const uint32_t n = radix_count(n_host, counters, capacity);
-  hist[threadIdx.x] = 0;
-  __syncthreads();
   const uint32_t base = blockIdx.x * kRdxBlock;
-  if (base < n) {
+  if (base >= n) return;
+  for (int p = 0; p < passes; ++p) hist[p][threadIdx.x] = 0;
+  __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kRdxItems; ++k) {
-      const uint32_t i = base + k * kRdxThreads + threadIdx.x;
-      if (i < n) atomicAdd(&hist[(keys[i] >> shift) & (kRdxBins - 1)], 1u);
+  for (int k = 0; k < kRdxItems; ++k) {
+    const uint32_t i = base + k * kRdxThreads + threadIdx.x;
+    if (i < n) {
+      const uint32_t key = keys[i];
+      for (int p = 0; p < passes; ++p) atomicAdd(&hist[p][(key >> (8 * p)) & (kRdxBins - 1)], 1u);
     }
   }
   __syncthreads();
-  table[threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];  // digit-major
-}
-
-// One CTA per digit: exclusive scan of the digit's per-block counts (in place), row total out.
-__global__ void __launch_bounds__(kRdxThreads) radix_scan_rows_kernel(uint32_t* __restrict__ table, uint32_t nblocks,
-                                                                     uint32_t* __restrict__ totals) {
-  __shared__ uint32_t warp_sums[kRdxWarps];
-  __shared__ uint32_t carry;
-  uint32_t* row = table + (size_t)blockIdx.x * nblocks;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (uint32_t b0 = 0; b0 < nblocks; b0 += kRdxThreads) {
-    const uint32_t i = b0 + threadIdx.x;
-    const uint32_t c = i < nblocks ? row[i] : 0u;
-    uint32_t incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0;
-#pragma unroll
-    for (int w = 0; w < kRdxWarps; ++w)
-      if (w < warp) wbase += warp_sums[w];
-    const uint32_t excl = carry + wbase + incl - c;
-    if (i < nblocks) row[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == kRdxThreads - 1) carry = excl + c;
-    __syncthreads();
+  for (int p = 0; p < passes; ++p) {
+    const uint32_t c = hist[p][threadIdx.x];
+    if (c) atomicAdd(&ghist[p * kRdxBins + threadIdx.x], c);
   }
-  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
-// Stable scatter of one pass.  When `ranges` != NULL this is the last pass of the tile sort:
-// keys are then fully sorted tile ids and the first / last instance of every tile seen by the
-// block updates ranges[tile] = (start, end) with atomicMin / atomicMax.
-__global__ void __launch_bounds__(kRdxThreads) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
-                                                                   const uint32_t* __restrict__ vals_in,
-                                                                   uint32_t* __restrict__ keys_out,
-                                                                   uint32_t* __restrict__ vals_out, uint32_t n_host,
-                                                                   const unsigned long long* __restrict__ counters,
-                                                                   int64_t capacity, int shift, uint32_t nblocks,
-                                                                   const uint32_t* __restrict__ table,
-                                                                   const uint32_t* __restrict__ totals,
-                                                                   uint2* __restrict__ ranges) {
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One stable pass.  `ghist` = this pass's 256 global digit counts, `status` = [nblocks][256] words and
+// `ticket` = block-order counter, both zeroed before the sort.  When `ranges` != NULL this is the last
+// pass of the tile sort: keys are then fully sorted tile ids and the first / last instance of every
+// tile seen by the block updates ranges[tile] = (start, end) with atomicMin / atomicMax.
+__global__ void __launch_bounds__(kRdxThreads) radix_pass_kernel(const uint32_t* __restrict__ keys_in,
+                                                                const uint32_t* __restrict__ vals_in,
+                                                                uint32_t* __restrict__ keys_out,
+                                                                uint32_t* __restrict__ vals_out, uint32_t n_host,
+                                                                const unsigned long long* __restrict__ counters,
+                                                                int64_t capacity, int shift,
+                                                                const uint32_t* __restrict__ ghist,
+                                                                uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
+                                                                uint2* __restrict__ ranges) {
   __shared__ uint32_t s_key[kRdxBlock];
   __shared__ uint32_t s_val[kRdxBlock];
   __shared__ uint32_t warp_hist[kRdxWarps][kRdxBins];  // per-warp digit counts -> per-warp bases
   __shared__ uint32_t digit_start[kRdxBins];           // first local slot of each digit in this block
   __shared__ uint32_t global_off[kRdxBins];            // global output position of that slot
   __shared__ uint32_t scan_tmp[kRdxWarps];
+  __shared__ uint32_t s_bid;
 
   const uint32_t n = radix_count(n_host, counters, capacity);
-  const uint32_t base = blockIdx.x * kRdxBlock;
+  // blocks are numbered in arrival order, so every predecessor of a block is already running
+  if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+#pragma unroll
+  for (int w = 0; w < kRdxWarps; ++w) warp_hist[w][threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t bid = s_bid;
+  const uint32_t base = bid * kRdxBlock;
   if (base >= n) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t count = min((uint32_t)kRdxBlock, n - base);
-
-#pragma unroll
-  for (int w = 0; w < kRdxWarps; ++w) warp_hist[w][threadIdx.x] = 0;
-  __syncthreads();
 
   // ---- phase 1: each warp walks its contiguous 512-item segment in order and ranks its items
   uint32_t key[kRdxItems], val[kRdxItems];
@@ -136,7 +127,7 @@ __global__ void __launch_bounds__(kRdxThreads) radix_scatter_kernel(const uint32
   }
   __syncthreads();
 
-  // ---- phase 2: thread d owns digit d: per-warp bases, block digit starts, global offsets
+  // ---- phase 2: thread d owns digit d
   {
     const int d = threadIdx.x;
     uint32_t run = 0;
@@ -146,7 +137,24 @@ __global__ void __launch_bounds__(kRdxThreads) radix_scatter_kernel(const uint32
       warp_hist[w][d] = run;  // base of warp w inside digit d
       run += c;
     }
-    // exclusive scan of `run` (digit totals of this block) over the 256 digits
+    // publish this block's count of digit d, then chain back over the predecessors
+    uint32_t* my = status + (size_t)bid * kRdxBins + d;
+    st_status(my, (bid == 0 ? kStIncl : kStAgg) | run);
+    uint32_t prev = 0;
+    if (bid > 0) {
+      for (int64_t b = (int64_t)bid - 1; b >= 0; --b) {
+        const uint32_t* sp = status + (size_t)b * kRdxBins + d;
+        uint32_t sv = ld_status(sp);
+        for (uint32_t spin = 0; (sv >> 30) == 0; ++spin) {
+          if (spin > (1u << 24)) __trap();  // a predecessor never published: fail loudly instead of hanging
+          sv = ld_status(sp);
+        }
+        prev += sv & kStVal;
+        if ((sv >> 30) == 2) break;
+      }
+      st_status(my, kStIncl | (prev + run));
+    }
+    // local digit starts: exclusive scan of `run` over the 256 digits
     uint32_t incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -161,8 +169,8 @@ __global__ void __launch_bounds__(kRdxThreads) radix_scatter_kernel(const uint32
       if (w < warp) wbase += scan_tmp[w];
     digit_start[d] = wbase + incl - run;
     __syncthreads();
-    // global digit base = exclusive scan of the totals over digits, + this block's row-scanned count
-    const uint32_t tot = totals[d];
+    // global digit base: exclusive scan of the global histogram over the 256 digits
+    const uint32_t tot = ghist[d];
     uint32_t tincl = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(kRdxThreads) radix_scatter_kernel(const uint32
 #pragma unroll
     for (int w = 0; w < kRdxWarps; ++w)
       if (w < warp) tbase += scan_tmp[w];
-    global_off[d] = tbase + tincl - tot + table[(size_t)d * nblocks + blockIdx.x];
+    global_off[d] = tbase + tincl - tot + prev;
   }
   __syncthreads();
 
@@ -207,31 +215,38 @@ __global__ void __launch_bounds__(kRdxThreads) radix_scatter_kernel(const uint32
   }
 }
 
-struct RadixScratch {
-  uint32_t* table;   // [256 * nblocks]
-  uint32_t* totals;  // [256]
-};
+// Scratch words one sort needs for `max_items` items.
+inline size_t radix_scratch_words(size_t max_items) {
+  const size_t nblocks = (max_items + kRdxBlock - 1) / kRdxBlock;
+  return (size_t)kRdxMaxPasses * (kRdxBins + nblocks * kRdxBins + 1) + 64;
+}
 
 // Enqueues ceil(bits/8) stable passes sorting (keys, vals) by key bits [0, bits).  `a`/`b` are
 // ping-pong buffers; returns which buffer holds the result (0 = a, 1 = b).  n is either the host
 // value (counters == NULL) or read on the device from counters[1] (clamped by capacity).
 inline int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_host,
                             const unsigned long long* counters, int64_t capacity, size_t max_items, int bits,
-                            const RadixScratch& sc, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches) {
+                            uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches) {
   const uint32_t nblocks = (uint32_t)((max_items + kRdxBlock - 1) / kRdxBlock);
   if (nblocks == 0) return 0;
   const int passes = (bits + 7) / 8;
+  uint32_t* ghist = scratch;                                    // [kRdxMaxPasses][256]
+  uint32_t* tickets = ghist + kRdxMaxPasses * kRdxBins;          // [kRdxMaxPasses]
+  uint32_t* status = tickets + 64;                               // [passes][nblocks][256]
+  const size_t words = (size_t)kRdxMaxPasses * kRdxBins + 64 + (size_t)passes * nblocks * kRdxBins;
+  cudaMemsetAsync(scratch, 0, words * sizeof(uint32_t), stream);
+  radix_histogram_kernel<<<nblocks, kRdxThreads, 0, stream>>>(keys_a, n_host, counters, capacity, passes, ghist);
+  *launches += 1;
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
     const uint32_t* kin = cur ? keys_b : keys_a;
     const uint32_t* vin = cur ? vals_b : vals_a;
     uint32_t* kout = cur ? keys_a : keys_b;
     uint32_t* vout = cur ? vals_a : vals_b;
-    radix_hist_kernel<<<nblocks, kRdxThreads, 0, stream>>>(kin, n_host, counters, capacity, 8 * p, nblocks, sc.table);
-    radix_scan_rows_kernel<<<kRdxBins, kRdxThreads, 0, stream>>>(sc.table, nblocks, sc.totals);
-    radix_scatter_kernel<<<nblocks, kRdxThreads, 0, stream>>>(kin, vin, kout, vout, n_host, counters, capacity, 8 * p, nblocks,
-                                                              sc.table, sc.totals, p == passes - 1 ? ranges_on_last_pass : nullptr);
-    *launches += 3;
+    radix_pass_kernel<<<nblocks, kRdxThreads, 0, stream>>>(kin, vin, kout, vout, n_host, counters, capacity, 8 * p,
+                                                           ghist + p * kRdxBins, status + (size_t)p * nblocks * kRdxBins,
+                                                           tickets + p, p == passes - 1 ? ranges_on_last_pass : nullptr);
+    *launches += 1;
     cur ^= 1;
   }
   return cur;

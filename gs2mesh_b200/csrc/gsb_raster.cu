@@ -177,20 +177,18 @@ __device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, 
   return rect_can_contribute(gxp, gyp, f, x0, y0, x0 + (kTile - 1), y0 + (kTile - 1));
 }
 
-// Enumerates the tiles a Gaussian is binned into, in ascending tile order.  All 32 lanes of the
-// warp must call this together (`active` false for idle lanes).  Small rectangles are walked by
-// their own lane; large ones are processed by the whole warp, one Gaussian at a time, so a few
-// huge splats do not serialise behind a single lane.  f(tile_id, ordinal, payload0, payload1) is
-// invoked once per kept tile (ordinal = 0,1,2.. in tile order); returns this lane's kept count.
-constexpr uint32_t kCoopTiles = 12;
-template <typename F>
-__device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, float py, float ca, float cb, float cc,
-                                                         float opacity, int radius, uint32_t gx, uint32_t gy, bool exact,
-                                                         uint32_t pay0, uint32_t pay1, F&& f) {
+// Warp-flattened binning.  The candidate tiles of the warp's 32 Gaussians (rectangles of up to
+// kMaskTiles tiles) are laid end to end and tested 32 at a time with every lane busy, instead of
+// each lane looping over its own rectangle.  Returns this lane's kept-tile count; for rectangles
+// of <= kMaskTiles tiles `mask` gets one bit per rectangle tile (row-major) so the emit pass can
+// replay the decision without re-testing.  Larger rectangles are counted cooperatively.
+constexpr uint32_t kMaskTiles = 64;
+__device__ __forceinline__ uint32_t bin_gaussians_warp(bool active, float px, float py, float ca, float cb, float cc,
+                                                       float opacity, int radius, uint32_t gx, uint32_t gy, bool exact,
+                                                       uint64_t& mask) {
   const int lane = threadIdx.x & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   TileRect rc{0, 0, 0, 0};
-  uint32_t w = 0, area = 0, kept = 0;
+  uint32_t w = 0, area = 0;
   Footprint fp = make_footprint(1.f, 0.f, 1.f, 0.f);
   bool test = false;
   if (active) {
@@ -202,16 +200,55 @@ __device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, 
       test = !fp.degenerate;
     }
   }
-  const bool big = active && area > kCoopTiles;
-  if (active && !big) {
-    for (uint32_t ty = rc.y0; ty < rc.y1; ++ty)
-      for (uint32_t tx = rc.x0; tx < rc.x1; ++tx)
-        if (!test || tile_can_contribute(px, py, fp.a, fp.b, fp.c, fp.nb_a, fp.nb_c, fp.two_tau, tx, ty)) {
-          f(ty * gx + tx, kept, pay0, pay1);
-          ++kept;
-        }
+  mask = 0ull;
+  const bool small = active && area <= kMaskTiles;
+  if (small && !test) mask = area == 64 ? ~0ull : ((1ull << area) - 1ull);  // rectangle binning: everything kept
+  const uint32_t cand = (small && test) ? area : 0u;
+  uint32_t incl = cand;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
-  unsigned todo = __ballot_sync(0xffffffffu, big);
+  const uint32_t excl = incl - cand;
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  for (uint32_t w0 = 0; w0 < total; w0 += 32) {
+    const uint32_t fidx = w0 + lane;
+    // owner = number of lanes whose inclusive prefix is <= fidx (binary search over the warp)
+    int lo = 0, hi = 32;
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+      const int mid = (lo + hi) >> 1;
+      const uint32_t v = __shfl_sync(0xffffffffu, incl, mid);
+      if (v <= fidx)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    const int owner = min(lo, 31);
+    const float opx = __shfl_sync(0xffffffffu, px, owner), opy = __shfl_sync(0xffffffffu, py, owner);
+    const float oa = __shfl_sync(0xffffffffu, fp.a, owner), ob = __shfl_sync(0xffffffffu, fp.b, owner);
+    const float oc = __shfl_sync(0xffffffffu, fp.c, owner), ot = __shfl_sync(0xffffffffu, fp.two_tau, owner);
+    const float ona = __shfl_sync(0xffffffffu, fp.nb_a, owner), onc = __shfl_sync(0xffffffffu, fp.nb_c, owner);
+    const uint32_t ox0 = __shfl_sync(0xffffffffu, rc.x0, owner), oy0 = __shfl_sync(0xffffffffu, rc.y0, owner);
+    const uint32_t ow = __shfl_sync(0xffffffffu, w, owner), oex = __shfl_sync(0xffffffffu, excl, owner);
+    bool keep = false;
+    if (fidx < total) {
+      const uint32_t k = fidx - oex;
+      keep = tile_can_contribute(opx, opy, oa, ob, oc, ona, onc, ot, ox0 + k % ow, oy0 + k / ow);
+    }
+    const unsigned votes = __ballot_sync(0xffffffffu, keep);
+    // collect the votes that belong to my own rectangle
+    const uint32_t my_lo = max(excl, w0), my_hi = min(excl + cand, w0 + 32);
+    if (my_lo < my_hi) {
+      const uint32_t nbits = my_hi - my_lo;
+      const uint32_t bits = (votes >> (my_lo - w0)) & (nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u));
+      mask |= (uint64_t)bits << (my_lo - excl);
+    }
+  }
+  uint32_t kept = small ? (uint32_t)__popcll(mask) : 0u;
+  // rectangles too large for a mask: whole warp per Gaussian, count only
+  unsigned todo = __ballot_sync(0xffffffffu, active && !small);
   while (todo) {
     const int src = __ffs(todo) - 1;
     todo &= todo - 1;
@@ -222,20 +259,12 @@ __device__ __forceinline__ uint32_t for_each_binned_tile(bool active, float px, 
     const bool stest = __shfl_sync(0xffffffffu, (int)test, src) != 0;
     const uint32_t sx0 = __shfl_sync(0xffffffffu, rc.x0, src), sy0 = __shfl_sync(0xffffffffu, rc.y0, src);
     const uint32_t sw = __shfl_sync(0xffffffffu, w, src), sarea = __shfl_sync(0xffffffffu, area, src);
-    const uint32_t sp0 = __shfl_sync(0xffffffffu, pay0, src), sp1 = __shfl_sync(0xffffffffu, pay1, src);
     uint32_t cnt = 0;
     for (uint32_t base = 0; base < sarea; base += 32) {
       const uint32_t k = base + lane;
-      bool keep = false;
-      uint32_t tile = 0;
-      if (k < sarea) {
-        const uint32_t ty = sy0 + k / sw, tx = sx0 + k % sw;
-        tile = ty * gx + tx;
-        keep = !stest || tile_can_contribute(spx, spy, sa, sb, sc, sna, snc, st, tx, ty);
-      }
-      const unsigned votes = __ballot_sync(0xffffffffu, keep);
-      if (keep) f(tile, cnt + __popc(votes & lt_mask), sp0, sp1);
-      cnt += __popc(votes);
+      const bool keep =
+          k < sarea && (!stest || tile_can_contribute(spx, spy, sa, sb, sc, sna, snc, st, sx0 + k % sw, sy0 + k / sw));
+      cnt += __popc(__ballot_sync(0xffffffffu, keep));
     }
     if (lane == src) kept = cnt;
   }
@@ -267,6 +296,7 @@ struct PreParams {
   unsigned long long* ref_count;  // sum of reference tile rectangles
   uint32_t* depth_keys;           // view-depth sort key per Gaussian (0xffffffff = not binned)
   uint32_t* ids;                  // identity permutation, the sort's payload
+  uint64_t* masks;                // kept-tile bitmask of rectangles with <= 64 tiles
 };
 
 struct WarpStage {  // one warp's staged parameter block; every member offset is a multiple of 128 B
@@ -438,9 +468,9 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
     }
   }
   // binning, pass 1: how many tiles this Gaussian is binned into
-  ntiles = for_each_binned_tile(visible, px, py, ca, cb, cc, opacity, radius, p.gx, p.gy,
-                                (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, 0u, 0u,
-                                [](uint32_t, uint32_t, uint32_t, uint32_t) {});
+  uint64_t tile_mask = 0ull;
+  ntiles = bin_gaussians_warp(visible, px, py, ca, cb, cc, opacity, radius, p.gx, p.gy,
+                              (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, tile_mask);
 
   // ---- stage 2: colour.  The 6 KB SH block is fetched only if some lane needs it -------------
   float cr = 0.f, cg = 0.f, cbl = 0.f;
@@ -521,6 +551,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
     if (p.depth_keys) {
       p.depth_keys[idx] = ntiles ? __float_as_uint(zv) : 0xffffffffu;  // z_view > 0.2: bit order == float order
       p.ids[idx] = (uint32_t)idx;
+      p.masks[idx] = tile_mask;
     }
   }
   unsigned long long wsum = nref;
@@ -654,15 +685,18 @@ __global__ void __launch_bounds__(kScanThreads) sorted_offsets_kernel(int P, con
   }
 }
 
-// thread k = k-th Gaussian in depth order; writes its (tile id, Gaussian id) instances at its offset
+// thread k = k-th Gaussian in depth order; the warp writes the (tile id, Gaussian id) instances of
+// its 32 Gaussians.  Rectangles with a stored bitmask are replayed from it, flattened across the
+// warp (every lane busy, stores run along the output); larger ones are re-tested cooperatively.
 __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t* __restrict__ ids_sorted,
                                                           const uint32_t* __restrict__ offsets,
                                                           const float4* __restrict__ recA, const float4* __restrict__ recB,
                                                           const uint32_t* __restrict__ tiles, const int* __restrict__ radii,
-                                                          uint32_t gx, uint32_t gy, uint32_t flags, int64_t capacity,
-                                                          const unsigned long long* __restrict__ counters,
+                                                          const uint64_t* __restrict__ masks, uint32_t gx, uint32_t gy,
+                                                          uint32_t flags, const unsigned long long* __restrict__ counters,
                                                           uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const bool fits = counters[2] == 0;
   uint32_t gid = 0, off = 0;
   bool active = false;
@@ -673,17 +707,94 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
   }
   float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
   int radius = 0;
+  TileRect rc{0, 0, 0, 0};
+  uint32_t w = 0, area = 0;
+  uint64_t mask = 0ull;
   if (active) {
     A = recA[gid];
-    B = recB[gid];
     radius = radii[gid];
+    rc = tile_rect(A.x, A.y, radius, gx, gy);
+    w = rc.x1 - rc.x0;
+    area = w * (rc.y1 - rc.y0);
+    if (area <= kMaskTiles)
+      mask = masks[gid];
+    else
+      B = recB[gid];
   }
-  (void)capacity;
-  for_each_binned_tile(active, A.x, A.y, B.x, B.y, B.z, A.w, radius, gx, gy, (flags & GSB_RASTER_EXACT_TILE_CULL) != 0, off,
-                       gid, [=](uint32_t tile, uint32_t ordinal, uint32_t base_off, uint32_t g) {
-                         tile_keys[base_off + ordinal] = tile;
-                         tile_vals[base_off + ordinal] = g;
-                       });
+  const bool small = active && area <= kMaskTiles;
+  // ---- flattened replay of the stored masks
+  const uint32_t cand = small ? area : 0u;
+  uint32_t incl = cand;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const uint32_t excl = incl - cand;
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t mlo = (uint32_t)mask, mhi = (uint32_t)(mask >> 32);
+  for (uint32_t w0 = 0; w0 < total; w0 += 32) {
+    const uint32_t fidx = w0 + lane;
+    int lo = 0, hi = 32;
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+      const int mid = (lo + hi) >> 1;
+      const uint32_t v = __shfl_sync(0xffffffffu, incl, mid);
+      if (v <= fidx)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    const int owner = min(lo, 31);
+    const uint32_t olo = __shfl_sync(0xffffffffu, mlo, owner), ohi = __shfl_sync(0xffffffffu, mhi, owner);
+    const uint32_t ox0 = __shfl_sync(0xffffffffu, rc.x0, owner), oy0 = __shfl_sync(0xffffffffu, rc.y0, owner);
+    const uint32_t ow = __shfl_sync(0xffffffffu, w, owner), oex = __shfl_sync(0xffffffffu, excl, owner);
+    const uint32_t ooff = __shfl_sync(0xffffffffu, off, owner), ogid = __shfl_sync(0xffffffffu, gid, owner);
+    if (fidx < total) {
+      const uint32_t kk = fidx - oex;
+      const uint64_t om = ((uint64_t)ohi << 32) | olo;
+      if ((om >> kk) & 1ull) {
+        const uint32_t ordinal = (uint32_t)__popcll(om & ((1ull << kk) - 1ull));
+        tile_keys[ooff + ordinal] = (oy0 + kk / ow) * gx + ox0 + kk % ow;
+        tile_vals[ooff + ordinal] = ogid;
+      }
+    }
+  }
+  // ---- rectangles without a mask: re-test, whole warp per Gaussian, ordered by ballot
+  const bool exact = (flags & GSB_RASTER_EXACT_TILE_CULL) != 0;
+  Footprint fp = make_footprint(1.f, 0.f, 1.f, 0.f);
+  bool test = false;
+  if (active && !small && exact) {
+    fp = make_footprint(B.x, B.y, B.z, 2.f * logf(255.f * A.w));
+    test = !fp.degenerate;
+  }
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  unsigned todo = __ballot_sync(0xffffffffu, active && !small);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const float spx = __shfl_sync(0xffffffffu, A.x, src), spy = __shfl_sync(0xffffffffu, A.y, src);
+    const float sa = __shfl_sync(0xffffffffu, fp.a, src), sb = __shfl_sync(0xffffffffu, fp.b, src);
+    const float sc = __shfl_sync(0xffffffffu, fp.c, src), st = __shfl_sync(0xffffffffu, fp.two_tau, src);
+    const float sna = __shfl_sync(0xffffffffu, fp.nb_a, src), snc = __shfl_sync(0xffffffffu, fp.nb_c, src);
+    const bool stest = __shfl_sync(0xffffffffu, (int)test, src) != 0;
+    const uint32_t sx0 = __shfl_sync(0xffffffffu, rc.x0, src), sy0 = __shfl_sync(0xffffffffu, rc.y0, src);
+    const uint32_t sw = __shfl_sync(0xffffffffu, w, src), sarea = __shfl_sync(0xffffffffu, area, src);
+    const uint32_t soff = __shfl_sync(0xffffffffu, off, src), sgid = __shfl_sync(0xffffffffu, gid, src);
+    uint32_t cnt = 0;
+    for (uint32_t base = 0; base < sarea; base += 32) {
+      const uint32_t kk = base + lane;
+      const uint32_t tx = sx0 + kk % sw, ty = sy0 + kk / sw;
+      const bool keep = kk < sarea && (!stest || tile_can_contribute(spx, spy, sa, sb, sc, sna, snc, st, tx, ty));
+      const unsigned votes = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const uint32_t dst = soff + cnt + __popc(votes & lt_mask);
+        tile_keys[dst] = ty * gx + tx;
+        tile_vals[dst] = sgid;
+      }
+      cnt += __popc(votes);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) init_ranges_kernel(uint2* __restrict__ ranges, uint32_t ntiles) {
@@ -908,9 +1019,9 @@ struct Workspace {
   uint32_t* ids_a;
   uint32_t* ids_b;
   uint32_t* sorted_offsets;
+  uint64_t* masks;
   uint32_t* block_sums;
-  uint32_t* radix_table;
-  uint32_t* radix_totals;
+  uint32_t* radix_scratch;
   uint64_t* keys_in;
   uint64_t* keys_out;
   uint32_t* vals_in;
@@ -940,12 +1051,9 @@ Workspace carve(void* base, int32_t P, int32_t W, int32_t H, int64_t R) {
   w.ids_a = c.take<uint32_t>(Pn);
   w.ids_b = c.take<uint32_t>(Pn);
   w.sorted_offsets = c.take<uint32_t>(Pn);
+  w.masks = c.take<uint64_t>(Pn);
   w.block_sums = c.take<uint32_t>((Pn + kScanBlock - 1) / kScanBlock + 1);
-  {
-    const size_t nb = (std::max(Pn, Rn) + kRdxBlock - 1) / kRdxBlock;
-    w.radix_table = c.take<uint32_t>((size_t)kRdxBins * nb);
-    w.radix_totals = c.take<uint32_t>(kRdxBins);
-  }
+  w.radix_scratch = c.take<uint32_t>(radix_scratch_words(std::max(Pn, Rn)));
   w.keys_in = c.take<uint64_t>(Rn);
   w.keys_out = c.take<uint64_t>(Rn);
   w.vals_in = c.take<uint32_t>(Rn);
@@ -1078,6 +1186,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   const size_t ntiles = (size_t)gx * gy;
   pp.depth_keys = use_cub ? nullptr : ws.depth_a;
   pp.ids = use_cub ? nullptr : ws.ids_a;
+  pp.masks = ws.masks;
   GSB_CUDA_OK(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream));
   const int pre_blocks = (P + kPreThreads - 1) / kPreThreads;
   {
@@ -1134,7 +1243,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     point_list = ws.vals_out;
   } else {
     // ---- default pipeline: depth-sort P, emit in that order, stable split by tile; nothing waits
-    const RadixScratch rs{ws.radix_table, ws.radix_totals};
+    uint32_t* rs = ws.radix_scratch;
     uint64_t nl = 0;
     const uint32_t* ids_sorted;
     {
@@ -1157,7 +1266,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     {
       StageTimer tm(kStEmit, stream);
       emit_sorted_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ids_sorted, ws.sorted_offsets, ws.recA, ws.recB, ws.tiles,
-                                                              pp.radii, gx, gy, a->flags, cap, ws.counters, tk_a, tv_a);
+                                                              pp.radii, ws.masks, gx, gy, a->flags, ws.counters, tk_a, tv_a);
       init_ranges_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream>>>(ws.ranges, (uint32_t)ntiles);
       nl += 2;
     }

@@ -91,18 +91,20 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// One voxel of UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier.
-// Returns true when (tsdf, w) was updated; `pix` receives the depth-image index used.
-__device__ __forceinline__ bool fuse_voxel(const FrameParams& f, const float* __restrict__ depth, float pcx, float pcy,
-                                           float pcz, float& tsdf, float& w, float& w_before, int& pix) {
-  if (pcz <= 0.f) return false;
+// UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier, one voxel, split in two so that
+// the depth-image gathers of all of a thread's voxels can be in flight together:
+//   project_voxel: camera-space point -> packed pixel (v << 16 | u), or -1 if the voxel is skipped
+//   fuse_voxel:    depth sample -> truncated distance -> running weighted mean
+__device__ __forceinline__ int project_voxel(const FrameParams& f, float pcx, float pcy, float pcz) {
+  if (pcz <= 0.f) return -1;
   const float u_f = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(pcx, f.fx), pcz), f.cx), 0.5f);
   const float v_f = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(pcy, f.fy), pcz), f.cy), 0.5f);
-  if (!(u_f >= 0.0001f && u_f < f.safe_w && v_f >= 0.0001f && v_f < f.safe_h)) return false;
-  const int u = (int)u_f, v = (int)v_f;
-  pix = v * f.W + u;
-  const float d = __ldg(depth + pix);
-  if (d <= 0.0f) return false;
+  if (!(u_f >= 0.0001f && u_f < f.safe_w && v_f >= 0.0001f && v_f < f.safe_h)) return -1;
+  return ((int)v_f << 16) | (int)u_f;
+}
+__device__ __forceinline__ bool fuse_voxel(const FrameParams& f, int uv, float d, float pcz, float& tsdf, float& w) {
+  if (uv < 0 || d <= 0.0f) return false;
+  const int u = uv & 0xffff, v = uv >> 16;
   // CreateDepthToCameraDistanceMultiplierFloatImage, recomputed per lookup
   const float xx = __fmul_rn(__fsub_rn((float)u, f.cx), f.inv_fx);
   const float yy = __fmul_rn(__fsub_rn((float)v, f.cy), f.inv_fy);
@@ -110,7 +112,6 @@ __device__ __forceinline__ bool fuse_voxel(const FrameParams& f, const float* __
   const float sdf = __fmul_rn(__fsub_rn(d, pcz), mult);
   if (!(sdf > -f.trunc)) return false;
   const float t = fminf(1.0f, __fmul_rn(sdf, f.trunc_inv));
-  w_before = w;
   tsdf = __fdiv_rn(__fadd_rn(__fmul_rn(tsdf, w), t), __fadd_rn(w, 1.0f));
   w = __fadd_rn(w, 1.0f);
   return true;
@@ -127,11 +128,11 @@ __device__ __forceinline__ void fuse_color(float4& c, float w_before, const uint
 constexpr int kIntThreads = 256;
 constexpr int kPasses = GSB_BRICK_VOXELS / 2 / kIntThreads;  // 8 voxel-pair passes per brick
 
-__global__ void __launch_bounds__(kIntThreads) integrate_kernel(const FrameParams f, const float* __restrict__ depth,
-                                                               const uint8_t* __restrict__ rgb, float4* __restrict__ tw,
-                                                               float4* __restrict__ color,
-                                                               const uint32_t* __restrict__ list,
-                                                               const uint32_t* __restrict__ counters) {
+__global__ void __launch_bounds__(kIntThreads, 2) integrate_kernel(const FrameParams f, const float* __restrict__ depth,
+                                                                  const uint8_t* __restrict__ rgb, float4* __restrict__ tw,
+                                                                  float4* __restrict__ color,
+                                                                  const uint32_t* __restrict__ list,
+                                                                  const uint32_t* __restrict__ counters) {
   const uint32_t n = counters[0];
   const int t = threadIdx.x;
   // thread -> voxel pair: pair q = pass*256 + t, first voxel 2q = (x, y, z) with
@@ -144,12 +145,16 @@ __global__ void __launch_bounds__(kIntThreads) integrate_kernel(const FrameParam
     const double oy = (double)(f.b0[1] + by) * f.unit_length;
     const double oz = (double)(f.b0[2] + bz) * f.unit_length;
     float4* base = tw + (size_t)brick * (GSB_BRICK_VOXELS / 2);
+    // (1) all 8 (tsdf, weight) pair loads in flight
     float4 v[kPasses];
 #pragma unroll
     for (int p = 0; p < kPasses; ++p) v[p] = ld_stream(base + p * kIntThreads + t);
 
+    // (2) project all 16 voxels of this thread
     const float py = (float)((double)__fadd_rn(f.half, __fmul_rn(f.vl, (float)y)) + oy);
     const float pz = (float)((double)f.half + oz);
+    int uv[kPasses][2];
+    float cz[kPasses][2];
 #pragma unroll
     for (int p = 0; p < kPasses; ++p) {
       const int x = 2 * p + xo;
@@ -163,28 +168,51 @@ __global__ void __launch_bounds__(kIntThreads) integrate_kernel(const FrameParam
         cym = __fadd_rn(cym, f.sy);
         czm = __fadd_rn(czm, f.sz);
       }
-      float wb0 = 0.f, wb1 = 0.f;
-      int pix0 = 0, pix1 = 0;
-      const bool up0 = fuse_voxel(f, depth, cxm, cym, czm, v[p].x, v[p].y, wb0, pix0);
+      uv[p][0] = project_voxel(f, cxm, cym, czm);
+      cz[p][0] = czm;
       cxm = __fadd_rn(cxm, f.sx);
       cym = __fadd_rn(cym, f.sy);
       czm = __fadd_rn(czm, f.sz);
-      const bool up1 = fuse_voxel(f, depth, cxm, cym, czm, v[p].z, v[p].w, wb1, pix1);
-      if (up0 || up1) {
-        st_stream(base + p * kIntThreads + t, v[p]);
-        if (color != nullptr && rgb != nullptr) {
-          float4* cp = color + ((size_t)brick * GSB_BRICK_VOXELS + 2 * (size_t)(p * kIntThreads + t));
-          if (up0) {
-            float4 c = ld_stream(cp);
-            fuse_color(c, wb0, rgb, pix0);
-            st_stream(cp, c);
-          }
-          if (up1) {
-            float4 c = ld_stream(cp + 1);
-            fuse_color(c, wb1, rgb, pix1);
-            st_stream(cp + 1, c);
-          }
-        }
+      uv[p][1] = project_voxel(f, cxm, cym, czm);
+      cz[p][1] = czm;
+    }
+    // (3) all depth gathers in flight
+    float dd[kPasses][2];
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        dd[p][e] = uv[p][e] >= 0 ? __ldg(depth + (uv[p][e] >> 16) * f.W + (uv[p][e] & 0xffff)) : 0.f;
+    // (4) fuse, store the pairs that changed
+    uint32_t changed = 0;  // bit 2p+e
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p) {
+      const bool up0 = fuse_voxel(f, uv[p][0], dd[p][0], cz[p][0], v[p].x, v[p].y);
+      const bool up1 = fuse_voxel(f, uv[p][1], dd[p][1], cz[p][1], v[p].z, v[p].w);
+      if (up0 || up1) st_stream(base + p * kIntThreads + t, v[p]);
+      changed |= (up0 ? 1u : 0u) << (2 * p) | (up1 ? 1u : 0u) << (2 * p + 1);
+    }
+    // (5) colour of the voxels that changed, four passes' loads in flight at a time
+    if (color != nullptr && rgb != nullptr && changed) {
+#pragma unroll
+      for (int g = 0; g < kPasses; g += 4) {
+        float4 c[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (changed >> (2 * (g + q) + e) & 1u)
+              c[q][e] = ld_stream(color + ((size_t)brick * GSB_BRICK_VOXELS + 2 * (size_t)((g + q) * kIntThreads + t) + e));
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (changed >> (2 * (g + q) + e) & 1u) {
+              const int p = g + q;
+              const float w_new = e ? v[p].w : v[p].y;
+              fuse_color(c[q][e], __fsub_rn(w_new, 1.0f), rgb, (uv[p][e] >> 16) * f.W + (uv[p][e] & 0xffff));
+              st_stream(color + ((size_t)brick * GSB_BRICK_VOXELS + 2 * (size_t)(p * kIntThreads + t) + e), c[q][e]);
+            }
       }
     }
   }
