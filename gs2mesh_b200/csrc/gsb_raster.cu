@@ -215,7 +215,7 @@ __device__ __forceinline__ uint32_t bin_gaussians_warp(bool active, float px, fl
   for (uint32_t w0 = 0; w0 < total; w0 += 32) {
     const uint32_t fidx = w0 + lane;
     // owner = number of lanes whose inclusive prefix is <= fidx (binary search over the warp)
-    int lo = 0, hi = 32;
+    int lo = 0, hi = 31;  // the owner of a valid slot is one of the 32 lanes: 5 halvings settle it
 #pragma unroll
     for (int step = 0; step < 5; ++step) {
       const int mid = (lo + hi) >> 1;
@@ -225,7 +225,7 @@ __device__ __forceinline__ uint32_t bin_gaussians_warp(bool active, float px, fl
       else
         hi = mid;
     }
-    const int owner = min(lo, 31);
+    const int owner = lo;
     const float opx = __shfl_sync(0xffffffffu, px, owner), opy = __shfl_sync(0xffffffffu, py, owner);
     const float oa = __shfl_sync(0xffffffffu, fp.a, owner), ob = __shfl_sync(0xffffffffu, fp.b, owner);
     const float oc = __shfl_sync(0xffffffffu, fp.c, owner), ot = __shfl_sync(0xffffffffu, fp.two_tau, owner);
@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
   const uint32_t mlo = (uint32_t)mask, mhi = (uint32_t)(mask >> 32);
   for (uint32_t w0 = 0; w0 < total; w0 += 32) {
     const uint32_t fidx = w0 + lane;
-    int lo = 0, hi = 32;
+    int lo = 0, hi = 31;  // the owner of a valid slot is one of the 32 lanes: 5 halvings settle it
 #pragma unroll
     for (int step = 0; step < 5; ++step) {
       const int mid = (lo + hi) >> 1;
@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
       else
         hi = mid;
     }
-    const int owner = min(lo, 31);
+    const int owner = lo;
     const uint32_t olo = __shfl_sync(0xffffffffu, mlo, owner), ohi = __shfl_sync(0xffffffffu, mhi, owner);
     const uint32_t ox0 = __shfl_sync(0xffffffffu, rc.x0, owner), oy0 = __shfl_sync(0xffffffffu, rc.y0, owner);
     const uint32_t ow = __shfl_sync(0xffffffffu, w, owner), oex = __shfl_sync(0xffffffffu, excl, owner);
