@@ -76,7 +76,7 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
 // `ticket` = block-order counter, both zeroed before the sort.  When `ranges` != NULL this is the last
 // pass of the tile sort: keys are then fully sorted tile ids and the first / last instance of every
 // tile seen by the block updates ranges[tile] = (start, end) with atomicMin / atomicMax.
-__global__ void __launch_bounds__(kRdxThreads) radix_pass_kernel(const uint32_t* __restrict__ keys_in,
+__global__ void __launch_bounds__(kRdxThreads, 3) radix_pass_kernel(const uint32_t* __restrict__ keys_in,
                                                                 const uint32_t* __restrict__ vals_in,
                                                                 uint32_t* __restrict__ keys_out,
                                                                 uint32_t* __restrict__ vals_out, uint32_t n_host,

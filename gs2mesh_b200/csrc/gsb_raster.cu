@@ -181,11 +181,13 @@ __device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, 
 // kMaskTiles tiles) are laid end to end and tested 32 at a time with every lane busy, instead of
 // each lane looping over its own rectangle.  Returns this lane's kept-tile count; for rectangles
 // of <= kMaskTiles tiles `mask` gets one bit per rectangle tile (row-major) so the emit pass can
-// replay the decision without re-testing.  Larger rectangles are counted cooperatively.
+// replay the decision without re-testing.  Larger rectangles are counted cooperatively (and
+// re-tested by the emit pass with the same __noinline__ routine, so both passes agree).
+// `stage` = 32 x 2 float4 of per-warp shared memory the lanes publish their footprint in.
 constexpr uint32_t kMaskTiles = 64;
 __device__ __forceinline__ uint32_t bin_gaussians_warp(bool active, float px, float py, float ca, float cb, float cc,
                                                        float opacity, int radius, uint32_t gx, uint32_t gy, bool exact,
-                                                       uint64_t& mask) {
+                                                       float4* stage, uint64_t& mask) {
   const int lane = threadIdx.x & 31;
   TileRect rc{0, 0, 0, 0};
   uint32_t w = 0, area = 0;
@@ -212,9 +214,15 @@ __device__ __forceinline__ uint32_t bin_gaussians_warp(bool active, float px, fl
   }
   const uint32_t excl = incl - cand;
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  // publish what a tester needs to know about my Gaussian
+  stage[2 * lane] = make_float4(px, py, fp.a, fp.b);
+  stage[2 * lane + 1] = make_float4(fp.c, fp.nb_a, fp.nb_c, fp.two_tau);
+  const uint32_t pack0 = rc.x0 | (rc.y0 << 16);  // tile coordinates < 65536
+  const uint32_t pack1 = w | (excl << 8);          // w <= 64, excl <= 31 * 64
+  __syncwarp();
   for (uint32_t w0 = 0; w0 < total; w0 += 32) {
     const uint32_t fidx = w0 + lane;
-    // owner = number of lanes whose inclusive prefix is <= fidx (binary search over the warp)
+    // owner = first lane whose inclusive prefix exceeds fidx
     int lo = 0, hi = 31;  // the owner of a valid slot is one of the 32 lanes: 5 halvings settle it
 #pragma unroll
     for (int step = 0; step < 5; ++step) {
@@ -226,16 +234,24 @@ __device__ __forceinline__ uint32_t bin_gaussians_warp(bool active, float px, fl
         hi = mid;
     }
     const int owner = lo;
-    const float opx = __shfl_sync(0xffffffffu, px, owner), opy = __shfl_sync(0xffffffffu, py, owner);
-    const float oa = __shfl_sync(0xffffffffu, fp.a, owner), ob = __shfl_sync(0xffffffffu, fp.b, owner);
-    const float oc = __shfl_sync(0xffffffffu, fp.c, owner), ot = __shfl_sync(0xffffffffu, fp.two_tau, owner);
-    const float ona = __shfl_sync(0xffffffffu, fp.nb_a, owner), onc = __shfl_sync(0xffffffffu, fp.nb_c, owner);
-    const uint32_t ox0 = __shfl_sync(0xffffffffu, rc.x0, owner), oy0 = __shfl_sync(0xffffffffu, rc.y0, owner);
-    const uint32_t ow = __shfl_sync(0xffffffffu, w, owner), oex = __shfl_sync(0xffffffffu, excl, owner);
+    const uint32_t o0 = __shfl_sync(0xffffffffu, pack0, owner), o1 = __shfl_sync(0xffffffffu, pack1, owner);
     bool keep = false;
     if (fidx < total) {
-      const uint32_t k = fidx - oex;
-      keep = tile_can_contribute(opx, opy, oa, ob, oc, ona, onc, ot, ox0 + k % ow, oy0 + k / ow);
+      const float4 q0 = stage[2 * owner], q1 = stage[2 * owner + 1];
+      const uint32_t ow = o1 & 0xffu, k = fidx - (o1 >> 8);
+      // k / ow for k < 64, ow <= 64: (k + 0.5) / ow is never within rounding distance of an integer
+      const uint32_t row = (uint32_t)__float2int_rd(__fdividef((float)k + 0.5f, (float)ow));
+      const uint32_t tx = (o0 & 0xffffu) + (k - row * ow), ty = (o0 >> 16) + row;
+      Footprint f;
+      f.a = q0.z;
+      f.b = q0.w;
+      f.c = q1.x;
+      f.nb_a = q1.y;
+      f.nb_c = q1.z;
+      f.two_tau = q1.w;
+      f.degenerate = false;
+      const float x0 = (float)(tx * kTile), y0 = (float)(ty * kTile);
+      keep = rect_can_contribute(q0.x, q0.y, f, x0, y0, x0 + (kTile - 1), y0 + (kTile - 1));
     }
     const unsigned votes = __ballot_sync(0xffffffffu, keep);
     // collect the votes that belong to my own rectangle
@@ -468,23 +484,28 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
     }
   }
   // binning, pass 1: how many tiles this Gaussian is binned into
+  // The 6 KB SH block is only fetched when some lane survived culling; the bulk copy is issued NOW
+  // so that it lands while the warp is busy binning.
+  const bool any_visible = __any_sync(0xffffffffu, visible);
+  const int shf = p.M * 3;  // SH floats per Gaussian
+  const bool need_sh = p.colors == nullptr && any_visible;
+  const bool tma_sh = need_sh && full_tma && (shf * 4) % 16 == 0 && shf <= kMaxShFloats;
+  if (tma_sh && lane == 0) {
+    mbar_expect_tx(&st.bar, (uint32_t)(32 * shf * 4));
+    tma_load_1d(st.sh, p.shs + (size_t)base * shf, (uint32_t)(32 * shf * 4), &st.bar);
+  }
+  // the staged rotations / positions / scales are dead by now: their 1280 bytes carry the lanes'
+  // footprints during binning (32 x 2 float4 = 1024 bytes)
+  __syncwarp();
   uint64_t tile_mask = 0ull;
   ntiles = bin_gaussians_warp(visible, px, py, ca, cb, cc, opacity, radius, p.gx, p.gy,
-                              (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, tile_mask);
+                              (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, reinterpret_cast<float4*>(st.rot), tile_mask);
 
-  // ---- stage 2: colour.  The 6 KB SH block is fetched only if some lane needs it -------------
+  // ---- stage 2: colour ------------------------------------------------------------------------
   float cr = 0.f, cg = 0.f, cbl = 0.f;
-  const bool any_visible = __any_sync(0xffffffffu, visible);
   if (p.colors == nullptr) {
-    const int shf = p.M * 3;  // floats per Gaussian
     if (any_visible) {
-      const bool tma_sh = full_tma && (shf * 4) % 16 == 0 && shf <= kMaxShFloats;
       if (tma_sh) {
-        if (lane == 0) {
-          mbar_expect_tx(&st.bar, (uint32_t)(32 * shf * 4));
-          tma_load_1d(st.sh, p.shs + (size_t)base * shf, (uint32_t)(32 * shf * 4), &st.bar);
-        }
-        __syncwarp();
         mbar_wait(&st.bar, 1);
       } else {
         for (int k = lane; k < count * shf; k += 32) st.sh[k] = p.shs[(size_t)base * shf + k];

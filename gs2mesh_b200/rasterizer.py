@@ -20,7 +20,7 @@ DEFAULT_FLAGS = _lib.RASTER_EXACT_TILE_CULL
 
 
 class _Scratch:
-    """Grow-only workspace + binning capacity, one per (device, stream-agnostic)."""
+    """Grow-only workspace + binning capacity."""
 
     def __init__(self, device):
         self.device = device
@@ -45,11 +45,13 @@ _scratch = {}
 
 
 def _scratch_for(device) -> _Scratch:
+    """One scratch block per (device, stream): frames enqueued on different streams may overlap."""
     dev = torch.device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    if idx not in _scratch:
-        _scratch[idx] = _Scratch(torch.device("cuda", idx))
-    return _scratch[idx]
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    if key not in _scratch:
+        _scratch[key] = _Scratch(torch.device("cuda", idx))
+    return _scratch[key]
 
 
 def _dev_f32(t, name, device):

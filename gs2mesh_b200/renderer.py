@@ -61,6 +61,9 @@ class Renderer:
         # blend with ex2.approx instead of full-precision expf (GSB_RASTER_FAST_EXP): ~2e-7 relative on
         # alpha, parity-tested against the reference rasterizer inside the 1e-4 budget
         self.fast_exp = True
+        # render the left and the right eye on two side streams (each with its own scratch) so that the
+        # small latency-bound binning kernels of one eye overlap the other eye's blend kernel
+        self.overlap_eyes = True
         self.keep_frames = False
         self._frames = {}
         self._ready = False
@@ -147,8 +150,8 @@ class Renderer:
             raise RuntimeError(f"{len(bad)} frame(s) needed more binning scratch than calibrated ({need} instances); "
                                "capacity has been raised, render them again")
 
-    def _buffers(self, w, h):
-        key = (w, h)
+    def _buffers(self, w, h, parity=0):
+        key = (w, h, parity)
         if key not in self._bufs:
             dev = self._camera_table.device
             f32 = dict(dtype=torch.float32, device=dev)
@@ -186,19 +189,47 @@ class Renderer:
         `host_right_u8`."""
         with torch.no_grad():
             vt = self._views[camera_number][0]
-            b = self._buffers(vt.width, vt.height)
+            dev = self._camera_table.device
+            main = torch.cuda.current_stream(dev)
+            if self.overlap_eyes:
+                # outputs are double-buffered: the tensors returned by call n stay valid during call n+1
+                self._call_index = getattr(self, "_call_index", -1) + 1
+                parity = self._call_index & 1
+                if not hasattr(self, "_side_streams"):
+                    self._side_streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+                    self._entry_events = [None, None]
+                b = self._buffers(vt.width, vt.height, parity)
+                entry = torch.cuda.Event()
+                entry.record(main)
+                gate = self._entry_events[parity ^ 1]  # recorded when the previous call was entered: everything that
+                self._entry_events[parity] = entry      # consumed this buffer set was enqueued before it
+                streams = self._side_streams
+                for st in streams:
+                    if gate is not None:
+                        st.wait_event(gate)
+                    elif self._call_index == 0:
+                        st.wait_stream(main)
+            else:
+                b = self._buffers(vt.width, vt.height)
+                streams = [main, main]
             for s in range(2):
-                self.render_view(camera_number, s, want_depth=(s == 0), out_color=b["color"][s],
-                                 out_depth=b["depth"] if s == 0 else None, out_final_T=b["final_T"] if s == 0 else None,
-                                 async_mode=True)
-                rast.image_to_u8(b["color"][s], out=b["u8"][s])
+                with torch.cuda.stream(streams[s]):
+                    self.render_view(camera_number, s, want_depth=(s == 0), out_color=b["color"][s],
+                                     out_depth=b["depth"] if s == 0 else None, out_final_T=b["final_T"] if s == 0 else None,
+                                     async_mode=True)
+                    rast.image_to_u8(b["color"][s], out=b["u8"][s])
             result = dict(left=b["color"][0], right=b["color"][1], left_u8=b["u8"][0], right_u8=b["u8"][1],
                           depth=b["depth"], final_T=b["final_T"])
             to_host = self.write_images if to_host is None else to_host
             if to_host:
                 for s in range(2):
-                    b["host_u8"][s].copy_(b["u8"][s], non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                    with torch.cuda.stream(streams[s]):
+                        b["host_u8"][s].copy_(b["u8"][s], non_blocking=True)
+            if self.overlap_eyes:
+                for st in streams:
+                    main.wait_stream(st)  # device-side dependency only: later work on the caller's stream sees both eyes
+            if to_host:
+                main.synchronize()
                 self.check_status([camera_number])
                 result["host_left_u8"], result["host_right_u8"] = b["host_u8"]
             if self.write_images:

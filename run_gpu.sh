@@ -9,4 +9,4 @@ tail -2 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 50 --warmup 3 > gpurun_out/bench_ours.log 2>&1
 echo "bench exit $?" >> gpurun_out/bench_ours.log
 tail -3 gpurun_out/bench_ours.log | cut -c1-300
-bash scripts/profile_gpu.sh r01c 2 > gpurun_out/profile.log 2>&1
+if grep -q "pytest exit 0" gpurun_out/pytest_gpu.log; then bash scripts/profile_gpu.sh r01c 2 > gpurun_out/profile.log 2>&1; fi
