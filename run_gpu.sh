@@ -6,7 +6,6 @@ tail -15 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
 tail -2 gpurun_out/smoke.log
-timeout 900 python bench.py --steps 50 --warmup 3 > gpurun_out/bench_ours.log 2>&1
+timeout 900 python bench.py --steps 100 --warmup 5 > gpurun_out/bench_ours.log 2>&1
 echo "bench exit $?" >> gpurun_out/bench_ours.log
 tail -3 gpurun_out/bench_ours.log | cut -c1-300
-if grep -q "pytest exit 0" gpurun_out/pytest_gpu.log; then bash scripts/profile_gpu.sh r01c 2 > gpurun_out/profile.log 2>&1; fi
