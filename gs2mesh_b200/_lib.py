@@ -67,6 +67,10 @@ SIGNATURES = {
     "gsb_tsdf_from_sums": (C.c_int, [_vp, _vp]),
     "gsb_tsdf_export_dense": (C.c_int, [_vp, _vp, _vp, _vp]),
     "gsb_tsdf_last_stats": (C.c_int, [_vp, _vp, _vp]),
+    "gsb_mesh_count": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp]),
+    "gsb_mesh_emit": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _vp]),
+    "gsb_mesh_vertices": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp]),
+    "gsb_mesh_vertex_normals": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, _vp]),
 }
 
 _lib = None

@@ -12,6 +12,13 @@
 
 #include "gs2mesh_b200.h"
 
+// Opaque handle of include/gs2mesh_b200.h: a copy of the caller's descriptor (owns no device memory).
+struct GsbVolume {
+  GsbVolumeDesc d;
+  uint32_t frame = 0;
+  size_t n_bricks = 0;
+};
+
 namespace gsb {
 
 constexpr int kTile = 16;          // DGR/cuda_rasterizer/config.h:16-17 (BLOCK_X, BLOCK_Y)

@@ -221,22 +221,36 @@ inline size_t radix_scratch_words(size_t max_items) {
   return (size_t)kRdxMaxPasses * (kRdxBins + nblocks * kRdxBins + 1) + 64;
 }
 
+// Scratch layout: ghist [kRdxMaxPasses][256] | tickets [64] | status [passes][nblocks][256]
+inline uint32_t* radix_ghist(uint32_t* scratch) { return scratch; }
+
+// Zeroes the histogram / ticket / status words one sort over `max_items` items with `bits` key bits needs.
+inline void radix_prepare(uint32_t* scratch, size_t max_items, int bits, cudaStream_t stream) {
+  const size_t nblocks = (max_items + kRdxBlock - 1) / kRdxBlock;
+  const int passes = (bits + 7) / 8;
+  const size_t words = (size_t)kRdxMaxPasses * kRdxBins + 64 + (size_t)passes * nblocks * kRdxBins;
+  cudaMemsetAsync(scratch, 0, words * sizeof(uint32_t), stream);
+}
+
 // Enqueues ceil(bits/8) stable passes sorting (keys, vals) by key bits [0, bits).  `a`/`b` are
 // ping-pong buffers; returns which buffer holds the result (0 = a, 1 = b).  n is either the host
 // value (counters == NULL) or read on the device from counters[1] (clamped by capacity).
+// histogram_ready: the caller already ran radix_prepare() and filled the digit histograms.
 inline int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_host,
                             const unsigned long long* counters, int64_t capacity, size_t max_items, int bits,
-                            uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches) {
+                            uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches,
+                            bool histogram_ready) {
   const uint32_t nblocks = (uint32_t)((max_items + kRdxBlock - 1) / kRdxBlock);
   if (nblocks == 0) return 0;
   const int passes = (bits + 7) / 8;
   uint32_t* ghist = scratch;                                    // [kRdxMaxPasses][256]
-  uint32_t* tickets = ghist + kRdxMaxPasses * kRdxBins;          // [kRdxMaxPasses]
+  uint32_t* tickets = ghist + kRdxMaxPasses * kRdxBins;          // [64]
   uint32_t* status = tickets + 64;                               // [passes][nblocks][256]
-  const size_t words = (size_t)kRdxMaxPasses * kRdxBins + 64 + (size_t)passes * nblocks * kRdxBins;
-  cudaMemsetAsync(scratch, 0, words * sizeof(uint32_t), stream);
-  radix_histogram_kernel<<<nblocks, kRdxThreads, 0, stream>>>(keys_a, n_host, counters, capacity, passes, ghist);
-  *launches += 1;
+  if (!histogram_ready) {
+    radix_prepare(scratch, max_items, bits, stream);
+    radix_histogram_kernel<<<nblocks, kRdxThreads, 0, stream>>>(keys_a, n_host, counters, capacity, passes, ghist);
+    *launches += 1;
+  }
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
     const uint32_t* kin = cur ? keys_b : keys_a;

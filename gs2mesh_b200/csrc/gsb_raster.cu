@@ -715,7 +715,16 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
                                                           const uint32_t* __restrict__ tiles, const int* __restrict__ radii,
                                                           const uint64_t* __restrict__ masks, uint32_t gx, uint32_t gy,
                                                           uint32_t flags, const unsigned long long* __restrict__ counters,
-                                                          uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals) {
+                                                          uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
+                                                          uint32_t* __restrict__ ghist, int hist_passes) {
+  // digit histograms of the tile ids this block emits (what the tile sort's passes need), so the
+  // sort does not have to read the instance stream once more just to count
+  __shared__ uint32_t shist[kRdxMaxPasses][kRdxBins];
+  for (int p = 0; p < hist_passes; ++p) shist[p][threadIdx.x] = 0;
+  __syncthreads();
+  auto tally = [&](uint32_t tile) {
+    for (int p = 0; p < hist_passes; ++p) atomicAdd(&shist[p][(tile >> (8 * p)) & (kRdxBins - 1)], 1u);
+  };
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool fits = counters[2] == 0;
@@ -776,8 +785,10 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
       const uint64_t om = ((uint64_t)ohi << 32) | olo;
       if ((om >> kk) & 1ull) {
         const uint32_t ordinal = (uint32_t)__popcll(om & ((1ull << kk) - 1ull));
-        tile_keys[ooff + ordinal] = (oy0 + kk / ow) * gx + ox0 + kk % ow;
+        const uint32_t tile = (oy0 + kk / ow) * gx + ox0 + kk % ow;
+        tile_keys[ooff + ordinal] = tile;
         tile_vals[ooff + ordinal] = ogid;
+        tally(tile);
       }
     }
   }
@@ -812,9 +823,15 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
         const uint32_t dst = soff + cnt + __popc(votes & lt_mask);
         tile_keys[dst] = ty * gx + tx;
         tile_vals[dst] = sgid;
+        tally(ty * gx + tx);
       }
       cnt += __popc(votes);
     }
+  }
+  __syncthreads();
+  for (int p = 0; p < hist_passes; ++p) {
+    const uint32_t c = shist[p][threadIdx.x];
+    if (c) atomicAdd(&ghist[p * kRdxBins + threadIdx.x], c);
   }
 }
 
@@ -871,7 +888,7 @@ __device__ __forceinline__ void sts64(uint32_t addr, const float2& v) {
 // kFastExp: alpha = opacity * ex2.approx(power * log2 e) instead of the reference's full-precision
 // expf (forward.cu:340): ~2e-7 relative on alpha, far inside the 1e-4 parity budget.
 template <bool kFastExp>
-__global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(kTilePixels, 6) render_kernel(const uint2* __restrict__ ranges,
                                                             const uint32_t* __restrict__ point_list, int W, int H,
                                                             const float4* __restrict__ recA,
                                                             const float4* __restrict__ recB,
@@ -1270,7 +1287,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     {
       StageTimer tm(kStScan, stream);
       const int which = radix_sort_pairs(ws.depth_a, ws.ids_a, ws.depth_b, ws.ids_b, (uint32_t)P, nullptr, 0, (size_t)P, 32, rs,
-                                         nullptr, stream, &nl);
+                                         nullptr, stream, &nl, /*histogram_ready=*/false);
       ids_sorted = which ? ws.ids_b : ws.ids_a;
       const int sblocks = (P + kScanBlock - 1) / kScanBlock;
       sorted_block_sums_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, ids_sorted, ws.tiles, ws.block_sums);
@@ -1284,18 +1301,21 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     uint32_t* tv_a = tk_a + cap;
     uint32_t* tk_b = reinterpret_cast<uint32_t*>(ws.keys_out);
     uint32_t* tv_b = tk_b + cap;
+    const int tile_bits = (int)higher_msb((uint32_t)ntiles);
     {
       StageTimer tm(kStEmit, stream);
+      radix_prepare(rs, (size_t)cap, tile_bits, stream);
       emit_sorted_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ids_sorted, ws.sorted_offsets, ws.recA, ws.recB, ws.tiles,
-                                                              pp.radii, ws.masks, gx, gy, a->flags, ws.counters, tk_a, tv_a);
+                                                              pp.radii, ws.masks, gx, gy, a->flags, ws.counters, tk_a, tv_a,
+                                                              radix_ghist(rs), (tile_bits + 7) / 8);
       init_ranges_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream>>>(ws.ranges, (uint32_t)ntiles);
       nl += 2;
     }
     if ((rc = check_launch("emit_sorted_kernel", stream, dbg))) return rc;
     {
       StageTimer tm(kStSort, stream);
-      const int bits = (int)higher_msb((uint32_t)ntiles);
-      const int which = radix_sort_pairs(tk_a, tv_a, tk_b, tv_b, 0u, ws.counters, cap, (size_t)cap, bits, rs, ws.ranges, stream, &nl);
+      const int which = radix_sort_pairs(tk_a, tv_a, tk_b, tv_b, 0u, ws.counters, cap, (size_t)cap, tile_bits, rs, ws.ranges,
+                                         stream, &nl, /*histogram_ready=*/true);
       point_list = which ? tv_b : tv_a;
     }
     count_launch(nl);

@@ -19,11 +19,6 @@
 // operation order, so results are bit-identical to oracle/tsdf_oracle.cpp.
 #include "gsb_common.h"
 
-struct GsbVolume {
-  GsbVolumeDesc d;
-  uint32_t frame = 0;
-  size_t n_bricks = 0;
-};
 
 namespace gsb {
 namespace {

@@ -342,7 +342,7 @@ class TSDF:
             raise RuntimeError("TSDF.extract_mesh() called before run()/integrate()")
         self.mesh = extract_triangle_mesh(self.volume)
         self.mesh.scale(float(self._arg("TSDF_scale", 1.0)), (0, 0, 0))
-        self.mesh.compute_vertex_normals()
+        self.mesh.compute_vertex_normals(self.volume.device)
         return self.mesh
 
     def save_mesh(self):

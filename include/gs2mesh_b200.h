@@ -204,6 +204,26 @@ int gsb_tsdf_export_dense(const GsbVolume* vol, float* tsdf, float* weight, void
  * host, uint32[4]): [0] bricks touched, [1] bricks outside the window, [2] frame id. */
 int gsb_tsdf_last_stats(const GsbVolume* vol, uint32_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Mesh extraction: volume.extract_triangle_mesh() + compute_vertex_normals()
+ * (gs2mesh_utils/tsdf_utils.py:108-110; Open3D ScalableTSDFVolume::ExtractTriangleMesh)
+ * ------------------------------------------------------------------------------------------
+ * Marching cubes over the bricks listed in `bricks` (device uint32[n_bricks], normally every brick with
+ * a non-zero stamp).  A cube is skipped when any of its 8 corners has weight 0; corners are inside when
+ * tsdf < 0.  Vertices are identified by an edge key = ((gx*NY + gy)*NZ + gz)*3 + axis over the window's
+ * voxel grid; the caller sorts/uniques the keys (that is the de-duplication Open3D does with a hash map)
+ * and asks for the attributes of the unique edges.
+ *   gsb_mesh_count    tri_counts[b]  = triangles produced by brick b
+ *   gsb_mesh_emit     edge_keys[3*t..3*t+2] for every triangle, brick b writing from tri_offsets[b]
+ *   gsb_mesh_vertices xyz (fp64, Open3D's interpolation) and rgb in [0,1] (or NULL) of n unique keys
+ *   gsb_mesh_vertex_normals area-weighted vertex normals (fp64 [n_vertices,3]) of an indexed mesh */
+int gsb_mesh_count(const GsbVolume* vol, const uint32_t* bricks, uint32_t n_bricks, uint32_t* tri_counts, void* stream);
+int gsb_mesh_emit(const GsbVolume* vol, const uint32_t* bricks, uint32_t n_bricks, const int64_t* tri_offsets, int64_t* edge_keys,
+                  void* stream);
+int gsb_mesh_vertices(const GsbVolume* vol, const int64_t* keys, int64_t n, double* xyz, float* rgb, void* stream);
+int gsb_mesh_vertex_normals(const double* xyz, int64_t n_vertices, const int64_t* triangles, int64_t n_triangles, double* normals,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -293,3 +293,74 @@ def ref_forward_torch(means3D, opacities, view, proj, campos, W, H, tan_fovx, ta
         out.update(g)
     torch.cuda.synchronize()
     return out
+
+
+# ----------------------------------------------------------------------------- marching cubes (Open3D ExtractTriangleMesh)
+
+def _mc_tables():
+    import re
+
+    text = open(os.path.join(os.path.dirname(_HERE), "include", "gsb_mc_tables.h")).read()
+
+    def grab(name, shape):
+        m = re.search(name + r"\[[^\]]*\](?:\[[^\]]*\])?\s*=\s*\{(.*?)\};", text, re.S)
+        return np.array([int(v) for v in re.findall(r"-?\d+", m.group(1))]).reshape(shape)
+
+    return grab("kMcShift", (8, 3)), grab("kMcEdgeShift", (12, 4)), grab("kMcEdgeToVert", (12, 2)), grab("kMcTriTable", (256, 16))
+
+
+def extract_mesh_from_bricks(tw, brick_origin, brick_count, voxel_length, color=None):
+    """CPU restatement of ScalableTSDFVolume::ExtractTriangleMesh on a dense brick window
+    (tw: [n_bricks,4096,2] as returned by OracleTSDFVolume.export_bricks; unallocated units have weight 0,
+    which is what Open3D's hash-map miss yields).  Returns dict(keys, vertices, colors, triangles):
+    `keys[i]` = (gx,gy,gz,axis) of vertex i in window voxel coordinates, vertices fp64 like Open3D."""
+    shift, edge_shift, e2v, tri = _mc_tables()
+    nbx, nby, nbz = (int(v) for v in brick_count)
+    g = np.asarray(tw).reshape(nbx, nby, nbz, 16, 16, 16, 2).transpose(0, 3, 1, 4, 2, 5, 6).reshape(nbx * 16, nby * 16, nbz * 16, 2)
+    f, w = g[..., 0], g[..., 1]
+    col = None
+    if color is not None:
+        col = np.asarray(color).reshape(nbx, nby, nbz, 16, 16, 16, -1).transpose(0, 3, 1, 4, 2, 5, 6).reshape(
+            nbx * 16, nby * 16, nbz * 16, -1)[..., :3]
+    X, Y, Z = f.shape
+    fp = np.pad(f, ((0, 1),) * 3)
+    wp = np.pad(w, ((0, 1),) * 3)  # outside the window == unallocated == weight 0
+    valid = np.ones((X, Y, Z), bool)
+    case = np.zeros((X, Y, Z), np.int32)
+    for i in range(8):
+        sx, sy, sz = shift[i]
+        valid &= wp[sx:sx + X, sy:sy + Y, sz:sz + Z] != 0
+        case |= (fp[sx:sx + X, sy:sy + Y, sz:sz + Z] < 0).astype(np.int32) << i
+    active = np.argwhere(valid & (case != 0) & (case != 255))
+    vmap, verts, cols, tris, keys = {}, [], [], [], []
+    half = voxel_length * 0.5
+    b0 = np.asarray(brick_origin, dtype=np.int64) * 16
+    for x, y, z in active:
+        c = case[x, y, z]
+        row = tri[c]
+        idx = {}
+        for e in set(int(v) for v in row if v >= 0):
+            es = edge_shift[e]
+            key = (int(x + es[0]), int(y + es[1]), int(z + es[2]), int(es[3]))
+            if key not in vmap:
+                vmap[key] = len(verts)
+                c0 = np.array([x, y, z]) + shift[e2v[e][0]]
+                c1 = np.array([x, y, z]) + shift[e2v[e][1]]
+                f0 = abs(float(fp[tuple(c0)]))
+                f1 = abs(float(fp[tuple(c1)]))
+                pt = half + voxel_length * (b0 + np.array(key[:3], dtype=np.float64))
+                pt[key[3]] += f0 * voxel_length / (f0 + f1)
+                verts.append(pt)
+                keys.append(key)
+                if col is not None:
+                    k0 = col[tuple(c0)].astype(np.float64) / 255.0
+                    k1 = col[tuple(c1)].astype(np.float64) / 255.0
+                    cols.append((f1 * k0 + f0 * k1) / (f0 + f1))
+            idx[e] = vmap[key]
+        for t in range(0, 15, 3):
+            if row[t] < 0:
+                break
+            tris.append((idx[int(row[t])], idx[int(row[t + 2])], idx[int(row[t + 1])]))
+    return dict(keys=np.array(keys, np.int64).reshape(-1, 4), vertices=np.array(verts, np.float64).reshape(-1, 3),
+                colors=np.array(cols, np.float64).reshape(-1, 3) if col is not None else None,
+                triangles=np.array(tris, np.int64).reshape(-1, 3))
