@@ -191,15 +191,17 @@ def view_transforms_from_camera(cam: dict) -> ViewTransforms:
 def make_stereo_rig(rot_deg, pos, baseline, width, height, fx, fy, cx, cy) -> dict:
     """One {'left','right'} camera pair as built in renderer_utils.py:178-206 (incl. the
     quirk that the right camera's 'extrinsic' is the LEFT camera's, :204)."""
-    rot_deg = np.asarray(rot_deg, dtype=np.float64)
+    # dtype matters: the reference keeps the float32 Euler angles `rotm2eul` returns for 'extrinsic' and the right
+    # camera (float32 radians inside eul2rotm) but stores python floats in 'rot' (renderer_utils.py:180-204)
+    rot_arr = np.asarray(rot_deg)
     pos = tuple(float(v) for v in pos)
-    rot_r, pos_r = right_camera_pose(rot_deg, pos, baseline)
+    rot_r, pos_r = right_camera_pose(rot_arr, pos, baseline)
     k = {"fx": fx, "fy": fy, "cx": cx, "cy": cy}
     common = {"width": int(width), "height": int(height), "fx": float(fx), "fy": float(fy), "cx": float(cx), "cy": float(cy)}
-    left = dict(rot=tuple(rot_deg.tolist()), pos=pos, **common, intrinsic=intrinsic_matrix(k),
-                extrinsic=pose_c2w_opencv(tuple(rot_deg), pos), baseline=baseline)
+    left = dict(rot=tuple(rot_arr.tolist()), pos=pos, **common, intrinsic=intrinsic_matrix(k),
+                extrinsic=pose_c2w_opencv(tuple(rot_arr), pos), baseline=baseline)
     right = dict(rot=rot_r, pos=pos_r, **common, intrinsic=intrinsic_matrix(k),
-                 extrinsic=pose_c2w_opencv(tuple(rot_deg), pos))
+                 extrinsic=pose_c2w_opencv(tuple(rot_arr), pos))
     return {"left": left, "right": right}
 
 
@@ -213,8 +215,9 @@ def scene_baseline(camera_locations, percentage=7.0, scene_360=True, dtu_compat=
     else:
         from scipy.optimize import least_squares
 
+        x_m, y_m, z_m = np.mean(ts, axis=0)
+        guess = np.array([x_m, y_m, z_m, 1.0])
         x, y, z = ts[:, 0], ts[:, 1], ts[:, 2]
-        guess = np.array([x.mean(), y.mean(), z.mean(), 1.0])
         fit = least_squares(lambda p: np.sqrt((x - p[0]) ** 2 + (y - p[1]) ** 2 + (z - p[2]) ** 2) - p[3], guess)
         radius = fit.x[3]
     return float(radius * (percentage / 100))
