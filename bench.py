@@ -420,14 +420,21 @@ def run_reference(args, cfg, rank, local, world):
 
     ovol = orc.OracleTSDFVolume(2.0 / cfg["tsdf_res"], bargs.TSDF_sdf_trunc, with_color=True)
 
+    raster_ms = []
+
     def step(i):
         frames = []
         for side in ("left", "right"):  # renderer_utils.py:378-390
             c = rigs[i][side]
             vt = cam.view_transforms_from_camera(c)
             view, proj, pos = up(vt.world_view), up(vt.full_proj), up(vt.cam_center)  # cameras.py:54-57 uploads per view
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             res = orc.ref_forward_torch(g["xyz"], g["op"], view, proj, pos, W, H, vt.tan_fovx, vt.tan_fovy, bg, shs=g["sh"],
                                         scales=g["sc"], rotations=g["ro"], sh_degree=3)
+            e1.record()
+            e1.synchronize()
+            raster_ms.append(e0.elapsed_time(e1))
             rendering = (res["color"].permute(1, 2, 0) * 255).cpu().numpy()  # :389
             frames.append(np.clip(np.rint(rendering), 0, 255).astype(np.uint8))  # imwrite's float->u8
         c = rigs[i]["left"]
@@ -438,6 +445,7 @@ def run_reference(args, cfg, rank, local, world):
     for i in order[:Wm]:
         step(i)
     torch.cuda.synchronize()
+    raster_ms.clear()
     sampler = ClockSampler(local)
     sampler.start()
     t0 = time.perf_counter()
@@ -455,7 +463,8 @@ def run_reference(args, cfg, rank, local, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config, cfg, total_views),
                    "note": "reference rasterizer (oracle/_ref, sm_100a build of the unmodified sources) x2 per pair as called by "
-                           "renderer_utils.py:378-390 + Open3D-0.17-equivalent CPU TSDF; rank 0 only; PNG encode and DLNR excluded"},
+                           "renderer_utils.py:378-390 + Open3D-0.17-equivalent CPU TSDF; rank 0 only; PNG encode and DLNR excluded",
+                   "reference_rasterizer_ms_per_view": round(float(np.mean(raster_ms)), 4) if raster_ms else None},
         "clocks": clocks,
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "reference+port",
                          "sample": f"{done} stereo pairs: GPU reference rasterizer + CPU TSDF port on {cores} threads"},

@@ -888,7 +888,7 @@ __device__ __forceinline__ void sts64(uint32_t addr, const float2& v) {
 // kFastExp: alpha = opacity * ex2.approx(power * log2 e) instead of the reference's full-precision
 // expf (forward.cu:340): ~2e-7 relative on alpha, far inside the 1e-4 parity budget.
 template <bool kFastExp>
-__global__ void __launch_bounds__(kTilePixels, 6) render_kernel(const uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __restrict__ ranges,
                                                             const uint32_t* __restrict__ point_list, int W, int H,
                                                             const float4* __restrict__ recA,
                                                             const float4* __restrict__ recB,
