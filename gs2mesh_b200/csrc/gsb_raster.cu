@@ -23,6 +23,7 @@
 //
 // All kernels run on the caller's stream.
 #include <algorithm>
+#include <cstdlib>
 
 #include <cub/cub.cuh>
 
@@ -997,6 +998,106 @@ __global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __rest
   }
 }
 
+// Barrier-free variant: the 8 warps of a tile never wait for each other.  Every warp streams the
+// tile's sorted instance list on its own, 32 Gaussians at a time: each lane gathers ONE record
+// (the 8 warps of the CTA hit the same lines, so all but the first gather is an L1 hit), tests it
+// against the warp's 8x4 pixel block straight from registers, and publishes it in the warp's private
+// double-buffered shared-memory slot for the broadcast reads of the blend loop.  The next chunk's
+// gathers are in flight while the current one is blended; no __syncthreads anywhere, and a warp
+// leaves as soon as its own 32 pixels are saturated.
+template <bool kFastExp>
+__global__ void __launch_bounds__(kTilePixels, 5) render_warp_kernel(const uint2* __restrict__ ranges,
+                                                                 const uint32_t* __restrict__ point_list, int W, int H,
+                                                                 const float4* __restrict__ recA,
+                                                                 const float4* __restrict__ recB,
+                                                                 const float2* __restrict__ recC,
+                                                                 const float* __restrict__ bg, float* __restrict__ out_color,
+                                                                 float* __restrict__ out_depth, float* __restrict__ out_T,
+                                                                 int64_t capacity) {
+  __shared__ __align__(16) float4 sA[8][2][32];
+  __shared__ __align__(16) float4 sB[8][2][32];
+  __shared__ __align__(16) float2 sC[8][2][32];
+  const uint32_t tiles_x = (W + kTile - 1) / kTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t aA = smem_u32(&sA[warp][0][0]), aB = smem_u32(&sB[warp][0][0]), aC = smem_u32(&sC[warp][0][0]);
+  const uint32_t blk_x = blockIdx.x * kTile + (warp & 1) * 8, blk_y = blockIdx.y * kTile + (warp >> 1) * 4;
+  const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
+  const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+  const float pfx = (float)pix_x, pfy = (float)pix_y;
+  const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 3);
+  uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
+  if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);
+  const int total = range.y - range.x;
+  bool done = !inside;
+  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
+
+  float4 cA = make_float4(0.f, 0.f, 0.f, 0.f), cB = cA, nA = cA, nB = cA;
+  float2 cC = make_float2(0.f, 0.f), nC = cC;
+  if (lane < total) {
+    const uint32_t g = point_list[range.x + lane];
+    cA = recA[g];
+    cB = recB[g];
+    cC = recC[g];
+  }
+  for (int c0 = 0; c0 < total; c0 += 32) {
+    if (__all_sync(0xffffffffu, done)) break;
+    const int buf = (c0 >> 5) & 1;
+    sts128(aA + (buf * 32 + lane) * 16, cA);
+    sts128(aB + (buf * 32 + lane) * 16, cB);
+    sts64(aC + (buf * 32 + lane) * 8, cC);
+    const int nxt = c0 + 32 + lane;
+    if (nxt < total) {  // next chunk's gathers fly while this one is blended
+      const uint32_t g = point_list[range.x + nxt];
+      nA = recA[g];
+      nB = recB[g];
+      nC = recC[g];
+    }
+    bool hit = false;
+    if (c0 + lane < total) {
+      const Footprint fp = make_footprint(cB.x, cB.y, cB.z, 2.f * __logf(255.f * cA.w) + 1e-3f);
+      hit = rect_can_contribute(cA.x, cA.y, fp, bx0, by0, bx1, by1);
+    }
+    __syncwarp();  // the chunk's records are visible to every lane of the warp
+    unsigned todo = __ballot_sync(0xffffffffu, hit);
+    const uint32_t bA = aA + buf * 512, bB = aB + buf * 512, bC = aC + buf * 256;
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      if (done) continue;
+      const float4 A = lds128(bA + j * 16);
+      const float4 B = lds128(bB + j * 16);
+      const float dx = A.x - pfx, dy = A.y - pfy;
+      const float power = -0.5f * (B.x * dx * dx + B.z * dy * dy) - B.y * dx * dy;
+      if (power > 0.0f) continue;
+      const float alpha = min(0.99f, A.w * (kFastExp ? __expf(power) : exp(power)));
+      if (alpha < 1.0f / 255.0f) continue;
+      const float test_T = T * (1 - alpha);
+      if (test_T < 0.0001f) {
+        done = true;
+        continue;
+      }
+      const float2 gb = lds64(bC + j * 8);
+      C0 += B.w * alpha * T;
+      C1 += gb.x * alpha * T;
+      C2 += gb.y * alpha * T;
+      Dz += A.z * alpha * T;
+      T = test_T;
+    }
+    cA = nA;
+    cB = nB;
+    cC = nC;
+  }
+  if (inside) {
+    const size_t pid = (size_t)pix_y * W + pix_x;
+    const size_t plane = (size_t)H * W;
+    out_color[pid] = C0 + T * bg[0];
+    out_color[plane + pid] = C1 + T * bg[1];
+    out_color[2 * plane + pid] = C2 + T * bg[2];
+    if (out_depth) out_depth[pid] = Dz;
+    if (out_T) out_T[pid] = T;
+  }
+}
+
 __global__ void write_counts_kernel(const uint32_t* __restrict__ offsets, int P, const unsigned long long* counters,
                                     int64_t* out) {
   // offsets != NULL: validation path (instance total = last element of the per-Gaussian scan)
@@ -1327,14 +1428,26 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   }
   {
     StageTimer tm(kStRender, stream);
-    if (a->flags & GSB_RASTER_FAST_EXP)
-      render_kernel<true><<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC,
-                                                                   a->background, a->out_color, a->out_depth,
-                                                                   a->out_final_T, cap);
-    else
-      render_kernel<false><<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC,
-                                                                    a->background, a->out_color, a->out_depth,
-                                                                    a->out_final_T, cap);
+    static const int render_impl = [] {
+      const char* e = getenv("GSB_RENDER_IMPL");  // A/B switch for profiling: "block" = barrier-per-batch variant
+      return (e && e[0] == 'b') ? 0 : 1;
+    }();
+    const bool fast = (a->flags & GSB_RASTER_FAST_EXP) != 0;
+#define GSB_LAUNCH_RENDER(KERNEL)                                                                                            \
+  KERNEL<<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, \
+                                                   a->out_color, a->out_depth, a->out_final_T, cap)
+    if (render_impl == 1) {
+      if (fast)
+        GSB_LAUNCH_RENDER(render_warp_kernel<true>);
+      else
+        GSB_LAUNCH_RENDER(render_warp_kernel<false>);
+    } else {
+      if (fast)
+        GSB_LAUNCH_RENDER(render_kernel<true>);
+      else
+        GSB_LAUNCH_RENDER(render_kernel<false>);
+    }
+#undef GSB_LAUNCH_RENDER
   }
   count_launch();
   if ((rc = check_launch("render_kernel", stream, dbg))) return rc;
