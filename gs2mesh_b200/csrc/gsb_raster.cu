@@ -1060,28 +1060,48 @@ __global__ void __launch_bounds__(kTilePixels, 5) render_warp_kernel(const uint2
     __syncwarp();  // the chunk's records are visible to every lane of the warp
     unsigned todo = __ballot_sync(0xffffffffu, hit);
     const uint32_t bA = aA + buf * 512, bB = aB + buf * 512, bC = aC + buf * 256;
+    // two hits per trip: their loads, quadratic forms and exponentials are independent and overlap; only
+    // the transmittance update is applied in order
     while (todo) {
-      const int j = __ffs(todo) - 1;
+      const int j0 = __ffs(todo) - 1;
       todo &= todo - 1;
+      const bool two = todo != 0;
+      const int j1 = two ? __ffs(todo) - 1 : j0;
+      todo &= todo - 1;  // no-op when todo is already 0
       if (done) continue;
-      const float4 A = lds128(bA + j * 16);
-      const float4 B = lds128(bB + j * 16);
-      const float dx = A.x - pfx, dy = A.y - pfy;
-      const float power = -0.5f * (B.x * dx * dx + B.z * dy * dy) - B.y * dx * dy;
-      if (power > 0.0f) continue;
-      const float alpha = min(0.99f, A.w * (kFastExp ? __expf(power) : exp(power)));
-      if (alpha < 1.0f / 255.0f) continue;
-      const float test_T = T * (1 - alpha);
-      if (test_T < 0.0001f) {
-        done = true;
-        continue;
+      const float4 A0 = lds128(bA + j0 * 16), B0 = lds128(bB + j0 * 16);
+      const float4 A1 = lds128(bA + j1 * 16), B1 = lds128(bB + j1 * 16);
+      const float dx0 = A0.x - pfx, dy0 = A0.y - pfy, dx1 = A1.x - pfx, dy1 = A1.y - pfy;
+      const float power0 = -0.5f * (B0.x * dx0 * dx0 + B0.z * dy0 * dy0) - B0.y * dx0 * dy0;
+      const float power1 = -0.5f * (B1.x * dx1 * dx1 + B1.z * dy1 * dy1) - B1.y * dx1 * dy1;
+      const float alpha0 = min(0.99f, A0.w * (kFastExp ? __expf(power0) : exp(power0)));
+      const float alpha1 = min(0.99f, A1.w * (kFastExp ? __expf(power1) : exp(power1)));
+      if (!(power0 > 0.0f) && !(alpha0 < 1.0f / 255.0f)) {
+        const float test_T = T * (1 - alpha0);
+        if (test_T < 0.0001f) {
+          done = true;
+        } else {
+          const float2 gb = lds64(bC + j0 * 8);
+          C0 += B0.w * alpha0 * T;
+          C1 += gb.x * alpha0 * T;
+          C2 += gb.y * alpha0 * T;
+          Dz += A0.z * alpha0 * T;
+          T = test_T;
+        }
       }
-      const float2 gb = lds64(bC + j * 8);
-      C0 += B.w * alpha * T;
-      C1 += gb.x * alpha * T;
-      C2 += gb.y * alpha * T;
-      Dz += A.z * alpha * T;
-      T = test_T;
+      if (two && !done && !(power1 > 0.0f) && !(alpha1 < 1.0f / 255.0f)) {
+        const float test_T = T * (1 - alpha1);
+        if (test_T < 0.0001f) {
+          done = true;
+        } else {
+          const float2 gb = lds64(bC + j1 * 8);
+          C0 += B1.w * alpha1 * T;
+          C1 += gb.x * alpha1 * T;
+          C2 += gb.y * alpha1 * T;
+          Dz += A1.z * alpha1 * T;
+          T = test_T;
+        }
+      }
     }
     cA = nA;
     cB = nB;

@@ -3,7 +3,5 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_warp.log 2>&1
-tail -1 gpurun_out/bench_warp.log | cut -c1-200
-GSB_RENDER_IMPL=block timeout 900 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_block.log 2>&1
-tail -1 gpurun_out/bench_block.log | cut -c1-200
+timeout 900 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_warp2.log 2>&1
+tail -1 gpurun_out/bench_warp2.log | cut -c1-200
