@@ -1,7 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/bench_warp2.log 2>&1
-tail -1 gpurun_out/bench_warp2.log | cut -c1-200
+for c in C2 C3 C4; do
+  timeout 900 python bench.py --config $c --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$c.log 2>&1
+  echo "exit $?" >> gpurun_out/bench_$c.log
+  tail -2 gpurun_out/bench_$c.log | cut -c1-400
+done
+timeout 900 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref.log 2>&1
+tail -1 gpurun_out/bench_ref.log | cut -c1-900
