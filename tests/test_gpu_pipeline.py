@@ -161,3 +161,66 @@ def test_full_size_properties(gsb_lib, cuda_device):
     assert torch.equal(t1[:, 1] * 2, w)
     assert float((t1[:, 0] - tw[:, 0]).abs().max()) <= 1e-6  # running mean of identical samples
     assert float(tw[:, 0].abs().max()) <= 1.0 and float(tw[:, 0].min()) < -0.5  # truncated to [-1, 1], surface crossed
+
+
+def test_full_size_parity_vs_reference_binary_and_oracle(oracle, gsb_lib, cuda_device):
+    """BASELINE config C1 at full size: the rendered frame against the UNMODIFIED reference rasterizer (sm_100a
+    build) on the same tensors, and the fused TSDF bricks against the Open3D restatement on the same depth."""
+    import torch
+
+    from gs2mesh_b200 import _lib
+    from gs2mesh_b200.renderer import Renderer
+    from gs2mesh_b200.tsdf import TSDF
+    from tests.raster_compare import compare_images
+
+    cfg = scene.CONFIGS["C1"]
+    W, H = cfg["width"], cfg["height"]
+    cloud = scene.make_gaussians(cfg["num_points"], seed=1)
+    rigs, baseline = scene.make_stereo_cameras(8, W, H)
+
+    class A(Args):
+        TSDF_voxel = 2
+        TSDF_sdf_trunc = 0.04
+        TSDF_skip = None
+
+    r = Renderer.from_scene(rigs, baseline, cloud, args=A(), device=str(cuda_device))
+    r.prepare_renderer()
+    if oracle.ref_available():
+        for side in (0, 1):
+            rec = r._camera_table[3, side]
+            vt = r._views[3][side]
+            ref = oracle.ref_forward_torch(r.means3D, r.opacity, rec[0:16], rec[16:32], rec[32:35], W, H, vt.tan_fovx, vt.tan_fovy,
+                                           r.background, shs=r.shs, scales=r.scales, rotations=r.rotations, sh_degree=3)
+            for flags in (_lib.RASTER_EXACT_TILE_CULL, _lib.RASTER_EXACT_TILE_CULL | _lib.RASTER_FAST_EXP):
+                ours = r.render_view(3, side, want_depth=True, want_counts=True, flags=flags)
+                cmp = compare_images(ours["color"].cpu().numpy(), ref["color"].cpu().numpy())
+                assert cmp["frac_bad"] <= 2e-4 and cmp["median"] <= 1e-6, (side, flags, cmp)
+                cmpT = compare_images(ours["final_T"].cpu().numpy(), ref["final_T"].cpu().numpy())
+                assert cmpT["frac_bad"] <= 2e-4, (side, flags, cmpT)
+                assert int(ours["counts"][1]) == ref["num_rendered"]  # the reference's instance count, exactly
+
+    pair = r.render_image_pair(3, to_host=False)
+    stage = TSDF(r, None, A(), "c1", window_resolution=512)
+    stage.integrate(pair["depth"], pair["left_u8"], rigs[3]["left"], final_T=pair["final_T"])
+    vol = stage.volume
+    torch.cuda.synchronize()
+    alpha = 1.0 - pair["final_T"].cpu().numpy()
+    d = np.where(alpha > 0.5, pair["depth"].cpu().numpy() / np.maximum(alpha, 1e-30), 0).astype(np.float32)
+    d = np.where(d < np.float32(A.TSDF_min_depth_baselines * baseline), 0, d).astype(np.float32)
+    ovol = oracle.OracleTSDFVolume(2.0 / 512, 0.04, with_color=True)
+    c = rigs[3]["left"]
+    n_units = ovol.integrate(d, pair["left_u8"].cpu().numpy(), W, H, c["fx"], c["fy"], c["cx"], c["cy"], np.linalg.inv(c["extrinsic"]),
+                             depth_scale=1.0, depth_trunc=baseline * A.TSDF_max_depth_baselines, threads=8)
+    touched, outside, _ = vol.last_stats()
+    assert outside == 0 and touched == n_units
+    units = ovol.unit_indices()
+    bricks = vol.bricks()
+    b0 = np.array(vol.brick_origin)
+    nb = vol.brick_count
+    step = max(1, len(units) // 300)  # compare ~300 of the ~2500 touched bricks bit for bit
+    for i in range(0, len(units), step):
+        t, w, _ = ovol.unit_data(i)
+        b = units[i] - b0
+        got = bricks[int((b[0] * nb[1] + b[1]) * nb[2] + b[2])].cpu().numpy()
+        np.testing.assert_array_equal(got[:, 1], w)
+        np.testing.assert_array_equal(got[:, 0], t)
