@@ -276,13 +276,20 @@ def run_ours(args, cfg, rank, local, world):
     K_e2e = K
     barrier(world)
     t0 = time.perf_counter()
-    for i in mine[:K_e2e]:
-        out = renderer.render_image_pair(i, to_host=True)  # both uint8 frames -> pinned host
+    # software-pipelined by one pair: while the host consumes pair i (waits for its frames, reads the depth back,
+    # hands depth + colour to TSDF.integrate, which uploads them), pair i+1 is already being rendered
+    views = mine[:K_e2e]
+    pending = renderer.render_image_pair(views[0], to_host=True, wait=False) if views else None
+    for n, i in enumerate(views):
+        out = pending
+        pending = renderer.render_image_pair(views[n + 1], to_host=True, wait=False) if n + 1 < len(views) else None
+        out["ready"].synchronize()  # both uint8 frames of pair i are in pinned host memory
         vol.prepare_depth(out["depth"], W, H, final_T=out["final_T"], out=dev_depth)  # expected depth of the left view
         host_depth.copy_(dev_depth, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         # what a host-side stereo stage would hand back: float depth + the uint8 left frame, both on the host
         stage.integrate(host_depth, out["host_left_u8"], rigs[i]["left"])
+    renderer.check_status(views)
     if world > 1:
         vol.reduce_across_ranks(dst=0)
     barrier(world)

@@ -31,6 +31,17 @@ from . import camera as cam
 from . import rasterizer as rast
 
 
+class _PairReady:
+    """Completion handle of an asynchronously rendered pair (render_image_pair(..., wait=False))."""
+
+    def __init__(self, events):
+        self._events = events
+
+    def synchronize(self):
+        for e in self._events:
+            e.synchronize()
+
+
 class Renderer:
     def __init__(self, base_dir=None, colmap_dir=None, output_dir_root=None, args=None, dataset="custom", splatting="custom",
                  experiment_name=None, device="cuda", *, cameras=None, baseline=None, gaussians=None):
@@ -181,33 +192,38 @@ class Renderer:
             out_color=out_color, out_depth=out_depth, out_final_T=out_final_T, async_mode=async_mode,
             counts_out=self._status[camera_number, side] if async_mode else None, min_instances=self._min_instances)
 
-    def render_image_pair(self, camera_number, visualize=False, *, to_host: Optional[bool] = None):
+    def render_image_pair(self, camera_number, visualize=False, *, to_host: Optional[bool] = None, wait: bool = True):
         """Render the stereo-aligned left/right pair of view `camera_number`
         (reference: renderer_utils.py:363-395).  Returns a dict of DEVICE tensors
         (left/right float CHW, left_u8/right_u8 HWC, depth = left sum(z*alpha*T), final_T) and, when
         `to_host` (default: whenever PNGs are written), pinned host copies `host_left_u8`,
-        `host_right_u8`."""
+        `host_right_u8`.  With `wait=False` the call only enqueues: `result["ready"]` is a CUDA event to
+        synchronise on before touching the host copies (lets the caller overlap the next pair's rendering
+        with the host-side consumption of this one)."""
         with torch.no_grad():
             vt = self._views[camera_number][0]
             dev = self._camera_table.device
             main = torch.cuda.current_stream(dev)
             if self.overlap_eyes:
-                # outputs are double-buffered: the tensors returned by call n stay valid during call n+1
+                # outputs are triple-buffered: the tensors returned by call n stay valid until call n+2 returns,
+                # which also covers a caller that consumes pair n only after enqueuing pair n+1 (wait=False)
                 self._call_index = getattr(self, "_call_index", -1) + 1
-                parity = self._call_index & 1
+                slot = self._call_index % 3
                 if not hasattr(self, "_side_streams"):
                     self._side_streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-                    self._entry_events = [None, None]
-                b = self._buffers(vt.width, vt.height, parity)
+                    self._entry_events = [None, None, None]
+                b = self._buffers(vt.width, vt.height, slot)
                 entry = torch.cuda.Event()
                 entry.record(main)
-                gate = self._entry_events[parity ^ 1]  # recorded when the previous call was entered: everything that
-                self._entry_events[parity] = entry      # consumed this buffer set was enqueued before it
+                # everything that read this buffer set (handed out three calls ago) was enqueued on the caller's
+                # stream before the PREVIOUS call was entered
+                gate = self._entry_events[(self._call_index - 1) % 3]
+                self._entry_events[slot] = entry
                 streams = self._side_streams
                 for st in streams:
                     if gate is not None:
                         st.wait_event(gate)
-                    elif self._call_index == 0:
+                    else:
                         st.wait_stream(main)
             else:
                 b = self._buffers(vt.width, vt.height)
@@ -225,13 +241,18 @@ class Renderer:
                 for s in range(2):
                     with torch.cuda.stream(streams[s]):
                         b["host_u8"][s].copy_(b["u8"][s], non_blocking=True)
-            if self.overlap_eyes:
+            asynchronous = to_host and not wait and not self.write_images and self.overlap_eyes
+            if self.overlap_eyes and not asynchronous:
                 for st in streams:
                     main.wait_stream(st)  # device-side dependency only: later work on the caller's stream sees both eyes
             if to_host:
-                main.synchronize()
-                self.check_status([camera_number])
                 result["host_left_u8"], result["host_right_u8"] = b["host_u8"]
+                if asynchronous:
+                    result["ready"] = _PairReady([st.record_event() for st in streams])
+                else:
+                    main.synchronize()
+                    self.check_status([camera_number])
+                    result["ready"] = _PairReady([])
             if self.write_images:
                 import cv2
 

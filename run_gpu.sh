@@ -1,8 +1,8 @@
 set -x
 mkdir -p gpurun_out
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_raster.py tests/test_gpu_tsdf.py tests/test_gpu_mesh.py -q -p no:cacheprovider -x -k "edge_sizes or binned_sort or bit_exact or mesh_matches or tma_staging or optional_input" > gpurun_out/sanitizer_memcheck.log 2>&1
-echo "memcheck exit $?" >> gpurun_out/sanitizer_memcheck.log
-tail -6 gpurun_out/sanitizer_memcheck.log
-timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_raster.py tests/test_gpu_mesh.py -q -p no:cacheprovider -x -k "edge_sizes or mesh_matches or tma_staging" > gpurun_out/sanitizer_racecheck.log 2>&1
-echo "racecheck exit $?" >> gpurun_out/sanitizer_racecheck.log
-tail -6 gpurun_out/sanitizer_racecheck.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -8 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1
+echo "bench exit $?" >> gpurun_out/bench_default.log
+tail -2 gpurun_out/bench_default.log | cut -c1-250
