@@ -65,6 +65,7 @@ SIGNATURES = {
                                      C.POINTER(C.c_double), _vp]),
     "gsb_tsdf_to_sums": (C.c_int, [_vp, _vp]),
     "gsb_tsdf_from_sums": (C.c_int, [_vp, _vp]),
+    "gsb_tsdf_sums_bricks": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, _vp]),
     "gsb_tsdf_export_dense": (C.c_int, [_vp, _vp, _vp, _vp]),
     "gsb_tsdf_last_stats": (C.c_int, [_vp, _vp, _vp]),
     "gsb_mesh_count": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp]),

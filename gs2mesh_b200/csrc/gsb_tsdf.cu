@@ -231,10 +231,13 @@ __global__ void __launch_bounds__(256) prepare_depth_kernel(const float* __restr
   out[i] = d;
 }
 
-// (mean, weight) <-> (sum, weight) over the whole store; mode 0: to sums, 1: from sums
-__global__ void __launch_bounds__(256) sums_kernel(float4* __restrict__ tw, float4* __restrict__ color, size_t n_pairs, int mode) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// (mean, weight) <-> (sum, weight); mode 0: to sums, 1: from sums.  `bricks` == NULL: the whole store,
+// else only the listed bricks (one CTA-row of 2048 voxel pairs per brick).
+__global__ void __launch_bounds__(256) sums_kernel(float4* __restrict__ tw, float4* __restrict__ color, size_t n_pairs, int mode,
+                                                   const uint32_t* __restrict__ bricks) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pairs) return;
+  if (bricks != nullptr) i = (size_t)bricks[i / (GSB_BRICK_VOXELS / 2)] * (GSB_BRICK_VOXELS / 2) + i % (GSB_BRICK_VOXELS / 2);
   float4 v = tw[i];
   if (v.y == 0.f && v.w == 0.f) return;
   const float w0 = v.y, w1 = v.w;
@@ -452,17 +455,22 @@ int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, i
   return check_launch("integrate_kernel", stream, false);
 }
 
-static int run_sums(GsbVolume* vol, int mode, cudaStream_t stream) {
+static int run_sums(GsbVolume* vol, int mode, const uint32_t* bricks, uint32_t n_bricks, cudaStream_t stream) {
   if (!vol) return fail(GSB_ERR_INVALID, "tsdf: volume is NULL");
-  const size_t n_pairs = vol->n_bricks * (GSB_BRICK_VOXELS / 2);
+  const size_t n_pairs = (bricks ? (size_t)n_bricks : vol->n_bricks) * (GSB_BRICK_VOXELS / 2);
+  if (n_pairs == 0) return GSB_OK;
   sums_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, stream>>>(reinterpret_cast<float4*>(vol->d.tsdf_weight),
-                                                                     reinterpret_cast<float4*>(vol->d.color), n_pairs, mode);
+                                                                     reinterpret_cast<float4*>(vol->d.color), n_pairs, mode, bricks);
   count_launch();
   return check_launch("sums_kernel", stream, false);
 }
 
-int gsb_tsdf_to_sums(GsbVolume* vol, void* stream) { return run_sums(vol, 0, static_cast<cudaStream_t>(stream)); }
-int gsb_tsdf_from_sums(GsbVolume* vol, void* stream) { return run_sums(vol, 1, static_cast<cudaStream_t>(stream)); }
+int gsb_tsdf_to_sums(GsbVolume* vol, void* stream) { return run_sums(vol, 0, nullptr, 0, static_cast<cudaStream_t>(stream)); }
+int gsb_tsdf_from_sums(GsbVolume* vol, void* stream) { return run_sums(vol, 1, nullptr, 0, static_cast<cudaStream_t>(stream)); }
+int gsb_tsdf_sums_bricks(GsbVolume* vol, int to_sums, const uint32_t* bricks, uint32_t n_bricks, void* stream) {
+  if (n_bricks && !bricks) return fail(GSB_ERR_INVALID, "tsdf_sums_bricks: brick list is NULL");
+  return run_sums(vol, to_sums ? 0 : 1, bricks, n_bricks, static_cast<cudaStream_t>(stream));
+}
 
 int gsb_tsdf_export_dense(const GsbVolume* vol, float* tsdf, float* weight, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);

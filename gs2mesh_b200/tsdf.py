@@ -160,16 +160,41 @@ class TSDFVolume:
         with torch.cuda.device(self.device):
             _lib.check(self._L.gsb_tsdf_from_sums(self._h, self._stream()))
 
-    def reduce_across_ranks(self, group=None, dst: Optional[int] = None, chunk_bytes: int = 256 << 20):
-        """Merge view-sharded volumes: (mean, w) -> (sum, w), ONE NCCL SUM reduce of the volume
-        (chunked), -> (mean, w).  With dst=None every rank ends with the merged volume."""
+    def reduce_across_ranks(self, group=None, dst: Optional[int] = None, chunk_bytes: int = 256 << 20, sparse: bool = True):
+        """Merge view-sharded volumes: (mean, w) -> (sum, w), ONE NCCL SUM reduce, -> (mean, w).  With dst=None every
+        rank ends with the merged volume, else only rank `dst`.
+
+        sparse=True (default) exchanges only the bricks at least one rank has touched: a small MAX all-reduce of the
+        brick stamps gives every rank the same brick list, the listed bricks are packed into a contiguous buffer,
+        reduced and unpacked.  A fused volume touches a few percent of its bricks, so the payload shrinks from
+        24 bytes x N^3 to 96 KB x touched bricks (C4, 1024^3: 25.8 GB -> ~2 GB per rank)."""
         import torch.distributed as dist
 
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return
-        self.to_sums()
-        reduce_sum_chunked([self.tsdf_weight, self.color], group=group, dst=dst, chunk_bytes=chunk_bytes)
-        self.from_sums()
+        if not sparse:
+            self.to_sums()
+            reduce_sum_chunked([self.tsdf_weight, self.color], group=group, dst=dst, chunk_bytes=chunk_bytes)
+            self.from_sums()
+            return
+        with torch.cuda.device(self.device):
+            touched = (self._stamp != 0).to(torch.int32)
+            dist.all_reduce(touched, op=dist.ReduceOp.MAX, group=group)
+            ids = torch.nonzero(touched).reshape(-1)
+            n = int(ids.numel())
+            if n == 0:
+                return
+            ids32 = ids.to(torch.int32).contiguous()
+            _lib.check(self._L.gsb_tsdf_sums_bricks(self._h, 1, ptr(ids32), n, self._stream()))
+            packed = [self.bricks()[ids]]  # [n, 4096, 2] contiguous copies of the listed bricks
+            if self.color is not None:
+                packed.append(self.color.view(self.n_bricks, BRICK_VOXELS, 4)[ids])
+            reduce_sum_chunked(packed, group=group, dst=dst, chunk_bytes=chunk_bytes)
+            self.bricks()[ids] = packed[0]
+            if self.color is not None:
+                self.color.view(self.n_bricks, BRICK_VOXELS, 4)[ids] = packed[1]
+            self._stamp[ids] = torch.clamp_min(self._stamp[ids], 1)  # merged bricks count as touched everywhere
+            _lib.check(self._L.gsb_tsdf_sums_bricks(self._h, 0, ptr(ids32), n, self._stream()))
 
     # ------------------------------------------------------------------ read-back
     def bricks(self):

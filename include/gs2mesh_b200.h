@@ -195,6 +195,9 @@ int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, i
  * before an NCCL SUM reduce of tsdf_weight (and color), and back afterwards. */
 int gsb_tsdf_to_sums(GsbVolume* vol, void* stream);
 int gsb_tsdf_from_sums(GsbVolume* vol, void* stream);
+/* Same conversion restricted to the listed bricks (device uint32[n_bricks]); to_sums != 0: (mean,w) -> (sum,w).
+ * Used by the sparse merge, which only exchanges the bricks some rank has touched. */
+int gsb_tsdf_sums_bricks(GsbVolume* vol, int to_sums, const uint32_t* bricks, uint32_t n_bricks, void* stream);
 
 /* Brick layout -> dense x*N^2... linear grids (dims = brick_count*16), for consumers that want
  * Open3D UniformTSDFVolume indexing.  tsdf / weight: device float [nx*ny*nz]. */

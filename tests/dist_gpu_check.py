@@ -46,8 +46,12 @@ def main():
 
     mine = shard_views(NV, rank, world)
     vol = fuse(mine)
-    vol.reduce_across_ranks(dst=None, chunk_bytes=1 << 20)  # all-reduce in many chunks
+    vol.reduce_across_ranks(dst=None, chunk_bytes=1 << 20)  # sparse merge (touched bricks only), many chunks
+    dense = fuse(mine)
+    dense.reduce_across_ranks(dst=None, chunk_bytes=1 << 22, sparse=False)  # whole-volume merge
     torch.cuda.synchronize()
+    assert torch.equal(vol.tsdf_weight, dense.tsdf_weight) and torch.equal(vol.color, dense.color), "sparse != dense merge"
+    del dense
     seq = fuse(range(NV))
     torch.cuda.synchronize()
     a = vol.bricks().cpu().numpy()
