@@ -50,7 +50,10 @@ def main():
     dense = fuse(mine)
     dense.reduce_across_ranks(dst=None, chunk_bytes=1 << 22, sparse=False)  # whole-volume merge
     torch.cuda.synchronize()
-    assert torch.equal(vol.tsdf_weight, dense.tsdf_weight) and torch.equal(vol.color, dense.color), "sparse != dense merge"
+    # same sums, but NCCL may associate them differently for the two buffer shapes: equal to rounding, same weights
+    assert torch.equal(vol.tsdf_weight.view(-1, 2)[:, 1], dense.tsdf_weight.view(-1, 2)[:, 1]), "sparse != dense merge (weights)"
+    assert float((vol.tsdf_weight - dense.tsdf_weight).abs().max()) <= 1e-6, "sparse != dense merge (tsdf)"
+    assert float((vol.color - dense.color).abs().max()) <= 1e-3, "sparse != dense merge (colour)"
     del dense
     seq = fuse(range(NV))
     torch.cuda.synchronize()
