@@ -61,6 +61,7 @@ SIGNATURES = {
     "gsb_tsdf_create": (_vp, [C.POINTER(GsbVolumeDesc)]),
     "gsb_tsdf_destroy": (None, [_vp]),
     "gsb_tsdf_prepare_depth": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_double, C.c_double, _vp, _vp]),
+    "gsb_mask_morphology": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "gsb_tsdf_integrate": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
                                      C.POINTER(C.c_double), _vp]),
     "gsb_tsdf_to_sums": (C.c_int, [_vp, _vp]),

@@ -231,6 +231,44 @@ __global__ void __launch_bounds__(256) prepare_depth_kernel(const float* __restr
   out[i] = d;
 }
 
+// k x k rectangular min (erode) / max (dilate) filter over a uint8 mask with OpenCV's window: anchor k/2, i.e. offsets
+// -(k/2) .. k-1-k/2 on both axes, pixels outside the image ignored (cv2.erode / cv2.dilate / MORPH_CLOSE with the default
+// border value; tsdf_utils.py:73-77).  One 64x16 output tile per CTA: halo tile -> smem, row pass, column pass.
+constexpr int kMorphTX = 64, kMorphTY = 16, kMorphMaxK = 64;
+__global__ void __launch_bounds__(256) morph_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W, int H, int k,
+                                                    int dilate) {
+  extern __shared__ uint8_t morph_sm[];
+  const int tw = kMorphTX + k - 1, th = kMorphTY + k - 1;
+  uint8_t* tile = morph_sm;            // [th][tw]
+  uint8_t* rows = morph_sm + th * tw;  // [th][kMorphTX]
+  const int ax = k / 2;
+  const int x0 = blockIdx.x * kMorphTX - ax, y0 = blockIdx.y * kMorphTY - ax;
+  const uint8_t neutral = dilate ? 0 : 255;
+  for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
+    const int x = x0 + i % tw, y = y0 + i / tw;
+    tile[i] = (x >= 0 && x < W && y >= 0 && y < H) ? in[(size_t)y * W + x] : neutral;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < th * kMorphTX; i += blockDim.x) {
+    const uint8_t* src = tile + (i / kMorphTX) * tw + i % kMorphTX;
+    uint8_t v = neutral;
+    for (int j = 0; j < k; ++j) v = dilate ? max(v, src[j]) : min(v, src[j]);
+    rows[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMorphTY * kMorphTX; i += blockDim.x) {
+    const int lx = i % kMorphTX, ly = i / kMorphTX;
+    const int x = blockIdx.x * kMorphTX + lx, y = blockIdx.y * kMorphTY + ly;
+    if (x >= W || y >= H) continue;
+    uint8_t v = neutral;
+    for (int j = 0; j < k; ++j) {
+      const uint8_t s = rows[(ly + j) * kMorphTX + lx];
+      v = dilate ? max(v, s) : min(v, s);
+    }
+    out[(size_t)y * W + x] = v;
+  }
+}
+
 // (mean, weight) <-> (sum, weight); mode 0: to sums, 1: from sums.  `bricks` == NULL: the whole store,
 // else only the listed bricks (one CTA-row of 2048 voxel pairs per brick).
 __global__ void __launch_bounds__(256) sums_kernel(float4* __restrict__ tw, float4* __restrict__ color, size_t n_pairs, int mode,
@@ -380,6 +418,20 @@ int gsb_tsdf_prepare_depth(const float* depth_in, const float* final_T, const ui
   }
   count_launch();
   return check_launch("prepare_depth_kernel", stream, false);
+}
+
+int gsb_mask_morphology(const uint8_t* mask_in, int32_t width, int32_t height, int32_t kernel_size, int32_t dilate, uint8_t* mask_out,
+                        void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!mask_in || !mask_out || mask_in == mask_out || width <= 0 || height <= 0)
+    return fail(GSB_ERR_INVALID, "mask_morphology: bad arguments (in-place filtering is not supported)");
+  if (kernel_size < 1 || kernel_size > kMorphMaxK) return fail(GSB_ERR_INVALID, "mask_morphology: kernel_size must be in 1..64");
+  const int tw = kMorphTX + kernel_size - 1, th = kMorphTY + kernel_size - 1;
+  const size_t smem = (size_t)th * tw + (size_t)th * kMorphTX;
+  dim3 grid((width + kMorphTX - 1) / kMorphTX, (height + kMorphTY - 1) / kMorphTY);
+  morph_kernel<<<grid, 256, smem, stream>>>(mask_in, mask_out, width, height, kernel_size, dilate != 0);
+  count_launch();
+  return check_launch("morph_kernel", stream, false);
 }
 
 int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, int32_t width, int32_t height, double fx,

@@ -218,6 +218,27 @@ class TSDFVolume:
         self.frames_integrated = 0
 
 
+def filter_object_mask(mask, closing_kernel_size: int = 10, erosion_kernel_size: int = 10, invert: bool = False, device="cuda"):
+    """tsdf_utils.py:69-77 on the GPU: optional inversion, cv2.morphologyEx(MORPH_CLOSE, ones(ck,ck)) (dilate, then
+    erode) and cv2.erode(ones(ek,ek)); returns a uint8 0/1 device mask [H,W] that `prepare_depth(mask=...)` takes."""
+    L = _lib.lib()
+    if not isinstance(mask, torch.Tensor):
+        mask = torch.as_tensor(np.ascontiguousarray(np.asarray(mask).astype(np.uint8)))
+    dev = mask.device if mask.is_cuda else torch.device(device)
+    m = (mask.to(dev) != 0)
+    if invert:
+        m = ~m
+    a = m.to(torch.uint8).contiguous()
+    h, w = a.shape
+    b = torch.empty_like(a)
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        for k, dilate in ((closing_kernel_size, 1), (closing_kernel_size, 0), (erosion_kernel_size, 0)):
+            _lib.check(L.gsb_mask_morphology(ptr(a), w, h, int(k), dilate, ptr(b), stream))
+            a, b = b, a
+    return a
+
+
 def reduce_sum_chunked(buffers, group=None, dst: Optional[int] = None, chunk_bytes: int = 256 << 20):
     """The one collective of the multi-GPU path: an in-place SUM reduce (all-reduce when dst is None)
     of each flat fp32 buffer, issued in `chunk_bytes` pieces so a 1024^3 volume (8.6 GB) does not
@@ -303,17 +324,13 @@ class TSDF:
             rgb = np.array(Image.open(os.path.join(out_dir, "left.png"))).astype(np.uint8)
             depth = np.load(os.path.join(out_dir, f"out_{self.model_name}", "depth.npy"))
         if self._arg("TSDF_use_mask", False):
-            import cv2
-
             m = np.load(os.path.join(out_dir, "left_mask.npy")).astype(bool)
-            if self._arg("TSDF_invert_mask", False):
-                m = ~m
-            if self._arg("TSDF_erode_mask", True):
-                ck = int(self._arg("TSDF_closing_kernel_size", 10))
-                ek = int(self._arg("TSDF_erosion_kernel_size", 10))
-                closing = cv2.morphologyEx(m.astype(np.uint8), cv2.MORPH_CLOSE, np.ones((ck, ck), np.uint8))
-                m = cv2.erode(closing, np.ones((ek, ek), np.uint8), iterations=1) > 0.5
-            obj_mask = m
+            invert = bool(self._arg("TSDF_invert_mask", False))
+            if self._arg("TSDF_erode_mask", True):  # tsdf_utils.py:72-77, on the GPU
+                obj_mask = filter_object_mask(m, int(self._arg("TSDF_closing_kernel_size", 10)),
+                                              int(self._arg("TSDF_erosion_kernel_size", 10)), invert, device=self.device)
+            else:
+                obj_mask = ~m if invert else m
         if self._arg("TSDF_use_occlusion_mask", True) and frame is None:
             occ_path = os.path.join(out_dir, f"out_{self.model_name}", "occlusion_mask.npy")
             if os.path.exists(occ_path):
@@ -348,13 +365,11 @@ class TSDF:
                 continue
             rgb, depth, obj_mask, occ_mask = self._load_view(camera_number)
             mask = None
-            if obj_mask is not None or occ_mask is not None:
-                mask = np.ones(np.asarray(obj_mask if obj_mask is not None else occ_mask).shape, dtype=bool)
-                if obj_mask is not None:
-                    mask &= obj_mask
-                if occ_mask is not None:
-                    mask &= occ_mask
-                mask = mask.astype(np.uint8)
+            for m in (obj_mask, occ_mask):  # depth * object_mask * occlusion_mask (tsdf_utils.py:78-81)
+                if m is None:
+                    continue
+                m = self.volume._u8(m if isinstance(m, torch.Tensor) else np.asarray(m).astype(np.uint8))
+                mask = m if mask is None else mask * m
             self.integrate(depth, rgb, left_camera, mask=mask)
         self.mesh = None
         return self.volume

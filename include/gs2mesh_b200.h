@@ -185,6 +185,12 @@ int gsb_tsdf_prepare_depth(const float* depth_in, const float* final_T, const ui
                            float alpha_min, float min_depth, double depth_scale, double depth_trunc, float* depth_out,
                            void* stream);
 
+/* T0 mask filters (tsdf_utils.py:73-77: cv2.morphologyEx(mask, MORPH_CLOSE, ones(k,k)) = dilate then erode, and
+ * cv2.erode(mask, ones(k,k))): one k x k rectangular max (dilate != 0) or min filter over a uint8 [H,W] device mask with
+ * OpenCV's window (anchor k/2; pixels outside the image ignored). kernel_size in 1..64; out must not alias in. */
+int gsb_mask_morphology(const uint8_t* mask_in, int32_t width, int32_t height, int32_t kernel_size, int32_t dilate,
+                        uint8_t* mask_out, void* stream);
+
 /* volume.integrate(rgbd, intrinsic, extrinsic): depth = prepared float depth [H,W] (device),
  * rgb = uint8 [H,W,3] (device) or NULL, extrinsic_w2c = row-major double[16] on the HOST
  * (what tsdf_utils.py:107 passes: inv(left_camera['extrinsic'])). */

@@ -364,3 +364,32 @@ def extract_mesh_from_bricks(tw, brick_origin, brick_count, voxel_length, color=
     return dict(keys=np.array(keys, np.int64).reshape(-1, 4), vertices=np.array(verts, np.float64).reshape(-1, 3),
                 colors=np.array(cols, np.float64).reshape(-1, 3) if col is not None else None,
                 triangles=np.array(tris, np.int64).reshape(-1, 3))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# T0 mask filters: numpy restatement of cv2.erode / cv2.dilate / cv2.morphologyEx(MORPH_CLOSE) with a k x k kernel of
+# ones and default anchor / border, as called at gs2mesh_utils/tsdf_utils.py:73-77.  OpenCV (opencv-python 4.x, an
+# un-vendored dependency of the reference) places the anchor at k/2 and ignores pixels outside the image; pinned
+# against cv2 itself in tests/test_oracle_tsdf.py::test_mask_morphology_matches_cv2.
+def mask_morphology(mask, k, dilate):
+    m = np.asarray(mask, dtype=np.uint8)
+    h, w = m.shape
+    ax = k // 2
+    neutral = 0 if dilate else 255
+    pad = np.full((h + k - 1, w + k - 1), neutral, np.uint8)
+    pad[ax:ax + h, ax:ax + w] = m
+    out = np.full((h, w), neutral, np.uint8)
+    op = np.maximum if dilate else np.minimum
+    for dy in range(k):
+        for dx in range(k):
+            out = op(out, pad[dy:dy + h, dx:dx + w])
+    return out
+
+
+def filter_object_mask(mask, closing_k=10, erosion_k=10, invert=False):
+    """tsdf_utils.py:69-77 -> bool mask."""
+    m = np.asarray(mask).astype(bool)
+    if invert:
+        m = ~m
+    closing = mask_morphology(mask_morphology(m.astype(np.uint8), closing_k, True), closing_k, False)
+    return mask_morphology(closing, erosion_k, False) > 0.5

@@ -1,8 +1,7 @@
-set -x
+#!/bin/bash
+# scratch: GPU run 12
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1
-echo "bench exit $?" >> gpurun_out/bench_default.log
-tail -2 gpurun_out/bench_default.log | cut -c1-250
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/run12_tests.log 2>&1
+tail -5 gpurun_out/run12_tests.log
+timeout 600 python bench.py --steps 100 --warmup 5 > gpurun_out/run12_bench.log 2>&1
+tail -1 gpurun_out/run12_bench.log

@@ -116,6 +116,59 @@ def test_tsdf_stage_in_memory_equals_files_equals_oracle(oracle, gsb_lib, cuda_d
     assert (tw[..., 1] > 0).sum() > 5000
 
 
+def test_tsdf_stage_object_masks_filtered_on_gpu(oracle, gsb_lib, cuda_device, small_scene, tmp_path):
+    """TSDF_use_mask / TSDF_invert_mask / TSDF_erode_mask (tsdf_utils.py:68-79): closing + erosion run on the GPU and the
+    fused volume equals the oracle fed with the cv2-restated filter."""
+    import torch
+
+    from gs2mesh_b200.renderer import Renderer
+    from gs2mesh_b200.tsdf import TSDF
+
+    class A(Args):
+        TSDF_use_mask = True
+        TSDF_invert_mask = True
+        TSDF_erode_mask = True
+        TSDF_closing_kernel_size = 10
+        TSDF_erosion_kernel_size = 6
+        TSDF_use_occlusion_mask = False
+        TSDF_skip = None
+
+    cloud, rigs, baseline = small_scene
+    r = Renderer.from_scene(rigs, baseline, cloud, output_dir_root=str(tmp_path), args=A(), device=str(cuda_device))
+    r.prepare_renderer()
+    rng = np.random.default_rng(3)
+    frames, masks = {}, {}
+    for i in range(NPAIRS):
+        out = r.render_image_pair(i)
+        depth = r.expected_depth(out["depth"], out["final_T"]).cpu().numpy()
+        frames[i] = (out["host_left_u8"].numpy().copy(), depth)
+        d = os.path.join(r.render_folder_name(i), f"out_{StereoStub.model_name}")
+        os.makedirs(d, exist_ok=True)
+        np.save(os.path.join(d, "depth.npy"), depth)
+        yy, xx = np.mgrid[0:H, 0:W]
+        m = (yy - H / 2) ** 2 + (xx - W / 2) ** 2 > (0.35 * H) ** 2  # stored mask = background; inverted -> object disc
+        m ^= rng.random((H, W)) < 0.03  # speckle the closing has to remove
+        masks[i] = m
+        np.save(os.path.join(r.render_folder_name(i), "left_mask.npy"), m)
+    r._frames = {}
+    vol = TSDF(r, StereoStub(), A(), "unit", window_resolution=128).run()
+    torch.cuda.synchronize()
+    got = vol.bricks().cpu().numpy()
+
+    ovol = oracle.OracleTSDFVolume(8.0 / 512, A.TSDF_sdf_trunc, with_color=True)
+    for i in range(NPAIRS):
+        rgb, depth = frames[i]
+        d = depth * oracle.filter_object_mask(masks[i], 10, 6, invert=True)
+        d = np.where(d < np.float32(A.TSDF_min_depth_baselines * baseline), 0, d).astype(np.float32)
+        c = rigs[i]["left"]
+        ovol.integrate(d, rgb, W, H, c["fx"], c["fy"], c["cx"], c["cy"], np.linalg.inv(c["extrinsic"]), depth_scale=1.0,
+                       depth_trunc=baseline * A.TSDF_max_depth_baselines)
+    tw, _, outside = ovol.export_bricks(vol.brick_origin, vol.brick_count)
+    assert outside < 50
+    np.testing.assert_array_equal(got, tw)
+    assert (tw[..., 1] > 0).sum() > 3000
+
+
 def test_full_size_properties(gsb_lib, cuda_device):
     """BASELINE config C1 shapes (1M Gaussians, 1600x1200, 512^3 lattice): properties that need no oracle."""
     import torch

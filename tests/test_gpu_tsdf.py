@@ -184,3 +184,37 @@ def test_invalid_inputs(gsb_lib, cuda_device):
         gvol.integrate(depth[:-1], None, W, H, FX, FY, CX, CY, np.eye(4))
     with pytest.raises(RuntimeError, match="singular"):
         gvol.integrate(depth, None, W, H, FX, FY, CX, CY, np.zeros((4, 4)))
+
+
+def test_mask_filters_bit_exact(oracle, gsb_lib, cuda_device):
+    """gsb_mask_morphology / filter_object_mask == the cv2 restatement (tsdf_utils.py:69-77), ragged sizes and kernel sizes."""
+    import torch
+
+    from gs2mesh_b200 import _lib
+    from gs2mesh_b200.tsdf import filter_object_mask
+    from tests.test_oracle_tsdf import _blob_mask
+
+    rng = np.random.default_rng(11)
+    for (h, w), k in (((37, 53), 10), ((130, 67), 3), ((20, 200), 7), ((9, 9), 10), ((31, 17), 1), ((240, 320), 64), ((1, 1), 2)):
+        m = _blob_mask(rng, h, w).astype(np.uint8) * rng.integers(1, 255, (h, w), dtype=np.uint8)  # general u8, not only 0/1
+        src = torch.as_tensor(m).to(cuda_device)
+        dst = torch.empty_like(src)
+        with torch.cuda.device(cuda_device):
+            stream = torch.cuda.current_stream().cuda_stream
+            for dilate in (0, 1):
+                _lib.check(gsb_lib.gsb_mask_morphology(_lib.ptr(src), w, h, k, dilate, _lib.ptr(dst), stream))
+                np.testing.assert_array_equal(dst.cpu().numpy(), oracle.mask_morphology(m, k, bool(dilate)))
+        got = filter_object_mask(m > 0, k, max(1, k // 2), invert=bool(k & 1), device=cuda_device)
+        np.testing.assert_array_equal(got.cpu().numpy() > 0, oracle.filter_object_mask(m > 0, k, max(1, k // 2), invert=bool(k & 1)))
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    if cv2 is not None:  # and against OpenCV itself at the reference's default sizes
+        m = _blob_mask(rng, 480, 640)
+        closing = cv2.morphologyEx(m.astype(np.uint8), cv2.MORPH_CLOSE, np.ones((10, 10), np.uint8))
+        want = cv2.erode(closing, np.ones((10, 10), np.uint8), iterations=1) > 0.5
+        np.testing.assert_array_equal(filter_object_mask(m, 10, 10, device=cuda_device).cpu().numpy() > 0, want)
+    src = torch.zeros(8, 8, dtype=torch.uint8, device=cuda_device)
+    assert gsb_lib.gsb_mask_morphology(_lib.ptr(src), 8, 8, 65, 0, _lib.ptr(torch.empty_like(src)), None) == _lib.GSB_ERR_INVALID
+    assert gsb_lib.gsb_mask_morphology(_lib.ptr(src), 8, 8, 3, 0, _lib.ptr(src), None) == _lib.GSB_ERR_INVALID

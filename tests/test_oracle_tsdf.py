@@ -122,3 +122,28 @@ def test_view_order_independence_and_sharded_merge(oracle):
     merged = merge_bricks_reference([fuse([0, 2]), fuse([1, 3])])
     np.testing.assert_array_equal(merged[..., 1], seq[..., 1])
     np.testing.assert_allclose(merged[..., 0], seq[..., 0], atol=1e-6)
+
+
+def _blob_mask(rng, h, w):
+    m = rng.random((h, w)) < 0.02
+    yy, xx = np.mgrid[0:h, 0:w]
+    m |= (yy - h * 0.5) ** 2 + (xx - w * 0.4) ** 2 < (0.3 * min(h, w)) ** 2
+    m &= rng.random((h, w)) > 0.05  # pin holes that the closing must fill
+    return m
+
+
+def test_mask_morphology_matches_cv2(oracle):
+    """oracle.mask_morphology / filter_object_mask vs OpenCV itself (the calls of tsdf_utils.py:73-77)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for (h, w), k in (((37, 53), 10), ((64, 64), 3), ((20, 90), 7), ((9, 9), 10), ((31, 17), 1), ((40, 40), 4)):
+        m = _blob_mask(rng, h, w)
+        kern = np.ones((k, k), np.uint8)
+        np.testing.assert_array_equal(oracle.mask_morphology(m, k, True), cv2.dilate(m.astype(np.uint8), kern))
+        np.testing.assert_array_equal(oracle.mask_morphology(m, k, False), cv2.erode(m.astype(np.uint8), kern, iterations=1))
+        closing = cv2.morphologyEx(m.astype(np.uint8), cv2.MORPH_CLOSE, kern)
+        want = cv2.erode(closing, kern, iterations=1) > 0.5
+        np.testing.assert_array_equal(oracle.filter_object_mask(m, k, k), want)
+    m = _blob_mask(rng, 48, 60)
+    closing = cv2.morphologyEx((~m).astype(np.uint8), cv2.MORPH_CLOSE, np.ones((10, 10), np.uint8))
+    np.testing.assert_array_equal(oracle.filter_object_mask(m, 10, 5, invert=True), cv2.erode(closing, np.ones((5, 5), np.uint8)) > 0.5)
