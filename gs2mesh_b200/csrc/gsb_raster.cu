@@ -138,8 +138,9 @@ __device__ __forceinline__ Footprint make_footprint(float a, float b, float c, f
   f.b = b;
   f.c = c;
   f.degenerate = !(a > 0.f && c > 0.f && a * c - b * b > 0.f);
-  f.nb_a = f.degenerate ? 0.f : -b / a;
-  f.nb_c = f.degenerate ? 0.f : -b / c;
+  // approximate division is enough: an error of a few ulp in the clamped minimiser changes q in second order only
+  f.nb_a = f.degenerate ? 0.f : __fdividef(-b, a);
+  f.nb_c = f.degenerate ? 0.f : __fdividef(-b, c);
   f.two_tau = two_tau;
   return f;
 }
@@ -151,17 +152,16 @@ __device__ __forceinline__ bool rect_can_contribute(float gxp, float gyp, const 
   if (dx_lo <= 0.f && dx_hi >= 0.f && dy_lo <= 0.f && dy_hi >= 0.f) return true;
   const float DX = fmaxf(fabsf(dx_lo), fabsf(dx_hi)), DY = fmaxf(fabsf(dy_lo), fabsf(dy_hi));
   const float margin = 1e-3f + 8e-6f * (f.a * DX * DX + f.c * DY * DY + 2.f * fabsf(f.b) * DX * DY);
-  float qmin = 3.0e38f;
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const float dx = e ? dx_hi : dx_lo;
-    const float dy = fminf(dy_hi, fmaxf(dy_lo, f.nb_c * dx));
-    qmin = fminf(qmin, f.a * dx * dx + 2.f * f.b * dx * dy + f.c * dy * dy);
-    const float ey = e ? dy_hi : dy_lo;
-    const float ex = fminf(dx_hi, fmaxf(dx_lo, f.nb_a * ey));
-    qmin = fminf(qmin, f.a * ex * ex + 2.f * f.b * ex * ey + f.c * ey * ey);
-  }
-  return qmin <= f.two_tau + margin;
+  // The centre lies outside the box, so the minimum of the (convex) quadratic over the box sits on an edge that faces the
+  // centre: the vertical edge nearer to it and the horizontal edge nearer to it.  (d = centre - pixel: the nearer edge is
+  // the one with the smaller |d|.)  An edge that does not face the centre only yields a value >= the minimum.
+  const float dx = fabsf(dx_lo) < fabsf(dx_hi) ? dx_lo : dx_hi;
+  const float dy = fminf(dy_hi, fmaxf(dy_lo, f.nb_c * dx));
+  const float qv = f.a * dx * dx + 2.f * f.b * dx * dy + f.c * dy * dy;
+  const float ey = fabsf(dy_lo) < fabsf(dy_hi) ? dy_lo : dy_hi;
+  const float ex = fminf(dx_hi, fmaxf(dx_lo, f.nb_a * ey));
+  const float qh = f.a * ex * ex + 2.f * f.b * ex * ey + f.c * ey * ey;
+  return fminf(qv, qh) <= f.two_tau + margin;
 }
 // __noinline__: the counting and the emitting kernel must execute the same instructions.
 __device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, float b, float c, float nb_a, float nb_c,

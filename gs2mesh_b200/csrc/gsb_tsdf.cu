@@ -97,7 +97,9 @@ __device__ __forceinline__ int project_voxel(const FrameParams& f, float pcx, fl
   if (!(u_f >= 0.0001f && u_f < f.safe_w && v_f >= 0.0001f && v_f < f.safe_h)) return -1;
   return ((int)v_f << 16) | (int)u_f;
 }
-__device__ __forceinline__ bool fuse_voxel(const FrameParams& f, int uv, float d, float pcz, float& tsdf, float& w) {
+// depth sample -> truncated distance `t` of one voxel; false if the voxel is not updated by this frame.  The decision does
+// not depend on the stored (tsdf, weight), so it is taken BEFORE the volume is read and only updated voxels are loaded.
+__device__ __forceinline__ bool sample_voxel(const FrameParams& f, int uv, float d, float pcz, float& t) {
   if (uv < 0 || d <= 0.0f) return false;
   const int u = uv & 0xffff, v = uv >> 16;
   // CreateDepthToCameraDistanceMultiplierFloatImage, recomputed per lookup
@@ -106,24 +108,38 @@ __device__ __forceinline__ bool fuse_voxel(const FrameParams& f, int uv, float d
   const float mult = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy)), 1.0f));
   const float sdf = __fmul_rn(__fsub_rn(d, pcz), mult);
   if (!(sdf > -f.trunc)) return false;
-  const float t = fminf(1.0f, __fmul_rn(sdf, f.trunc_inv));
-  tsdf = __fdiv_rn(__fadd_rn(__fmul_rn(tsdf, w), t), __fadd_rn(w, 1.0f));
-  w = __fadd_rn(w, 1.0f);
+  t = fminf(1.0f, __fmul_rn(sdf, f.trunc_inv));
   return true;
 }
-
-__device__ __forceinline__ void fuse_color(float4& c, float w_before, const uint8_t* __restrict__ rgb, int pix) {
-  const float r = (float)rgb[3 * (size_t)pix], g = (float)rgb[3 * (size_t)pix + 1], b = (float)rgb[3 * (size_t)pix + 2];
+// running weighted mean of one voxel (tsdf, weight) and its colour
+__device__ __forceinline__ void fuse_voxel(float t, float& tsdf, float& w) {
+  tsdf = __fdiv_rn(__fadd_rn(__fmul_rn(tsdf, w), t), __fadd_rn(w, 1.0f));
+  w = __fadd_rn(w, 1.0f);
+}
+__device__ __forceinline__ void fuse_color(float4& c, float w_before, uint32_t rgb) {
+  const float r = (float)(rgb & 0xffu), g = (float)((rgb >> 8) & 0xffu), b = (float)((rgb >> 16) & 0xffu);
   const float den = __fadd_rn(w_before, 1.0f);
   c.x = __fdiv_rn(__fadd_rn(__fmul_rn(c.x, w_before), r), den);
   c.y = __fdiv_rn(__fadd_rn(__fmul_rn(c.y, w_before), g), den);
   c.z = __fdiv_rn(__fadd_rn(__fmul_rn(c.z, w_before), b), den);
 }
+__device__ __forceinline__ uint32_t load_rgb(const uint8_t* __restrict__ rgb, int pix) {
+  const uint8_t* p = rgb + 3 * (size_t)pix;
+  return (uint32_t)__ldg(p) | (uint32_t)__ldg(p + 1) << 8 | (uint32_t)__ldg(p + 2) << 16;
+}
 
 constexpr int kIntThreads = 256;
 constexpr int kPasses = GSB_BRICK_VOXELS / 2 / kIntThreads;  // 8 voxel-pair passes per brick
+constexpr int kSweep = 2;                                    // passes handled together (4 voxels per thread)
 
-__global__ void __launch_bounds__(kIntThreads, 2) integrate_kernel(const FrameParams f, const float* __restrict__ depth,
+// One brick per CTA iteration, in sweeps of kSweep voxel-pair passes:
+//   (A) project the sweep's voxels, all depth gathers in flight (image reads hit L2)
+//   (B) per voxel: updated by this frame? -> t.  Threads with nothing to update skip the rest of the sweep.
+//   (C) loads of the UPDATED pairs only: (tsdf, weight), colour, rgb -- all in flight together
+//   (D) fuse + store
+// ~60% of the voxels of a touched brick lie outside the truncation band and are never read or written.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kIntThreads, kMinBlocks) integrate_kernel(const FrameParams f, const float* __restrict__ depth,
                                                                   const uint8_t* __restrict__ rgb, float4* __restrict__ tw,
                                                                   float4* __restrict__ color,
                                                                   const uint32_t* __restrict__ list,
@@ -133,81 +149,94 @@ __global__ void __launch_bounds__(kIntThreads, 2) integrate_kernel(const FramePa
   // thread -> voxel pair: pair q = pass*256 + t, first voxel 2q = (x, y, z) with
   //   x = 2*pass + (t >> 7), y = (t >> 3) & 15, z = 2 * (t & 7)
   const int y = (t >> 3) & 15, z0 = 2 * (t & 7), xo = t >> 7;
+  const bool with_color = color != nullptr && rgb != nullptr;
   for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
     const uint32_t brick = list[it];
     const int bz = brick % f.nb[2], by = (brick / f.nb[2]) % f.nb[1], bx = brick / (f.nb[2] * f.nb[1]);
     const double ox = (double)(f.b0[0] + bx) * f.unit_length;  // origin = index * unit_length (OpenVolumeUnit)
     const double oy = (double)(f.b0[1] + by) * f.unit_length;
     const double oz = (double)(f.b0[2] + bz) * f.unit_length;
-    float4* base = tw + (size_t)brick * (GSB_BRICK_VOXELS / 2);
-    // (1) all 8 (tsdf, weight) pair loads in flight
-    float4 v[kPasses];
-#pragma unroll
-    for (int p = 0; p < kPasses; ++p) v[p] = ld_stream(base + p * kIntThreads + t);
-
-    // (2) project all 16 voxels of this thread
+    float4* base = tw + (size_t)brick * (GSB_BRICK_VOXELS / 2) + t;
+    float4* cbase = color + ((size_t)brick * GSB_BRICK_VOXELS + 2 * (size_t)t);
     const float py = (float)((double)__fadd_rn(f.half, __fmul_rn(f.vl, (float)y)) + oy);
     const float pz = (float)((double)f.half + oz);
-    int uv[kPasses][2];
-    float cz[kPasses][2];
+    // the y/z part of extrinsic * (px,py,pz,1) is the same for all passes; the reference adds the four products left to right,
+    // so only the products (not their sum) can be hoisted
+    const float e1y = __fmul_rn(f.E[1], py), e2z = __fmul_rn(f.E[2], pz);
+    const float e5y = __fmul_rn(f.E[5], py), e6z = __fmul_rn(f.E[6], pz);
+    const float e9y = __fmul_rn(f.E[9], py), e10z = __fmul_rn(f.E[10], pz);
+#pragma unroll 1
+    for (int s = 0; s < kPasses; s += kSweep) {
+      int uv[kSweep][2];
+      float cz[kSweep][2];
 #pragma unroll
-    for (int p = 0; p < kPasses; ++p) {
-      const int x = 2 * p + xo;
-      const float px = (float)((double)__fadd_rn(f.half, __fmul_rn(f.vl, (float)x)) + ox);
-      // pt_camera = extrinsic * (px,py,pz,1), then z0 incremental steps along the brick's z axis
-      float cxm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.E[0], px), __fmul_rn(f.E[1], py)), __fmul_rn(f.E[2], pz)), f.E[3]);
-      float cym = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.E[4], px), __fmul_rn(f.E[5], py)), __fmul_rn(f.E[6], pz)), f.E[7]);
-      float czm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.E[8], px), __fmul_rn(f.E[9], py)), __fmul_rn(f.E[10], pz)), f.E[11]);
-      for (int k = 0; k < z0; ++k) {
+      for (int p = 0; p < kSweep; ++p) {
+        const int x = 2 * (s + p) + xo;
+        const float px = (float)((double)__fadd_rn(f.half, __fmul_rn(f.vl, (float)x)) + ox);
+        // pt_camera = extrinsic * (px,py,pz,1), then z0 incremental steps along the brick's z axis
+        float cxm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.E[0], px), e1y), e2z), f.E[3]);
+        float cym = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.E[4], px), e5y), e6z), f.E[7]);
+        float czm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.E[8], px), e9y), e10z), f.E[11]);
+        for (int k = 0; k < z0; ++k) {
+          cxm = __fadd_rn(cxm, f.sx);
+          cym = __fadd_rn(cym, f.sy);
+          czm = __fadd_rn(czm, f.sz);
+        }
+        uv[p][0] = project_voxel(f, cxm, cym, czm);
+        cz[p][0] = czm;
         cxm = __fadd_rn(cxm, f.sx);
         cym = __fadd_rn(cym, f.sy);
         czm = __fadd_rn(czm, f.sz);
+        uv[p][1] = project_voxel(f, cxm, cym, czm);
+        cz[p][1] = czm;
       }
-      uv[p][0] = project_voxel(f, cxm, cym, czm);
-      cz[p][0] = czm;
-      cxm = __fadd_rn(cxm, f.sx);
-      cym = __fadd_rn(cym, f.sy);
-      czm = __fadd_rn(czm, f.sz);
-      uv[p][1] = project_voxel(f, cxm, cym, czm);
-      cz[p][1] = czm;
-    }
-    // (3) all depth gathers in flight
-    float dd[kPasses][2];
+      float dd[kSweep][2];
 #pragma unroll
-    for (int p = 0; p < kPasses; ++p)
+      for (int p = 0; p < kSweep; ++p)
 #pragma unroll
-      for (int e = 0; e < 2; ++e)
-        dd[p][e] = uv[p][e] >= 0 ? __ldg(depth + (uv[p][e] >> 16) * f.W + (uv[p][e] & 0xffff)) : 0.f;
-    // (4) fuse, store the pairs that changed
-    uint32_t changed = 0;  // bit 2p+e
+        for (int e = 0; e < 2; ++e)
+          dd[p][e] = uv[p][e] >= 0 ? __ldg(depth + (uv[p][e] >> 16) * f.W + (uv[p][e] & 0xffff)) : 0.f;
+      uint32_t upd = 0;  // bit 2p+e
+      float tt[kSweep][2];
 #pragma unroll
-    for (int p = 0; p < kPasses; ++p) {
-      const bool up0 = fuse_voxel(f, uv[p][0], dd[p][0], cz[p][0], v[p].x, v[p].y);
-      const bool up1 = fuse_voxel(f, uv[p][1], dd[p][1], cz[p][1], v[p].z, v[p].w);
-      if (up0 || up1) st_stream(base + p * kIntThreads + t, v[p]);
-      changed |= (up0 ? 1u : 0u) << (2 * p) | (up1 ? 1u : 0u) << (2 * p + 1);
-    }
-    // (5) colour of the voxels that changed, four passes' loads in flight at a time
-    if (color != nullptr && rgb != nullptr && changed) {
+      for (int p = 0; p < kSweep; ++p)
 #pragma unroll
-      for (int g = 0; g < kPasses; g += 4) {
-        float4 c[4][2];
+        for (int e = 0; e < 2; ++e) upd |= (sample_voxel(f, uv[p][e], dd[p][e], cz[p][e], tt[p][e]) ? 1u : 0u) << (2 * p + e);
+      if (upd == 0) continue;
+
+      float4 v[kSweep];
+      float4 c[kSweep][2];
+      uint32_t px8[kSweep][2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+      for (int p = 0; p < kSweep; ++p)
+        if (upd >> (2 * p) & 3u) v[p] = ld_stream(base + (s + p) * kIntThreads);
+      if (with_color) {
+#pragma unroll
+        for (int p = 0; p < kSweep; ++p)
 #pragma unroll
           for (int e = 0; e < 2; ++e)
-            if (changed >> (2 * (g + q) + e) & 1u)
-              c[q][e] = ld_stream(color + ((size_t)brick * GSB_BRICK_VOXELS + 2 * (size_t)((g + q) * kIntThreads + t) + e));
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-            if (changed >> (2 * (g + q) + e) & 1u) {
-              const int p = g + q;
-              const float w_new = e ? v[p].w : v[p].y;
-              fuse_color(c[q][e], __fsub_rn(w_new, 1.0f), rgb, (uv[p][e] >> 16) * f.W + (uv[p][e] & 0xffff));
-              st_stream(color + ((size_t)brick * GSB_BRICK_VOXELS + 2 * (size_t)(p * kIntThreads + t) + e), c[q][e]);
+            if (upd >> (2 * p + e) & 1u) {
+              c[p][e] = ld_stream(cbase + 2 * (size_t)((s + p) * kIntThreads) + e);
+              px8[p][e] = load_rgb(rgb, (uv[p][e] >> 16) * f.W + (uv[p][e] & 0xffff));
             }
+      }
+#pragma unroll
+      for (int p = 0; p < kSweep; ++p) {
+        if (!(upd >> (2 * p) & 3u)) continue;
+        const float w0 = v[p].y, w1 = v[p].w;
+        if (upd >> (2 * p) & 1u) fuse_voxel(tt[p][0], v[p].x, v[p].y);
+        if (upd >> (2 * p + 1) & 1u) fuse_voxel(tt[p][1], v[p].z, v[p].w);
+        st_stream(base + (s + p) * kIntThreads, v[p]);
+        if (with_color) {
+          if (upd >> (2 * p) & 1u) {
+            fuse_color(c[p][0], w0, px8[p][0]);
+            st_stream(cbase + 2 * (size_t)((s + p) * kIntThreads), c[p][0]);
+          }
+          if (upd >> (2 * p + 1) & 1u) {
+            fuse_color(c[p][1], w1, px8[p][1]);
+            st_stream(cbase + 2 * (size_t)((s + p) * kIntThreads) + 1, c[p][1]);
+          }
+        }
       }
     }
   }
@@ -500,8 +529,16 @@ int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, i
   const int grid = (int)((size_t)num_sms() * 8 < vol->n_bricks ? (size_t)num_sms() * 8 : vol->n_bricks);
   {
     StageTimer tm(kStIntegrate, stream);
-    integrate_kernel<<<grid, kIntThreads, 0, stream>>>(f, depth, rgb, reinterpret_cast<float4*>(d.tsdf_weight),
-                                                       reinterpret_cast<float4*>(d.color), d.brick_list, d.counters);
+    static const int occ = [] {  // A/B switch for profiling: GSB_INTEGRATE_OCC=3 -> 85 registers, no spills
+      const char* e = getenv("GSB_INTEGRATE_OCC");
+      return e ? atoi(e) : 4;
+    }();
+    if (occ == 3)
+      integrate_kernel<3><<<grid, kIntThreads, 0, stream>>>(f, depth, rgb, reinterpret_cast<float4*>(d.tsdf_weight),
+                                                            reinterpret_cast<float4*>(d.color), d.brick_list, d.counters);
+    else
+      integrate_kernel<4><<<grid, kIntThreads, 0, stream>>>(f, depth, rgb, reinterpret_cast<float4*>(d.tsdf_weight),
+                                                            reinterpret_cast<float4*>(d.color), d.brick_list, d.counters);
   }
   count_launch();
   return check_launch("integrate_kernel", stream, false);
