@@ -178,6 +178,44 @@ __device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, 
   return rect_can_contribute(gxp, gyp, f, x0, y0, x0 + (kTile - 1), y0 + (kTile - 1));
 }
 
+// Candidate tiles under the exact test: the reference rectangle intersected with the tiles that overlap the axis-aligned
+// bounding box of the ellipse q(d) <= tau (half extents sqrt(tau c / det), sqrt(tau a / det)).  tau carries the same
+// rounding allowance as rect_can_contribute's margin (its S term is <= 4 tau k over the box, k = ac/det); very elongated
+// conics (k > 1000) keep the reference rectangle.  Explicitly rounded operations only: the binning, the emitting and the
+// validation kernel must all arrive at the same rectangle.
+constexpr uint32_t kRectLarge = 0xffffffffu;  // packed-rectangle sentinel: no mask stored, re-test when emitting
+__device__ __forceinline__ TileRect shrink_rect(TileRect r, float px, float py, const Footprint& f) {
+  if (f.degenerate) return r;
+  const float ac = __fmul_rn(f.a, f.c);
+  const float det = __fsub_rn(ac, __fmul_rn(f.b, f.b));
+  const float k = __fdiv_rn(ac, det);
+  if (!(k <= 1000.f)) return r;
+  const float tau = __fmul_rn(__fadd_rn(f.two_tau, 2e-3f), __fadd_rn(1.f, __fmul_rn(5e-5f, k)));
+  if (!(tau > 0.f)) {  // opacity < 1/255: nothing can be blended
+    r.x1 = r.x0;
+    r.y1 = r.y0;
+    return r;
+  }
+  const float hx = __fadd_rn(__fmul_rn(__fsqrt_rn(__fdiv_rn(__fmul_rn(tau, f.c), det)), 1.0001f), 0.01f);
+  const float hy = __fadd_rn(__fmul_rn(__fsqrt_rn(__fdiv_rn(__fmul_rn(tau, f.a), det)), 1.0001f), 0.01f);
+  const float inv = 1.0f / kTile;  // power of two: exact
+  const float lox = floorf(__fmul_rn(__fsub_rn(px, hx), inv)), hix = floorf(__fmul_rn(__fadd_rn(px, hx), inv));
+  const float loy = floorf(__fmul_rn(__fsub_rn(py, hy), inv)), hiy = floorf(__fmul_rn(__fadd_rn(py, hy), inv));
+  // compare in float (the bounds may be negative or huge), then convert
+  const float x0 = fmaxf((float)r.x0, lox), x1 = fminf((float)r.x1, hix + 1.f);
+  const float y0 = fmaxf((float)r.y0, loy), y1 = fminf((float)r.y1, hiy + 1.f);
+  if (!(x0 < x1 && y0 < y1)) {
+    r.x1 = r.x0;
+    r.y1 = r.y0;
+    return r;
+  }
+  r.x0 = (uint32_t)x0;
+  r.x1 = (uint32_t)x1;
+  r.y0 = (uint32_t)y0;
+  r.y1 = (uint32_t)y1;
+  return r;
+}
+
 // Warp-flattened binning.  The candidate tiles of the warp's 32 Gaussians (rectangles of up to
 // kMaskTiles tiles) are laid end to end and tested 32 at a time with every lane busy, instead of
 // each lane looping over its own rectangle.  Returns this lane's kept-tile count; for rectangles
@@ -188,7 +226,7 @@ __device__ __noinline__ bool tile_can_contribute(float gxp, float gyp, float a, 
 constexpr uint32_t kMaskTiles = 64;
 __device__ __forceinline__ uint32_t bin_gaussians_warp(bool active, float px, float py, float ca, float cb, float cc,
                                                        float opacity, int radius, uint32_t gx, uint32_t gy, bool exact,
-                                                       float4* stage, uint64_t& mask) {
+                                                       float4* stage, uint64_t& mask, uint32_t& rect_word) {
   const int lane = threadIdx.x & 31;
   TileRect rc{0, 0, 0, 0};
   uint32_t w = 0, area = 0;
@@ -196,15 +234,18 @@ __device__ __forceinline__ uint32_t bin_gaussians_warp(bool active, float px, fl
   bool test = false;
   if (active) {
     rc = tile_rect(px, py, radius, gx, gy);
-    w = rc.x1 - rc.x0;
-    area = w * (rc.y1 - rc.y0);
     if (exact) {
       fp = make_footprint(ca, cb, cc, 2.f * logf(255.f * opacity));
       test = !fp.degenerate;
+      rc = shrink_rect(rc, px, py, fp);
     }
+    w = rc.x1 - rc.x0;
+    area = w * (rc.y1 - rc.y0);
   }
   mask = 0ull;
   const bool small = active && area <= kMaskTiles;
+  // what the emit pass needs to replay the mask: x0 (13 bits) | y0 (13 bits) | w - 1 (6 bits)
+  rect_word = (small && area != 0) ? (rc.x0 | (rc.y0 << 13) | ((w - 1u) << 26)) : kRectLarge;
   if (small && !test) mask = area == 64 ? ~0ull : ((1ull << area) - 1ull);  // rectangle binning: everything kept
   const uint32_t cand = (small && test) ? area : 0u;
   uint32_t incl = cand;
@@ -313,7 +354,8 @@ struct PreParams {
   unsigned long long* ref_count;  // sum of reference tile rectangles
   uint32_t* depth_keys;           // view-depth sort key per Gaussian (0xffffffff = not binned)
   uint32_t* ids;                  // identity permutation, the sort's payload
-  uint64_t* masks;                // kept-tile bitmask of rectangles with <= 64 tiles
+  uint64_t* masks;                // kept-tile bitmask of candidate rectangles with <= 64 tiles
+  uint32_t* rects;                // packed candidate rectangle the mask refers to (kRectLarge: none)
 };
 
 struct WarpStage {  // one warp's staged parameter block; every member offset is a multiple of 128 B
@@ -499,8 +541,10 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
   // footprints during binning (32 x 2 float4 = 1024 bytes)
   __syncwarp();
   uint64_t tile_mask = 0ull;
+  uint32_t rect_word = kRectLarge;
   ntiles = bin_gaussians_warp(visible, px, py, ca, cb, cc, opacity, radius, p.gx, p.gy,
-                              (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, reinterpret_cast<float4*>(st.rot), tile_mask);
+                              (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, reinterpret_cast<float4*>(st.rot), tile_mask,
+                              rect_word);
 
   // ---- stage 2: colour ------------------------------------------------------------------------
   float cr = 0.f, cg = 0.f, cbl = 0.f;
@@ -573,7 +617,10 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
     if (p.depth_keys) {
       p.depth_keys[idx] = ntiles ? __float_as_uint(zv) : 0xffffffffu;  // z_view > 0.2: bit order == float order
       p.ids[idx] = (uint32_t)idx;
-      p.masks[idx] = tile_mask;
+      if (ntiles) {
+        p.masks[idx] = tile_mask;
+        p.rects[idx] = rect_word;
+      }
     }
   }
   unsigned long long wsum = nref;
@@ -601,11 +648,12 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const float4
   if ((int64_t)end > capacity) return;  // host reports GSB_ERR_WORKSPACE
   const float4 A = recA[idx];
   const float4 B = recB[idx];
-  const TileRect rc = tile_rect(A.x, A.y, radii[idx], gx, gy);
+  TileRect rc = tile_rect(A.x, A.y, radii[idx], gx, gy);
   const uint32_t depth_bits = __float_as_uint(A.z);
   const bool exact = flags & GSB_RASTER_EXACT_TILE_CULL;
   const Footprint fp = make_footprint(B.x, B.y, B.z, exact ? 2.f * logf(255.f * A.w) : 0.f);
   const bool test = exact && !fp.degenerate;
+  if (exact) rc = shrink_rect(rc, A.x, A.y, fp);
   for (uint32_t ty = rc.y0; ty < rc.y1; ++ty)
     for (uint32_t tx = rc.x0; tx < rc.x1; ++tx) {
       if (test && !tile_can_contribute(A.x, A.y, fp.a, fp.b, fp.c, fp.nb_a, fp.nb_c, fp.two_tau, tx, ty)) continue;
@@ -714,7 +762,8 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
                                                           const uint32_t* __restrict__ offsets,
                                                           const float4* __restrict__ recA, const float4* __restrict__ recB,
                                                           const uint32_t* __restrict__ tiles, const int* __restrict__ radii,
-                                                          const uint64_t* __restrict__ masks, uint32_t gx, uint32_t gy,
+                                                          const uint64_t* __restrict__ masks,
+                                                          const uint32_t* __restrict__ rects, uint32_t gx, uint32_t gy,
                                                           uint32_t flags, const unsigned long long* __restrict__ counters,
                                                           uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
                                                           uint32_t* __restrict__ ghist, int hist_passes) {
@@ -729,32 +778,19 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool fits = counters[2] == 0;
-  uint32_t gid = 0, off = 0;
+  uint32_t gid = 0, off = 0, rect = kRectLarge;
   bool active = false;
   if (k < P && fits) {
     gid = ids_sorted[k];
     active = tiles[gid] != 0;
     off = offsets[k];
   }
-  float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
-  int radius = 0;
-  TileRect rc{0, 0, 0, 0};
-  uint32_t w = 0, area = 0;
   uint64_t mask = 0ull;
-  if (active) {
-    A = recA[gid];
-    radius = radii[gid];
-    rc = tile_rect(A.x, A.y, radius, gx, gy);
-    w = rc.x1 - rc.x0;
-    area = w * (rc.y1 - rc.y0);
-    if (area <= kMaskTiles)
-      mask = masks[gid];
-    else
-      B = recB[gid];
-  }
-  const bool small = active && area <= kMaskTiles;
-  // ---- flattened replay of the stored masks
-  const uint32_t cand = small ? area : 0u;
+  if (active) rect = rects[gid];
+  const bool small = active && rect != kRectLarge;
+  if (small) mask = masks[gid];
+  // ---- flattened replay of the stored masks (bits up to the highest kept tile of each rectangle)
+  const uint32_t cand = small ? 64u - (uint32_t)__clzll((long long)mask) : 0u;
   uint32_t incl = cand;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -778,15 +814,17 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
     }
     const int owner = lo;
     const uint32_t olo = __shfl_sync(0xffffffffu, mlo, owner), ohi = __shfl_sync(0xffffffffu, mhi, owner);
-    const uint32_t ox0 = __shfl_sync(0xffffffffu, rc.x0, owner), oy0 = __shfl_sync(0xffffffffu, rc.y0, owner);
-    const uint32_t ow = __shfl_sync(0xffffffffu, w, owner), oex = __shfl_sync(0xffffffffu, excl, owner);
+    const uint32_t orect = __shfl_sync(0xffffffffu, rect, owner), oex = __shfl_sync(0xffffffffu, excl, owner);
     const uint32_t ooff = __shfl_sync(0xffffffffu, off, owner), ogid = __shfl_sync(0xffffffffu, gid, owner);
     if (fidx < total) {
       const uint32_t kk = fidx - oex;
       const uint64_t om = ((uint64_t)ohi << 32) | olo;
       if ((om >> kk) & 1ull) {
         const uint32_t ordinal = (uint32_t)__popcll(om & ((1ull << kk) - 1ull));
-        const uint32_t tile = (oy0 + kk / ow) * gx + ox0 + kk % ow;
+        const uint32_t ow = (orect >> 26) + 1u;
+        // kk / ow for kk < 64, ow <= 64: (kk + 0.5) / ow is never within rounding distance of an integer
+        const uint32_t row = (uint32_t)__float2int_rd(__fdividef((float)kk + 0.5f, (float)ow));
+        const uint32_t tile = (((orect >> 13) & 0x1fffu) + row) * gx + (orect & 0x1fffu) + (kk - row * ow);
         tile_keys[ooff + ordinal] = tile;
         tile_vals[ooff + ordinal] = ogid;
         tally(tile);
@@ -795,11 +833,22 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
   }
   // ---- rectangles without a mask: re-test, whole warp per Gaussian, ordered by ballot
   const bool exact = (flags & GSB_RASTER_EXACT_TILE_CULL) != 0;
+  float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+  TileRect rc{0, 0, 0, 0};
+  uint32_t w = 0, area = 0;
   Footprint fp = make_footprint(1.f, 0.f, 1.f, 0.f);
   bool test = false;
-  if (active && !small && exact) {
-    fp = make_footprint(B.x, B.y, B.z, 2.f * logf(255.f * A.w));
-    test = !fp.degenerate;
+  if (active && !small) {
+    A = recA[gid];
+    rc = tile_rect(A.x, A.y, radii[gid], gx, gy);
+    if (exact) {
+      const float4 B = recB[gid];
+      fp = make_footprint(B.x, B.y, B.z, 2.f * logf(255.f * A.w));
+      test = !fp.degenerate;
+      rc = shrink_rect(rc, A.x, A.y, fp);
+    }
+    w = rc.x1 - rc.x0;
+    area = w * (rc.y1 - rc.y0);
   }
   const uint32_t lt_mask = (1u << lane) - 1u;
   unsigned todo = __ballot_sync(0xffffffffu, active && !small);
@@ -1179,6 +1228,7 @@ struct Workspace {
   uint32_t* ids_b;
   uint32_t* sorted_offsets;
   uint64_t* masks;
+  uint32_t* rects;
   uint32_t* block_sums;
   uint32_t* radix_scratch;
   uint64_t* keys_in;
@@ -1211,6 +1261,7 @@ Workspace carve(void* base, int32_t P, int32_t W, int32_t H, int64_t R) {
   w.ids_b = c.take<uint32_t>(Pn);
   w.sorted_offsets = c.take<uint32_t>(Pn);
   w.masks = c.take<uint64_t>(Pn);
+  w.rects = c.take<uint32_t>(Pn);
   w.block_sums = c.take<uint32_t>((Pn + kScanBlock - 1) / kScanBlock + 1);
   w.radix_scratch = c.take<uint32_t>(radix_scratch_words(std::max(Pn, Rn)));
   w.keys_in = c.take<uint64_t>(Rn);
@@ -1275,6 +1326,8 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!a) return fail(GSB_ERR_INVALID, "args is NULL");
   if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(GSB_ERR_INVALID, "bad P / image size");
+  if (a->width > 8191 * kTile || a->height > 8191 * kTile)  // packed candidate rectangles hold 13-bit tile coordinates
+    return fail(GSB_ERR_INVALID, "image side exceeds %d pixels", 8191 * kTile);
   if (!a->out_color || !a->background || !a->viewmatrix || !a->projmatrix || !a->cam_pos)
     return fail(GSB_ERR_INVALID, "out_color, background, viewmatrix, projmatrix and cam_pos are required");
   // DGR/diff_gaussian_rasterization/__init__.py:191-195
@@ -1346,6 +1399,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   pp.depth_keys = use_cub ? nullptr : ws.depth_a;
   pp.ids = use_cub ? nullptr : ws.ids_a;
   pp.masks = ws.masks;
+  pp.rects = ws.rects;
   GSB_CUDA_OK(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream));
   const int pre_blocks = (P + kPreThreads - 1) / kPreThreads;
   {
@@ -1427,7 +1481,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
       StageTimer tm(kStEmit, stream);
       radix_prepare(rs, (size_t)cap, tile_bits, stream);
       emit_sorted_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ids_sorted, ws.sorted_offsets, ws.recA, ws.recB, ws.tiles,
-                                                              pp.radii, ws.masks, gx, gy, a->flags, ws.counters, tk_a, tv_a,
+                                                              pp.radii, ws.masks, ws.rects, gx, gy, a->flags, ws.counters, tk_a, tv_a,
                                                               radix_ghist(rs), (tile_bits + 7) / 8);
       init_ranges_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream>>>(ws.ranges, (uint32_t)ntiles);
       nl += 2;
