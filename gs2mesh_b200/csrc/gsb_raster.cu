@@ -1167,6 +1167,144 @@ __global__ void __launch_bounds__(kTilePixels, 5) render_warp_kernel(const uint2
   }
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Compacting variant of render_warp_kernel: the lanes whose Gaussian passed the warp's footprint test
+// store their record at consecutive 48-byte slots (ballot rank) of the warp's private list, so the
+// blend loop walks plain consecutive addresses (no bit scan, no per-hit address arithmetic) and is
+// branch-free: the three thresholds of forward.cu:336-353 become predicates that gate a weight
+// w = alpha*T (0 when the pixel skips the Gaussian) and the transmittance update.  An all-zero
+// sentinel record (opacity 0 -> alpha 0 -> skipped) pads an odd hit count so the loop always takes
+// two records per trip.  Thresholds are decided on exactly the same alpha / T values as in
+// render_warp_kernel; colours accumulate as fma(c, alpha*T, C) instead of fma(c*alpha, T, C)
+// (<= 1 ulp per term).
+constexpr int kDefaultRenderImpl = 1;        // 0 block, 1 warp, 2 compact (GSB_RENDER_IMPL overrides)
+constexpr int kSlotBytes = 48;               // A (16) | B (16) | green, blue (8) | pad (8)
+constexpr int kSlotsPerBuf = 33;             // 32 hits + sentinel
+// kPix = pixels per lane: 1 -> 8 warps per tile, each an 8x4 block; 2 -> 4 warps per tile, each an 8x8 block whose
+// lanes own (x, y) and (x, y + 4): the list walk, the footprint test and the record loads are shared by 64 pixels.
+template <bool kFastExp, int kPix>
+__global__ void __launch_bounds__(kTilePixels / kPix, kPix == 1 ? 5 : 8)
+    render_compact_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+                          const float4* __restrict__ recA, const float4* __restrict__ recB, const float2* __restrict__ recC,
+                          const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
+                          float* __restrict__ out_T, int64_t capacity) {
+  constexpr int kWarps = 8 / kPix;
+  __shared__ __align__(16) unsigned char slots[kWarps][2][kSlotsPerBuf * kSlotBytes];
+  const uint32_t tiles_x = (W + kTile - 1) / kTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t a0 = smem_u32(&slots[warp][0][0]);
+  const uint32_t blk_x = blockIdx.x * kTile + (warp & 1) * 8, blk_y = blockIdx.y * kTile + (warp >> 1) * (4 * kPix);
+  const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
+  const float pfx = (float)pix_x;
+  const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 4 * kPix - 1);
+  uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
+  if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);
+  const int total = range.y - range.x;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  bool inside[kPix], done[kPix];
+  float pfy[kPix], T[kPix], C0[kPix], C1[kPix], C2[kPix], Dz[kPix];
+#pragma unroll
+  for (int k = 0; k < kPix; ++k) {
+    inside[k] = pix_x < (uint32_t)W && pix_y + 4 * k < (uint32_t)H;
+    done[k] = !inside[k];
+    pfy[k] = (float)(pix_y + 4 * k);
+    T[k] = 1.0f;
+    C0[k] = C1[k] = C2[k] = Dz[k] = 0.f;
+  }
+
+  float4 cA = make_float4(0.f, 0.f, 0.f, 0.f), cB = cA, nA = cA, nB = cA;
+  float2 cC = make_float2(0.f, 0.f), nC = cC;
+  if (lane < total) {
+    const uint32_t g = point_list[range.x + lane];
+    cA = recA[g];
+    cB = recB[g];
+    cC = recC[g];
+  }
+  // one Gaussian of the warp's list against this lane's pixel(s)
+  auto blend = [&](uint32_t addr) {
+    const float4 A = lds128(addr), B = lds128(addr + 16);
+    const float2 gb = lds64(addr + 32);
+    const float dx = A.x - pfx;
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) {
+      const float dy = A.y - pfy[k];
+      const float power = -0.5f * (B.x * dx * dx + B.z * dy * dy) - B.y * dx * dy;
+      const float e = kFastExp ? ex2_ftz(power * 1.4426950408889634f) : exp(power);
+      const float alpha = min(0.99f, A.w * e);
+      const float test_T = T[k] * (1 - alpha);
+      const bool cand = !done[k] && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+      const bool sat = cand && test_T < 0.0001f;
+      const bool ok = cand && !sat;
+      done[k] = done[k] || sat;
+      const float w = ok ? alpha * T[k] : 0.f;
+      C0[k] = fmaf(B.w, w, C0[k]);
+      C1[k] = fmaf(gb.x, w, C1[k]);
+      C2[k] = fmaf(gb.y, w, C2[k]);
+      Dz[k] = fmaf(A.z, w, Dz[k]);
+      T[k] = ok ? test_T : T[k];
+    }
+  };
+  for (int c0 = 0; c0 < total; c0 += 32) {
+    bool all_done = done[0];
+#pragma unroll
+    for (int k = 1; k < kPix; ++k) all_done = all_done && done[k];
+    if (__all_sync(0xffffffffu, all_done)) break;
+    const int nxt = c0 + 32 + lane;
+    if (nxt < total) {  // next chunk's gathers fly while this one is tested and blended
+      const uint32_t g = point_list[range.x + nxt];
+      nA = recA[g];
+      nB = recB[g];
+      nC = recC[g];
+    }
+    bool hit = false;
+    if (c0 + lane < total) {
+      const Footprint fp = make_footprint(cB.x, cB.y, cB.z, 2.f * __logf(255.f * cA.w) + 1e-3f);
+      hit = rect_can_contribute(cA.x, cA.y, fp, bx0, by0, bx1, by1);
+    }
+    const unsigned votes = __ballot_sync(0xffffffffu, hit);
+    const int n = __popc(votes);
+    const uint32_t buf = a0 + ((c0 >> 5) & 1) * (kSlotsPerBuf * kSlotBytes);
+    if (hit) {
+      const uint32_t dst = buf + __popc(votes & lt_mask) * kSlotBytes;
+      sts128(dst, cA);
+      sts128(dst + 16, cB);
+      sts64(dst + 32, cC);
+    }
+    if (lane == 0) {  // sentinel after the last hit
+      const uint32_t dst = buf + n * kSlotBytes;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      sts128(dst, z);
+      sts128(dst + 16, z);
+      sts64(dst + 32, make_float2(0.f, 0.f));
+    }
+    __syncwarp();  // the list is visible to every lane of the warp
+    uint32_t addr = buf;
+    for (int j = 0; j < n; j += 2, addr += 2 * kSlotBytes) {
+      blend(addr);
+      blend(addr + kSlotBytes);
+    }
+    cA = nA;
+    cB = nB;
+    cC = nC;
+  }
+  const size_t plane = (size_t)H * W;
+#pragma unroll
+  for (int k = 0; k < kPix; ++k)
+    if (inside[k]) {
+      const size_t pid = (size_t)(pix_y + 4 * k) * W + pix_x;
+      out_color[pid] = C0[k] + T[k] * bg[0];
+      out_color[plane + pid] = C1[k] + T[k] * bg[1];
+      out_color[2 * plane + pid] = C2[k] + T[k] * bg[2];
+      if (out_depth) out_depth[pid] = Dz[k];
+      if (out_T) out_T[pid] = T[k];
+    }
+}
+
 __global__ void write_counts_kernel(const uint32_t* __restrict__ offsets, int P, const unsigned long long* counters,
                                     int64_t* out) {
   // offsets != NULL: validation path (instance total = last element of the per-Gaussian scan)
@@ -1503,14 +1641,31 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   {
     StageTimer tm(kStRender, stream);
     static const int render_impl = [] {
-      const char* e = getenv("GSB_RENDER_IMPL");  // A/B switch for profiling: "block" = barrier-per-batch variant
-      return (e && e[0] == 'b') ? 0 : 1;
+      // A/B switch for profiling: "block" = barrier-per-batch variant, "warp" = per-warp bit-scan variant,
+      // "compact" = per-warp compacted hit list with a branch-free blend
+      const char* e = getenv("GSB_RENDER_IMPL");
+      if (e && e[0] == 'b') return 0;
+      if (e && e[0] == 'c') return 2;
+      if (e && e[0] == 'd') return 3;  // "dual": compact, two pixels per lane
+      if (e && e[0] == 'w') return 1;
+      return kDefaultRenderImpl;
     }();
     const bool fast = (a->flags & GSB_RASTER_FAST_EXP) != 0;
-#define GSB_LAUNCH_RENDER(KERNEL)                                                                                            \
-  KERNEL<<<dim3(gx, gy), kTilePixels, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, \
-                                                   a->out_color, a->out_depth, a->out_final_T, cap)
-    if (render_impl == 1) {
+#define GSB_LAUNCH_RENDER_T(THREADS, ...)                                                                                \
+  __VA_ARGS__<<<dim3(gx, gy), THREADS, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, \
+                                                    a->out_color, a->out_depth, a->out_final_T, cap)
+#define GSB_LAUNCH_RENDER(KERNEL) GSB_LAUNCH_RENDER_T(kTilePixels, KERNEL)
+    if (render_impl == 3) {
+      if (fast)
+        GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<true, 2>);
+      else
+        GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<false, 2>);
+    } else if (render_impl == 2) {
+      if (fast)
+        GSB_LAUNCH_RENDER_T(kTilePixels, render_compact_kernel<true, 1>);
+      else
+        GSB_LAUNCH_RENDER_T(kTilePixels, render_compact_kernel<false, 1>);
+    } else if (render_impl == 1) {
       if (fast)
         GSB_LAUNCH_RENDER(render_warp_kernel<true>);
       else
@@ -1522,6 +1677,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
         GSB_LAUNCH_RENDER(render_kernel<false>);
     }
 #undef GSB_LAUNCH_RENDER
+#undef GSB_LAUNCH_RENDER_T
   }
   count_launch();
   if ((rc = check_launch("render_kernel", stream, dbg))) return rc;
