@@ -13,6 +13,8 @@
 // memory and written out in runs.
 #pragma once
 
+#include <cstdlib>
+
 #include "gsb_common.h"
 
 namespace gsb {
@@ -20,10 +22,14 @@ namespace {
 
 constexpr int kRdxThreads = 256;
 constexpr int kRdxWarps = kRdxThreads / 32;
-constexpr int kRdxItems = 16;                          // items per thread
+constexpr int kRdxItems = 16;                          // items per thread of the R-sized (instance) sorts
 constexpr int kRdxBlock = kRdxThreads * kRdxItems;     // 4096 items per CTA
 constexpr int kRdxBins = 256;
 constexpr int kRdxMaxPasses = 4;
+constexpr int kRdxWindow = 8;                          // predecessors inspected per look-back round
+constexpr int kRdxDefaultPItems = 16;                  // items per thread of small sorts; GSB_RADIX_P_ITEMS overrides
+constexpr size_t kRdxSmallSort = 1u << 22;             // sorts of up to 4M items count as "small" (the P-sized depth sort)
+constexpr int kRdxDefaultWindowed = 1;                 // GSB_RADIX_LOOKBACK=serial|window overrides (A/B switch)
 
 // status word of (block, digit): [31:30] 0 = not ready, 1 = block aggregate, 2 = inclusive prefix
 constexpr uint32_t kStAgg = 1u << 30, kStIncl = 2u << 30, kStVal = (1u << 30) - 1u;
@@ -38,20 +44,36 @@ __device__ __forceinline__ uint32_t radix_count(uint32_t n_host, const unsigned 
 }
 
 // Digit histograms of every pass in one read of the keys: ghist[pass][digit].
+template <int kItems>
 __global__ void __launch_bounds__(kRdxThreads) radix_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n_host,
                                                                      const unsigned long long* __restrict__ counters,
                                                                      int64_t capacity, int passes,
                                                                      uint32_t* __restrict__ ghist) {
   __shared__ uint32_t hist[kRdxMaxPasses][kRdxBins];
   const uint32_t n = radix_count(n_host, counters, capacity);
-  const uint32_t base = blockIdx.x * kRdxBlock;
+  const uint32_t base = blockIdx.x * (kRdxThreads * kItems);
   if (base >= n) return;
   for (int p = 0; p < passes; ++p) hist[p][threadIdx.x] = 0;
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < kRdxItems; ++k) {
+  for (int k = 0; k < kItems; ++k) {
     const uint32_t i = base + k * kRdxThreads + threadIdx.x;
-    if (i < n) {
+    const uint32_t wbase = i - (threadIdx.x & 31);  // first item of this warp's 32
+    if (wbase + 32 <= n) {
+      // full warp.  Depth keys of one view share their upper bytes, tile ids of neighbouring instances their
+      // upper byte: when all 32 lanes agree on a digit one lane adds 32 instead of 32 serialised atomics.
+      const uint32_t key = keys[i];
+      for (int p = 0; p < passes; ++p) {
+        const uint32_t dgt = (key >> (8 * p)) & (kRdxBins - 1);
+        int same;
+        __match_all_sync(0xffffffffu, dgt, &same);
+        if (same) {
+          if ((threadIdx.x & 31) == 0) atomicAdd(&hist[p][dgt], 32u);
+        } else {
+          atomicAdd(&hist[p][dgt], 1u);
+        }
+      }
+    } else if (i < n) {
       const uint32_t key = keys[i];
       for (int p = 0; p < passes; ++p) atomicAdd(&hist[p][(key >> (8 * p)) & (kRdxBins - 1)], 1u);
     }
@@ -76,7 +98,10 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
 // `ticket` = block-order counter, both zeroed before the sort.  When `ranges` != NULL this is the last
 // pass of the tile sort: keys are then fully sorted tile ids and the first / last instance of every
 // tile seen by the block updates ranges[tile] = (start, end) with atomicMin / atomicMax.
-__global__ void __launch_bounds__(kRdxThreads, 3) radix_pass_kernel(const uint32_t* __restrict__ keys_in,
+// kItems = items per thread: 16 for the R-sized instance sorts; the P-sized depth sort, whose whole grid is co-resident
+// and therefore runs at the latency of ONE block, may use smaller blocks (more, shorter critical paths).
+template <int kItems>
+__global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ? 4 : 5)) radix_pass_kernel(const uint32_t* __restrict__ keys_in,
                                                                 const uint32_t* __restrict__ vals_in,
                                                                 uint32_t* __restrict__ keys_out,
                                                                 uint32_t* __restrict__ vals_out, uint32_t n_host,
@@ -84,9 +109,10 @@ __global__ void __launch_bounds__(kRdxThreads, 3) radix_pass_kernel(const uint32
                                                                 int64_t capacity, int shift,
                                                                 const uint32_t* __restrict__ ghist,
                                                                 uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                                                                uint2* __restrict__ ranges) {
-  __shared__ uint32_t s_key[kRdxBlock];
-  __shared__ uint32_t s_val[kRdxBlock];
+                                                                uint2* __restrict__ ranges, int window, int write_keys) {
+  constexpr int kBlock = kRdxThreads * kItems;
+  __shared__ uint32_t s_key[kBlock];
+  __shared__ uint32_t s_val[kBlock];
   __shared__ uint32_t warp_hist[kRdxWarps][kRdxBins];  // per-warp digit counts -> per-warp bases
   __shared__ uint32_t digit_start[kRdxBins];           // first local slot of each digit in this block
   __shared__ uint32_t global_off[kRdxBins];            // global output position of that slot
@@ -100,18 +126,18 @@ __global__ void __launch_bounds__(kRdxThreads, 3) radix_pass_kernel(const uint32
   for (int w = 0; w < kRdxWarps; ++w) warp_hist[w][threadIdx.x] = 0;
   __syncthreads();
   const uint32_t bid = s_bid;
-  const uint32_t base = bid * kRdxBlock;
+  const uint32_t base = bid * kBlock;
   if (base >= n) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t count = min((uint32_t)kRdxBlock, n - base);
+  const uint32_t count = min((uint32_t)kBlock, n - base);
 
-  // ---- phase 1: each warp walks its contiguous 512-item segment in order and ranks its items
-  uint32_t key[kRdxItems], val[kRdxItems];
-  uint32_t lrank[kRdxItems];  // rank among same-digit items of this warp's segment
-  const uint32_t seg = base + warp * (kRdxBlock / kRdxWarps);
+  // ---- phase 1: each warp walks its contiguous (32 * kItems)-item segment in order and ranks its items
+  uint32_t key[kItems], val[kItems];
+  uint32_t lrank[kItems];  // rank among same-digit items of this warp's segment
+  const uint32_t seg = base + warp * (kBlock / kRdxWarps);
 #pragma unroll
-  for (int k = 0; k < kRdxItems; ++k) {
+  for (int k = 0; k < kItems; ++k) {
     const uint32_t i = seg + k * 32 + lane;
     const bool ok = i < n;
     key[k] = ok ? keys_in[i] : 0xffffffffu;
@@ -142,15 +168,42 @@ __global__ void __launch_bounds__(kRdxThreads, 3) radix_pass_kernel(const uint32
     st_status(my, (bid == 0 ? kStIncl : kStAgg) | run);
     uint32_t prev = 0;
     if (bid > 0) {
-      for (int64_t b = (int64_t)bid - 1; b >= 0; --b) {
-        const uint32_t* sp = status + (size_t)b * kRdxBins + d;
-        uint32_t sv = ld_status(sp);
-        for (uint32_t spin = 0; (sv >> 30) == 0; ++spin) {
-          if (spin > (1u << 24)) __trap();  // a predecessor never published: fail loudly instead of hanging
-          sv = ld_status(sp);
+      if (window <= 1) {
+        for (int64_t b = (int64_t)bid - 1; b >= 0; --b) {
+          const uint32_t* sp = status + (size_t)b * kRdxBins + d;
+          uint32_t sv = ld_status(sp);
+          for (uint32_t spin = 0; (sv >> 30) == 0; ++spin) {
+            if (spin > (1u << 24)) __trap();  // a predecessor never published: fail loudly instead of hanging
+            sv = ld_status(sp);
+          }
+          prev += sv & kStVal;
+          if ((sv >> 30) == 2) break;
         }
-        prev += sv & kStVal;
-        if ((sv >> 30) == 2) break;
+      } else {
+        // Windowed look-back: the status words of kRdxWindow predecessors are requested at once (independent
+        // loads), then consumed newest-first.  When every block of a pass starts at the same time (the whole
+        // P-sized grid is co-resident) a one-word-at-a-time walk costs ~nblocks/2 dependent L2 round trips;
+        // this cuts the chain by the window length.  Every word is self-contained (flag + count), so a
+        // speculative read of an older word is valid whatever state the newer ones were in.
+        bool closed = false;
+        for (int64_t b = (int64_t)bid - 1; !closed; b -= kRdxWindow) {
+          uint32_t sv[kRdxWindow];
+#pragma unroll
+          for (int j = 0; j < kRdxWindow; ++j)
+            sv[j] = b - j >= 0 ? ld_status(status + (size_t)(b - j) * kRdxBins + d) : kStIncl;  // before block 0: prefix 0
+#pragma unroll
+          for (int j = 0; j < kRdxWindow; ++j) {
+            if (!closed) {
+              uint32_t v = sv[j];
+              for (uint32_t spin = 0; (v >> 30) == 0; ++spin) {
+                if (spin > (1u << 24)) __trap();  // a predecessor never published: fail loudly instead of hanging
+                v = ld_status(status + (size_t)(b - j) * kRdxBins + d);
+              }
+              prev += v & kStVal;
+              closed = (v >> 30) == 2;
+            }
+          }
+        }
       }
       st_status(my, kStIncl | (prev + run));
     }
@@ -189,7 +242,7 @@ __global__ void __launch_bounds__(kRdxThreads, 3) radix_pass_kernel(const uint32
 
   // ---- phase 3: stage the block's items in digit order
 #pragma unroll
-  for (int k = 0; k < kRdxItems; ++k) {
+  for (int k = 0; k < kItems; ++k) {
     const uint32_t i = seg + k * 32 + lane;
     if (i < n) {
       const uint32_t d = (key[k] >> shift) & (kRdxBins - 1);
@@ -205,7 +258,7 @@ __global__ void __launch_bounds__(kRdxThreads, 3) radix_pass_kernel(const uint32
     const uint32_t kk = s_key[sidx];
     const uint32_t d = (kk >> shift) & (kRdxBins - 1);
     const uint32_t dst = global_off[d] + (sidx - digit_start[d]);
-    keys_out[dst] = kk;
+    if (write_keys) keys_out[dst] = kk;  // nobody reads the keys of a sort's last pass
     vals_out[dst] = s_val[sidx];
     if (ranges != nullptr) {
       // slots are in ascending tile order inside the block (stable LSD => low digit sorted within high digit)
@@ -215,9 +268,33 @@ __global__ void __launch_bounds__(kRdxThreads, 3) radix_pass_kernel(const uint32
   }
 }
 
-// Scratch words one sort needs for `max_items` items.
+inline int radix_lookback_window() {
+  static const int w = [] {
+    const char* e = getenv("GSB_RADIX_LOOKBACK");
+    if (e && e[0] == 's') return 1;
+    if (e && e[0] == 'w') return kRdxWindow;
+    return kRdxDefaultWindowed ? kRdxWindow : 1;
+  }();
+  return w;
+}
+
+// Items per thread of a sort over at most `max_items` items.
+inline int radix_items_for(size_t max_items) {
+  static const int p_items = [] {
+    const char* e = getenv("GSB_RADIX_P_ITEMS");  // A/B switch: 4 | 8 | 16
+    const int v = e ? atoi(e) : kRdxDefaultPItems;
+    return (v == 4 || v == 8) ? v : 16;
+  }();
+  return max_items <= kRdxSmallSort ? p_items : kRdxItems;
+}
+inline size_t radix_blocks_for(size_t max_items) {
+  const size_t block = (size_t)kRdxThreads * radix_items_for(max_items);
+  return (max_items + block - 1) / block;
+}
+
+// Scratch words one sort needs for `max_items` items (sized for the smallest block either sort may use).
 inline size_t radix_scratch_words(size_t max_items) {
-  const size_t nblocks = (max_items + kRdxBlock - 1) / kRdxBlock;
+  const size_t nblocks = (max_items + kRdxThreads * 4 - 1) / (kRdxThreads * 4);
   return (size_t)kRdxMaxPasses * (kRdxBins + nblocks * kRdxBins + 1) + 64;
 }
 
@@ -226,7 +303,7 @@ inline uint32_t* radix_ghist(uint32_t* scratch) { return scratch; }
 
 // Zeroes the histogram / ticket / status words one sort over `max_items` items with `bits` key bits needs.
 inline void radix_prepare(uint32_t* scratch, size_t max_items, int bits, cudaStream_t stream) {
-  const size_t nblocks = (max_items + kRdxBlock - 1) / kRdxBlock;
+  const size_t nblocks = radix_blocks_for(max_items);
   const int passes = (bits + 7) / 8;
   const size_t words = (size_t)kRdxMaxPasses * kRdxBins + 64 + (size_t)passes * nblocks * kRdxBins;
   cudaMemsetAsync(scratch, 0, words * sizeof(uint32_t), stream);
@@ -236,11 +313,12 @@ inline void radix_prepare(uint32_t* scratch, size_t max_items, int bits, cudaStr
 // ping-pong buffers; returns which buffer holds the result (0 = a, 1 = b).  n is either the host
 // value (counters == NULL) or read on the device from counters[1] (clamped by capacity).
 // histogram_ready: the caller already ran radix_prepare() and filled the digit histograms.
-inline int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_host,
-                            const unsigned long long* counters, int64_t capacity, size_t max_items, int bits,
-                            uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches,
-                            bool histogram_ready) {
-  const uint32_t nblocks = (uint32_t)((max_items + kRdxBlock - 1) / kRdxBlock);
+template <int kItems>
+inline int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_host,
+                              const unsigned long long* counters, int64_t capacity, size_t max_items, int bits,
+                              uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches,
+                              bool histogram_ready) {
+  const uint32_t nblocks = (uint32_t)radix_blocks_for(max_items);
   if (nblocks == 0) return 0;
   const int passes = (bits + 7) / 8;
   uint32_t* ghist = scratch;                                    // [kRdxMaxPasses][256]
@@ -248,7 +326,7 @@ inline int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b
   uint32_t* status = tickets + 64;                               // [passes][nblocks][256]
   if (!histogram_ready) {
     radix_prepare(scratch, max_items, bits, stream);
-    radix_histogram_kernel<<<nblocks, kRdxThreads, 0, stream>>>(keys_a, n_host, counters, capacity, passes, ghist);
+    radix_histogram_kernel<kItems><<<nblocks, kRdxThreads, 0, stream>>>(keys_a, n_host, counters, capacity, passes, ghist);
     *launches += 1;
   }
   int cur = 0;
@@ -257,13 +335,28 @@ inline int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b
     const uint32_t* vin = cur ? vals_b : vals_a;
     uint32_t* kout = cur ? keys_a : keys_b;
     uint32_t* vout = cur ? vals_a : vals_b;
-    radix_pass_kernel<<<nblocks, kRdxThreads, 0, stream>>>(kin, vin, kout, vout, n_host, counters, capacity, 8 * p,
-                                                           ghist + p * kRdxBins, status + (size_t)p * nblocks * kRdxBins,
-                                                           tickets + p, p == passes - 1 ? ranges_on_last_pass : nullptr);
+    radix_pass_kernel<kItems><<<nblocks, kRdxThreads, 0, stream>>>(
+        kin, vin, kout, vout, n_host, counters, capacity, 8 * p, ghist + p * kRdxBins, status + (size_t)p * nblocks * kRdxBins,
+        tickets + p, p == passes - 1 ? ranges_on_last_pass : nullptr, radix_lookback_window(), p != passes - 1);
     *launches += 1;
     cur ^= 1;
   }
   return cur;
+}
+
+inline int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_host,
+                            const unsigned long long* counters, int64_t capacity, size_t max_items, int bits,
+                            uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches,
+                            bool histogram_ready) {
+#define GSB_RADIX_CALL(ITEMS)                                                                                              \
+  radix_sort_pairs_t<ITEMS>(keys_a, vals_a, keys_b, vals_b, n_host, counters, capacity, max_items, bits, scratch,          \
+                            ranges_on_last_pass, stream, launches, histogram_ready)
+  switch (radix_items_for(max_items)) {
+    case 4: return GSB_RADIX_CALL(4);
+    case 8: return GSB_RADIX_CALL(8);
+    default: return GSB_RADIX_CALL(16);
+  }
+#undef GSB_RADIX_CALL
 }
 
 }  // namespace

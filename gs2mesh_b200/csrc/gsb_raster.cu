@@ -329,6 +329,37 @@ __device__ __forceinline__ uint32_t bin_gaussians_warp(bool active, float px, fl
   return kept;
 }
 
+// forward.cu:20-71 (computeColorFromSH): `sh(i)` = i-th float of the Gaussian's [M,3] coefficient block.
+template <class Acc>
+__device__ __forceinline__ void eval_sh(int D, Acc sh, float3 dir, float res[3]) {
+  const float SH_C0 = 0.28209479177387814f, SH_C1 = 0.4886025119029199f;
+  const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                          0.5462742152960396f};
+  const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                          -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = SH_C0 * sh(ch);
+    if (D > 0) {
+      const float x = dir.x, y = dir.y, z = dir.z;
+      v = v - SH_C1 * y * sh(3 + ch) + SH_C1 * z * sh(6 + ch) - SH_C1 * x * sh(9 + ch);
+      if (D > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        v = v + SH_C2[0] * xy * sh(12 + ch) + SH_C2[1] * yz * sh(15 + ch) + SH_C2[2] * (2.0f * zz - xx - yy) * sh(18 + ch) +
+            SH_C2[3] * xz * sh(21 + ch) + SH_C2[4] * (xx - yy) * sh(24 + ch);
+        if (D > 2) {
+          v = v + SH_C3[0] * y * (3.0f * xx - yy) * sh(27 + ch) + SH_C3[1] * xy * z * sh(30 + ch) +
+              SH_C3[2] * y * (4.0f * zz - xx - yy) * sh(33 + ch) + SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh(36 + ch) +
+              SH_C3[4] * x * (4.0f * zz - xx - yy) * sh(39 + ch) + SH_C3[5] * z * (xx - yy) * sh(42 + ch) +
+              SH_C3[6] * x * (xx - 3.0f * yy) * sh(45 + ch);
+        }
+      }
+    }
+    v += 0.5f;
+    res[ch] = max(v, 0.0f);
+  }
+}
+
 struct PreParams {
   int P, D, M, W, H;
   const float* means3D;
@@ -346,6 +377,8 @@ struct PreParams {
   uint32_t gx, gy;
   uint32_t flags;
   int use_tma;
+  int sh_mode;  // staging of full-degree SH blocks (M = 16): 0 linear + scalar reads, 1 linear + 16-byte reads,
+                // 2 one 192-byte bulk copy per lane into padded slots + 16-byte reads (bank-conflict free)
   float4* recA;
   float4* recB;
   float2* recC;
@@ -358,8 +391,10 @@ struct PreParams {
   uint32_t* rects;                // packed candidate rectangle the mask refers to (kRectLarge: none)
 };
 
+constexpr int kDefaultShMode = 1;                // GSB_PRE_SH overrides (A/B switch)
+constexpr int kShPadStride = kMaxShFloats + 4;  // 208-byte slots: 16-byte reads of 32 lanes hit distinct banks
 struct WarpStage {  // one warp's staged parameter block; every member offset is a multiple of 128 B
-  float sh[32 * kMaxShFloats];  // 6144 B
+  float sh[32 * kShPadStride];  // 6656 B
   float rot[32 * 4];            // 512 B
   float xyz[32 * 3];            // 384 B
   float scale[32 * 3];          // 384 B
@@ -533,9 +568,16 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
   const int shf = p.M * 3;  // SH floats per Gaussian
   const bool need_sh = p.colors == nullptr && any_visible;
   const bool tma_sh = need_sh && full_tma && (shf * 4) % 16 == 0 && shf <= kMaxShFloats;
-  if (tma_sh && lane == 0) {
-    mbar_expect_tx(&st.bar, (uint32_t)(32 * shf * 4));
-    tma_load_1d(st.sh, p.shs + (size_t)base * shf, (uint32_t)(32 * shf * 4), &st.bar);
+  const int sh_mode = shf == kMaxShFloats ? p.sh_mode : 0;
+  const int sh_stride = sh_mode == 2 ? kShPadStride : shf;
+  if (tma_sh) {
+    if (lane == 0) mbar_expect_tx(&st.bar, (uint32_t)(32 * shf * 4));
+    if (sh_mode == 2) {
+      __syncwarp();  // the transaction count is armed before any lane's copy can complete
+      tma_load_1d(st.sh + lane * kShPadStride, p.shs + (size_t)(base + lane) * shf, (uint32_t)(shf * 4), &st.bar);
+    } else if (lane == 0) {
+      tma_load_1d(st.sh, p.shs + (size_t)base * shf, (uint32_t)(32 * shf * 4), &st.bar);
+    }
   }
   // the staged rotations / positions / scales are dead by now: their 1280 bytes carry the lanes'
   // footprints during binning (32 x 2 float4 = 1024 bytes)
@@ -553,46 +595,32 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
       if (tma_sh) {
         mbar_wait(&st.bar, 1);
       } else {
-        for (int k = lane; k < count * shf; k += 32) st.sh[k] = p.shs[(size_t)base * shf + k];
+        for (int k = lane; k < count * shf; k += 32) st.sh[(k / shf) * sh_stride + k % shf] = p.shs[(size_t)base * shf + k];
         __syncwarp();
       }
       if (visible) {
-        // forward.cu:20-71
-        const float* sh = st.sh + lane * shf;
         const float3 cam = make_float3(p.campos[0], p.campos[1], p.campos[2]);
         float3 dir = make_float3(pos.x - cam.x, pos.y - cam.y, pos.z - cam.z);
         const float len = sqrt(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
         dir.x = dir.x / len;
         dir.y = dir.y / len;
         dir.z = dir.z / len;
-        const float SH_C0 = 0.28209479177387814f, SH_C1 = 0.4886025119029199f;
-        const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
-                                0.5462742152960396f};
-        const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
-                                -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
         float res[3];
+        const float* sh = st.sh + lane * sh_stride;
+        if (sh_mode != 0) {  // 12 x 16-byte reads, then the same arithmetic from registers
+          float shreg[kMaxShFloats];
+          const float4* s4 = reinterpret_cast<const float4*>(sh);
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          float v = SH_C0 * sh[ch];
-          if (p.D > 0) {
-            const float x = dir.x, y = dir.y, z = dir.z;
-            v = v - SH_C1 * y * sh[3 + ch] + SH_C1 * z * sh[6 + ch] - SH_C1 * x * sh[9 + ch];
-            if (p.D > 1) {
-              const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-              v = v + SH_C2[0] * xy * sh[12 + ch] + SH_C2[1] * yz * sh[15 + ch] +
-                  SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + ch] + SH_C2[3] * xz * sh[21 + ch] +
-                  SH_C2[4] * (xx - yy) * sh[24 + ch];
-              if (p.D > 2) {
-                v = v + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + ch] + SH_C3[1] * xy * z * sh[30 + ch] +
-                    SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + ch] +
-                    SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + ch] +
-                    SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + ch] + SH_C3[5] * z * (xx - yy) * sh[42 + ch] +
-                    SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + ch];
-              }
-            }
+          for (int k = 0; k < kMaxShFloats / 4; ++k) {
+            const float4 v4 = s4[k];
+            shreg[4 * k] = v4.x;
+            shreg[4 * k + 1] = v4.y;
+            shreg[4 * k + 2] = v4.z;
+            shreg[4 * k + 3] = v4.w;
           }
-          v += 0.5f;
-          res[ch] = max(v, 0.0f);
+          eval_sh(p.D, [&](int i) { return shreg[i]; }, dir, res);
+        } else {
+          eval_sh(p.D, [&](int i) { return sh[i]; }, dir, res);
         }
         cr = res[0];
         cg = res[1];
@@ -1182,7 +1210,7 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // two records per trip.  Thresholds are decided on exactly the same alpha / T values as in
 // render_warp_kernel; colours accumulate as fma(c, alpha*T, C) instead of fma(c*alpha, T, C)
 // (<= 1 ulp per term).
-constexpr int kDefaultRenderImpl = 1;        // 0 block, 1 warp, 2 compact (GSB_RENDER_IMPL overrides)
+constexpr int kDefaultRenderImpl = 2;        // 0 block, 1 warp, 2 compact (GSB_RENDER_IMPL overrides)
 constexpr int kSlotBytes = 48;               // A (16) | B (16) | green, blue (8) | pad (8)
 constexpr int kSlotsPerBuf = 33;             // 32 hits + sentinel
 // kPix = pixels per lane: 1 -> 8 warps per tile, each an 8x4 block; 2 -> 4 warps per tile, each an 8x8 block whose
@@ -1525,6 +1553,14 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   pp.flags = a->flags;
   pp.use_tma = !(a->flags & GSB_RASTER_NO_TMA) && aligned16(a->means3D) && aligned16(a->opacities) &&
                (!has_sr || (aligned16(a->scales) && aligned16(a->rotations))) && (!a->shs || aligned16(a->shs));
+  static const int sh_mode_default = [] {
+    const char* e = getenv("GSB_PRE_SH");  // A/B switch: "scalar" | "vec" | "padded"
+    if (e && e[0] == 's') return 0;
+    if (e && e[0] == 'v') return 1;
+    if (e && e[0] == 'p') return 2;
+    return kDefaultShMode;
+  }();
+  pp.sh_mode = sh_mode_default;
   pp.recA = ws.recA;
   pp.recB = ws.recB;
   pp.recC = ws.recC;

@@ -31,6 +31,9 @@ from . import camera as cam
 from . import rasterizer as rast
 
 
+DEFAULT_PAIRS_IN_FLIGHT = 1
+
+
 class _PairReady:
     """Completion handle of an asynchronously rendered pair (render_image_pair(..., wait=False))."""
 
@@ -75,6 +78,8 @@ class Renderer:
         # render the left and the right eye on two side streams (each with its own scratch) so that the
         # small latency-bound binning kernels of one eye overlap the other eye's blend kernel
         self.overlap_eyes = True
+        # how many stereo pairs may be in flight at once (stream sets); GSB_PAIRS_IN_FLIGHT overrides (A/B switch)
+        self.pairs_in_flight = int(os.environ.get("GSB_PAIRS_IN_FLIGHT", DEFAULT_PAIRS_IN_FLIGHT))
         self.keep_frames = False
         self._frames = {}
         self._ready = False
@@ -209,9 +214,15 @@ class Renderer:
                 # which also covers a caller that consumes pair n only after enqueuing pair n+1 (wait=False)
                 self._call_index = getattr(self, "_call_index", -1) + 1
                 slot = self._call_index % 3
-                if not hasattr(self, "_side_streams"):
-                    self._side_streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+                depth = max(1, int(self.pairs_in_flight))
+                if not hasattr(self, "_side_streams") or len(self._side_streams) != depth:
+                    # `pairs_in_flight` sets of (left, right) streams, used round-robin: consecutive pairs run on
+                    # different stream sets (each stream has its own scratch), so pair n+1's latency-bound binning
+                    # kernels fill the gaps of pair n's blend kernels
+                    self._side_streams = [[torch.cuda.Stream(dev), torch.cuda.Stream(dev)] for _ in range(depth)]
+                if not hasattr(self, "_entry_events"):
                     self._entry_events = [None, None, None]
+                    self._slot_done = [[], [], []]
                 b = self._buffers(vt.width, vt.height, slot)
                 entry = torch.cuda.Event()
                 entry.record(main)
@@ -219,12 +230,14 @@ class Renderer:
                 # stream before the PREVIOUS call was entered
                 gate = self._entry_events[(self._call_index - 1) % 3]
                 self._entry_events[slot] = entry
-                streams = self._side_streams
+                streams = self._side_streams[self._call_index % depth]
                 for st in streams:
                     if gate is not None:
                         st.wait_event(gate)
                     else:
                         st.wait_stream(main)
+                    for done in self._slot_done[slot]:  # the renders that last wrote this buffer set (another stream set)
+                        st.wait_event(done)
             else:
                 b = self._buffers(vt.width, vt.height)
                 streams = [main, main]
@@ -241,6 +254,8 @@ class Renderer:
                 for s in range(2):
                     with torch.cuda.stream(streams[s]):
                         b["host_u8"][s].copy_(b["u8"][s], non_blocking=True)
+            if self.overlap_eyes:
+                self._slot_done[slot] = [st.record_event() for st in streams]
             asynchronous = to_host and not wait and not self.write_images and self.overlap_eyes
             if self.overlap_eyes and not asynchronous:
                 for st in streams:
