@@ -281,13 +281,15 @@ def run_ours(args, cfg, rank, local, world):
     K_e2e = K
     barrier(world)
     t0 = time.perf_counter()
-    # software-pipelined by one pair: while the host consumes pair i (waits for its frames, reads the depth back,
-    # hands depth + colour to TSDF.integrate, which uploads them), pair i+1 is already being rendered
+    # software-pipelined by `pairs_in_flight` pairs: while the host consumes pair i (waits for its frames, reads the
+    # depth back, hands depth + colour to TSDF.integrate, which uploads them), the next pairs are already being rendered
     views = mine[:K_e2e]
-    pending = renderer.render_image_pair(views[0], to_host=True, wait=False) if views else None
+    lag = max(1, int(renderer.pairs_in_flight))
+    pending = [renderer.render_image_pair(v, to_host=True, wait=False) for v in views[:lag]]
     for n, i in enumerate(views):
-        out = pending
-        pending = renderer.render_image_pair(views[n + 1], to_host=True, wait=False) if n + 1 < len(views) else None
+        out = pending.pop(0)
+        if n + lag < len(views):
+            pending.append(renderer.render_image_pair(views[n + lag], to_host=True, wait=False))
         out["ready"].synchronize()  # both uint8 frames of pair i are in pinned host memory
         vol.prepare_depth(out["depth"], W, H, final_T=out["final_T"], out=dev_depth)  # expected depth of the left view
         host_depth.copy_(dev_depth, non_blocking=True)
@@ -353,8 +355,9 @@ def run_ours(args, cfg, rank, local, world):
         "config": {"workload": workload_name(args.config, cfg, total_views), "pairs_per_rank": K, "sharding": f"views round-robin x{world}",
                    "volume_merge": None if world == 1 else {"kind": "whole volume" if args.dense_reduce else "touched bricks only",
                                                             "ms": round(reduce_ms, 3)},
-                   "l2": "inputs larger than L2: 236 MB of Gaussian parameters re-read per view + brick volume window per view",
+                   "l2": f"inputs larger than L2: {236 * cfg['num_points'] / 1e6:.0f} MB of Gaussian parameters re-read per view + brick volume window per view",
                    "tsdf_colour": "fused (float4 running mean)", "exact_tile_cull": True,
+                   "pairs_in_flight": int(renderer.pairs_in_flight),
                    "per_view": {k: round(v, 1) for k, v in mean.items()}, "points_outside_tsdf_window": int(outside)},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": K_e2e},

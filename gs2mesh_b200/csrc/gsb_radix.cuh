@@ -27,7 +27,7 @@ constexpr int kRdxBlock = kRdxThreads * kRdxItems;     // 4096 items per CTA
 constexpr int kRdxBins = 256;
 constexpr int kRdxMaxPasses = 4;
 constexpr int kRdxWindow = 8;                          // predecessors inspected per look-back round
-constexpr int kRdxDefaultPItems = 16;                  // items per thread of small sorts; GSB_RADIX_P_ITEMS overrides
+constexpr int kRdxDefaultPItems = 8;                   // items per thread of small sorts; GSB_RADIX_P_ITEMS overrides
 constexpr size_t kRdxSmallSort = 1u << 22;             // sorts of up to 4M items count as "small" (the P-sized depth sort)
 constexpr int kRdxDefaultWindowed = 1;                 // GSB_RADIX_LOOKBACK=serial|window overrides (A/B switch)
 
@@ -136,20 +136,39 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
   uint32_t key[kItems], val[kItems];
   uint32_t lrank[kItems];  // rank among same-digit items of this warp's segment
   const uint32_t seg = base + warp * (kBlock / kRdxWarps);
+  // (a) every load of the thread is issued before anything waits for one
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const uint32_t i = seg + k * 32 + lane;
     const bool ok = i < n;
     key[k] = ok ? keys_in[i] : 0xffffffffu;
     val[k] = ok ? vals_in[i] : 0u;
+  }
+  // (b) same-digit groups of each 32-item row (independent votes, pipelined)
+  uint32_t peers[kItems];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const bool ok = seg + k * 32 + lane < n;
     const uint32_t d = ok ? ((key[k] >> shift) & (kRdxBins - 1)) : (uint32_t)kRdxBins;  // 256 = "no item"
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    peers[k] = __match_any_sync(0xffffffffu, d);
+  }
+  // (c) one shared-memory atomic per group, by its lowest lane, rows in order: the value it returns is the number of
+  //     same-digit items in the warp's earlier rows.  __syncwarp() orders the atomics of consecutive rows (their
+  //     leaders may be different lanes); nothing waits for a returned value inside this loop.
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const bool ok = seg + k * 32 + lane < n;
     uint32_t before = 0;
-    if (ok) before = warp_hist[warp][d];
+    if (ok && (peers[k] & lt_mask) == 0)
+      before = atomicAdd(&warp_hist[warp][(key[k] >> shift) & (kRdxBins - 1)], (uint32_t)__popc(peers[k]));
+    lrank[k] = before;
     __syncwarp();
-    if (ok && (peers & lt_mask) == 0) warp_hist[warp][d] = before + __popc(peers);  // lowest lane of the group
-    __syncwarp();
-    lrank[k] = before + __popc(peers & lt_mask);
+  }
+  // (d) the group's count-before comes from its leader
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const uint32_t before = __shfl_sync(0xffffffffu, lrank[k], __ffs(peers[k]) - 1);
+    lrank[k] = before + __popc(peers[k] & lt_mask);
   }
   __syncthreads();
 

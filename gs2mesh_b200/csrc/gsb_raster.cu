@@ -1210,7 +1210,7 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // two records per trip.  Thresholds are decided on exactly the same alpha / T values as in
 // render_warp_kernel; colours accumulate as fma(c, alpha*T, C) instead of fma(c*alpha, T, C)
 // (<= 1 ulp per term).
-constexpr int kDefaultRenderImpl = 2;        // 0 block, 1 warp, 2 compact (GSB_RENDER_IMPL overrides)
+constexpr int kDefaultRenderImpl = 3;        // 0 block, 1 warp, 2 compact, 3 compact with two pixels per lane (GSB_RENDER_IMPL overrides)
 constexpr int kSlotBytes = 48;               // A (16) | B (16) | green, blue (8) | pad (8)
 constexpr int kSlotsPerBuf = 33;             // 32 hits + sentinel
 // kPix = pixels per lane: 1 -> 8 warps per tile, each an 8x4 block; 2 -> 4 warps per tile, each an 8x8 block whose

@@ -31,7 +31,7 @@ from . import camera as cam
 from . import rasterizer as rast
 
 
-DEFAULT_PAIRS_IN_FLIGHT = 1
+DEFAULT_PAIRS_IN_FLIGHT = 2
 
 
 class _PairReady:
@@ -210,25 +210,30 @@ class Renderer:
             dev = self._camera_table.device
             main = torch.cuda.current_stream(dev)
             if self.overlap_eyes:
-                # outputs are triple-buffered: the tensors returned by call n stay valid until call n+2 returns,
-                # which also covers a caller that consumes pair n only after enqueuing pair n+1 (wait=False)
+                # outputs rotate over pairs_in_flight + 2 buffer sets: the tensors returned by call n stay valid until
+                # call n + pairs_in_flight + 1 returns, which covers a caller that consumes pair n only after
+                # enqueuing the next pairs_in_flight pairs (wait=False)
                 self._call_index = getattr(self, "_call_index", -1) + 1
-                slot = self._call_index % 3
                 depth = max(1, int(self.pairs_in_flight))
+                nslots = depth + 2
+                slot = self._call_index % nslots
                 if not hasattr(self, "_side_streams") or len(self._side_streams) != depth:
                     # `pairs_in_flight` sets of (left, right) streams, used round-robin: consecutive pairs run on
                     # different stream sets (each stream has its own scratch), so pair n+1's latency-bound binning
                     # kernels fill the gaps of pair n's blend kernels
                     self._side_streams = [[torch.cuda.Stream(dev), torch.cuda.Stream(dev)] for _ in range(depth)]
-                if not hasattr(self, "_entry_events"):
-                    self._entry_events = [None, None, None]
-                    self._slot_done = [[], [], []]
+                if not hasattr(self, "_entry_events") or len(self._entry_events) != nslots:
+                    main.synchronize()  # (re)configuration only: nothing may still use the old rotation
+                    self._call_index = 0
+                    slot = 0
+                    self._entry_events = [None] * nslots
+                    self._slot_done = [[] for _ in range(nslots)]
                 b = self._buffers(vt.width, vt.height, slot)
                 entry = torch.cuda.Event()
                 entry.record(main)
-                # everything that read this buffer set (handed out three calls ago) was enqueued on the caller's
+                # everything that read this buffer set (handed out nslots calls ago) was enqueued on the caller's
                 # stream before the PREVIOUS call was entered
-                gate = self._entry_events[(self._call_index - 1) % 3]
+                gate = self._entry_events[(self._call_index - 1) % nslots]
                 self._entry_events[slot] = entry
                 streams = self._side_streams[self._call_index % depth]
                 for st in streams:
