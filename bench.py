@@ -185,6 +185,10 @@ def run_ours(args, cfg, rank, local, world):
     bargs = BenchArgs(cfg)
     dev = f"cuda:{local}"
     renderer = Renderer.from_scene(rigs, baseline, cloud, output_dir_root=None, args=bargs, device=dev)
+    # the caller's stream (TSDF fusion, the e2e copies) gets a higher priority than the renderer's side streams: with
+    # several views in flight its short kernels and copies are otherwise queued behind thousands of blend CTAs
+    if os.environ.get("BENCH_MAIN_PRIORITY", "-1") != "0":
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=int(os.environ.get("BENCH_MAIN_PRIORITY", "-1"))))
     renderer.prepare_renderer()
     stage = TSDF(renderer, None, bargs, "bench", window_resolution=cfg["tsdf_res"], device=dev)
     stage.volume = stage._make_volume()
@@ -358,6 +362,7 @@ def run_ours(args, cfg, rank, local, world):
                    "l2": f"inputs larger than L2: {236 * cfg['num_points'] / 1e6:.0f} MB of Gaussian parameters re-read per view + brick volume window per view",
                    "tsdf_colour": "fused (float4 running mean)", "exact_tile_cull": True,
                    "pairs_in_flight": int(renderer.pairs_in_flight),
+                   "caller_stream_priority": int(torch.cuda.current_stream().priority),
                    "per_view": {k: round(v, 1) for k, v in mean.items()}, "points_outside_tsdf_window": int(outside)},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": K_e2e},

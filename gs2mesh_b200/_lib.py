@@ -19,6 +19,18 @@ RASTER_DEBUG_SYNC = 4
 RASTER_CUB_SORT = 8
 RASTER_ASYNC = 16
 RASTER_FAST_EXP = 32
+RENDER_IMPLS = {"block": 1, "warp": 2, "compact": 3, "dual": 4}
+SH_MODES = {"scalar": 1, "vec": 2, "padded": 3}
+
+
+def RASTER_RENDER_IMPL(name_or_n):
+    """flags field selecting the blend kernel variant (include/gs2mesh_b200.h: GSB_RASTER_RENDER_IMPL)."""
+    return (int(RENDER_IMPLS.get(name_or_n, name_or_n)) & 7) << 8
+
+
+def RASTER_SH_MODE(name_or_n):
+    """flags field selecting the SH staging variant (GSB_RASTER_SH_MODE)."""
+    return (int(SH_MODES.get(name_or_n, name_or_n)) & 3) << 12
 
 BRICK = 16
 BRICK_VOXELS = 4096

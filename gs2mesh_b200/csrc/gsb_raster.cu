@@ -1560,7 +1560,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     if (e && e[0] == 'p') return 2;
     return kDefaultShMode;
   }();
-  pp.sh_mode = sh_mode_default;
+  pp.sh_mode = ((a->flags >> 12) & 3u) ? (int)((a->flags >> 12) & 3u) - 1 : sh_mode_default;
   pp.recA = ws.recA;
   pp.recB = ws.recB;
   pp.recC = ws.recC;
@@ -1686,22 +1686,23 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
       if (e && e[0] == 'w') return 1;
       return kDefaultRenderImpl;
     }();
+    const int impl = ((a->flags >> 8) & 7u) ? (int)((a->flags >> 8) & 7u) - 1 : render_impl;
     const bool fast = (a->flags & GSB_RASTER_FAST_EXP) != 0;
 #define GSB_LAUNCH_RENDER_T(THREADS, ...)                                                                                \
   __VA_ARGS__<<<dim3(gx, gy), THREADS, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, \
                                                     a->out_color, a->out_depth, a->out_final_T, cap)
 #define GSB_LAUNCH_RENDER(KERNEL) GSB_LAUNCH_RENDER_T(kTilePixels, KERNEL)
-    if (render_impl == 3) {
+    if (impl == 3) {
       if (fast)
         GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<true, 2>);
       else
         GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<false, 2>);
-    } else if (render_impl == 2) {
+    } else if (impl == 2) {
       if (fast)
         GSB_LAUNCH_RENDER_T(kTilePixels, render_compact_kernel<true, 1>);
       else
         GSB_LAUNCH_RENDER_T(kTilePixels, render_compact_kernel<false, 1>);
-    } else if (render_impl == 1) {
+    } else if (impl == 1) {
       if (fast)
         GSB_LAUNCH_RENDER(render_warp_kernel<true>);
       else

@@ -79,6 +79,15 @@ int gsb_profile_collect(double* total_ms, uint64_t* samples, int n_stages);
                                          stable tile split                                      */
 #define GSB_RASTER_FAST_EXP 32u       /* blend with ex2.approx(power*log2e) instead of full-precision
                                          expf: ~2e-7 relative on alpha (parity budget is 1e-4)   */
+/* A/B overrides of the library defaults, for tests and profiling (0 in a field = library default, which the
+ * environment variables GSB_RENDER_IMPL / GSB_PRE_SH may also change):
+ *   bits 8..10  blend kernel: 1 block (one barrier per 256-record batch), 2 warp (per-warp bit scan), 3 compact
+ *               (per-warp compacted hit list, 8x4 pixels per warp), 4 dual (compact, 8x8 pixels per warp; default)
+ *   bits 12..13 SH staging of full-degree blocks: 1 scalar reads, 2 16-byte reads (default), 3 per-lane bulk copies
+ *               into padded slots + 16-byte reads
+ * All variants produce the same transmittance bit for bit; colours differ by accumulation rounding only. */
+#define GSB_RASTER_RENDER_IMPL(n) (((uint32_t)(n) & 7u) << 8)
+#define GSB_RASTER_SH_MODE(n) (((uint32_t)(n) & 3u) << 12)
 #define GSB_RASTER_ASYNC 16u          /* never wait for the stream: an undersized workspace is then
                                          reported through num_rendered[2] instead of the return
                                          value                                                 */

@@ -242,6 +242,42 @@ def test_fast_exp_stays_inside_parity_budget(oracle, gsb_lib, cuda_device):
         _assert_parity(fast["depth"], o["depth"], "fast-exp depth vs oracle")
 
 
+@pytest.mark.parametrize("fast", [False, True])
+def test_blend_kernel_variants_agree(gsb_lib, cuda_device, fast):
+    """block / warp / compact / dual blend kernels decide the three thresholds of forward.cu:336-353 on the same
+    alpha and T values: the transmittance image is bit-identical; colour and depth differ only by the rounding of
+    fma(c, alpha*T, C) vs fma(c*alpha, T, C)."""
+    from gs2mesh_b200 import _lib
+
+    for n, W, H, seed in [(10000, 640, 480, 1), (3000, 333, 250, 5)]:  # 333x250: ragged tiles on both axes
+        g, vt = _case(n, W, H, seed)
+        inp = _np_inputs(g, vt)
+        base = _lib.RASTER_EXACT_TILE_CULL | (_lib.RASTER_FAST_EXP if fast else 0)
+        outs = {name: _ours(cuda_device, inp, flags=base | _lib.RASTER_RENDER_IMPL(name)) for name in _lib.RENDER_IMPLS}
+        ref = outs["warp"]
+        for name, out in outs.items():
+            np.testing.assert_array_equal(out["final_T"], ref["final_T"], err_msg=f"final_T {name}")
+            np.testing.assert_array_equal(out["counts"], ref["counts"], err_msg=f"counts {name}")
+            np.testing.assert_allclose(out["color"], ref["color"], rtol=0, atol=5e-6, err_msg=f"color {name}")
+            np.testing.assert_allclose(out["depth"], ref["depth"], rtol=5e-6, atol=1e-6, err_msg=f"depth {name}")
+        np.testing.assert_array_equal(outs["compact"]["color"], outs["dual"]["color"])  # same arithmetic per pixel
+        np.testing.assert_array_equal(outs["block"]["color"], outs["warp"]["color"])
+
+
+def test_sh_staging_variants_are_bit_identical(gsb_lib, cuda_device):
+    """scalar / 16-byte / padded-slot staging of the SH block feed the same arithmetic (also without TMA and on the
+    ragged last warp)."""
+    from gs2mesh_b200 import _lib
+
+    g, vt = _case(4099, 320, 240, seed=22)
+    inp = _np_inputs(g, vt)
+    for extra in (0, _lib.RASTER_NO_TMA):
+        outs = [_ours(cuda_device, inp, flags=_lib.RASTER_EXACT_TILE_CULL | extra | _lib.RASTER_SH_MODE(m)) for m in _lib.SH_MODES]
+        for out in outs[1:]:
+            for k in ("color", "depth", "final_T", "radii", "counts"):
+                np.testing.assert_array_equal(out[k], outs[0][k], err_msg=k)
+
+
 def test_tma_staging_equals_plain_loads(gsb_lib, cuda_device):
     from gs2mesh_b200 import _lib
 
