@@ -55,6 +55,12 @@ __global__ void __launch_bounds__(kRdxThreads) radix_histogram_kernel(const uint
   if (base >= n) return;
   for (int p = 0; p < passes; ++p) hist[p][threadIdx.x] = 0;
   __syncthreads();
+  uint32_t kreg[kItems];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {  // every load in flight before the first vote waits for one
+    const uint32_t i = base + k * kRdxThreads + threadIdx.x;
+    kreg[k] = i < n ? keys[i] : 0u;
+  }
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const uint32_t i = base + k * kRdxThreads + threadIdx.x;
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(kRdxThreads) radix_histogram_kernel(const uint
     if (wbase + 32 <= n) {
       // full warp.  Depth keys of one view share their upper bytes, tile ids of neighbouring instances their
       // upper byte: when all 32 lanes agree on a digit one lane adds 32 instead of 32 serialised atomics.
-      const uint32_t key = keys[i];
+      const uint32_t key = kreg[k];
       for (int p = 0; p < passes; ++p) {
         const uint32_t dgt = (key >> (8 * p)) & (kRdxBins - 1);
         int same;
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(kRdxThreads) radix_histogram_kernel(const uint
         }
       }
     } else if (i < n) {
-      const uint32_t key = keys[i];
+      const uint32_t key = kreg[k];
       for (int p = 0; p < passes; ++p) atomicAdd(&hist[p][(key >> (8 * p)) & (kRdxBins - 1)], 1u);
     }
   }
@@ -109,7 +115,9 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
                                                                 int64_t capacity, int shift,
                                                                 const uint32_t* __restrict__ ghist,
                                                                 uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                                                                uint2* __restrict__ ranges, int window, int write_keys) {
+                                                                uint2* __restrict__ ranges, int window, int write_keys,
+                                                                const uint32_t* __restrict__ gather_src,
+                                                                uint32_t* __restrict__ gather_dst) {
   constexpr int kBlock = kRdxThreads * kItems;
   __shared__ uint32_t s_key[kBlock];
   __shared__ uint32_t s_val[kBlock];
@@ -278,7 +286,9 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
     const uint32_t d = (kk >> shift) & (kRdxBins - 1);
     const uint32_t dst = global_off[d] + (sidx - digit_start[d]);
     if (write_keys) keys_out[dst] = kk;  // nobody reads the keys of a sort's last pass
-    vals_out[dst] = s_val[sidx];
+    const uint32_t vv = s_val[sidx];
+    vals_out[dst] = vv;
+    if (gather_dst != nullptr) gather_dst[dst] = gather_src[vv];  // a per-value attribute, delivered in sorted order
     if (ranges != nullptr) {
       // slots are in ascending tile order inside the block (stable LSD => low digit sorted within high digit)
       if (sidx == 0 || s_key[sidx - 1] != kk) atomicMin(&ranges[kk].x, dst);
@@ -328,7 +338,8 @@ inline void radix_prepare(uint32_t* scratch, size_t max_items, int bits, cudaStr
   cudaMemsetAsync(scratch, 0, words * sizeof(uint32_t), stream);
 }
 
-// Enqueues ceil(bits/8) stable passes sorting (keys, vals) by key bits [0, bits).  `a`/`b` are
+// Enqueues ceil(bits/8) stable passes sorting (keys, vals) by key bits [0, bits).  gather_dst != NULL: the last pass
+// also writes gather_dst[j] = gather_src[value of sorted item j].  `a`/`b` are
 // ping-pong buffers; returns which buffer holds the result (0 = a, 1 = b).  n is either the host
 // value (counters == NULL) or read on the device from counters[1] (clamped by capacity).
 // histogram_ready: the caller already ran radix_prepare() and filled the digit histograms.
@@ -336,7 +347,7 @@ template <int kItems>
 inline int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_host,
                               const unsigned long long* counters, int64_t capacity, size_t max_items, int bits,
                               uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches,
-                              bool histogram_ready) {
+                              bool histogram_ready, const uint32_t* gather_src, uint32_t* gather_dst) {
   const uint32_t nblocks = (uint32_t)radix_blocks_for(max_items);
   if (nblocks == 0) return 0;
   const int passes = (bits + 7) / 8;
@@ -356,7 +367,8 @@ inline int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
     uint32_t* vout = cur ? vals_a : vals_b;
     radix_pass_kernel<kItems><<<nblocks, kRdxThreads, 0, stream>>>(
         kin, vin, kout, vout, n_host, counters, capacity, 8 * p, ghist + p * kRdxBins, status + (size_t)p * nblocks * kRdxBins,
-        tickets + p, p == passes - 1 ? ranges_on_last_pass : nullptr, radix_lookback_window(), p != passes - 1);
+        tickets + p, p == passes - 1 ? ranges_on_last_pass : nullptr, radix_lookback_window(), p != passes - 1,
+        gather_src, p == passes - 1 ? gather_dst : nullptr);
     *launches += 1;
     cur ^= 1;
   }
@@ -366,10 +378,10 @@ inline int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
 inline int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_host,
                             const unsigned long long* counters, int64_t capacity, size_t max_items, int bits,
                             uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches,
-                            bool histogram_ready) {
+                            bool histogram_ready, const uint32_t* gather_src = nullptr, uint32_t* gather_dst = nullptr) {
 #define GSB_RADIX_CALL(ITEMS)                                                                                              \
   radix_sort_pairs_t<ITEMS>(keys_a, vals_a, keys_b, vals_b, n_host, counters, capacity, max_items, bits, scratch,          \
-                            ranges_on_last_pass, stream, launches, histogram_ready)
+                            ranges_on_last_pass, stream, launches, histogram_ready, gather_src, gather_dst)
   switch (radix_items_for(max_items)) {
     case 4: return GSB_RADIX_CALL(4);
     case 8: return GSB_RADIX_CALL(8);

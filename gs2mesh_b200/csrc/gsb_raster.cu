@@ -718,23 +718,21 @@ __device__ __forceinline__ uint32_t block_reduce_sum_1024(uint32_t v, uint32_t* 
   return t;  // every thread holds the block total
 }
 
-// tiles-per-Gaussian in depth-sorted order: per-block sums
-__global__ void __launch_bounds__(kScanThreads) sorted_block_sums_kernel(int P, const uint32_t* __restrict__ ids_sorted,
-                                                                        const uint32_t* __restrict__ tiles,
+// tiles-per-Gaussian in depth-sorted order (written by the depth sort's last pass): per-block sums
+__global__ void __launch_bounds__(kScanThreads) sorted_block_sums_kernel(int P, const uint32_t* __restrict__ tiles_sorted,
                                                                         uint32_t* __restrict__ block_sums) {
   __shared__ uint32_t red[32];
   uint32_t sum = 0;
   const int base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k)
-    if (base + k < P) sum += tiles[ids_sorted[base + k]];
+    if (base + k < P) sum += tiles_sorted[base + k];
   sum = block_reduce_sum_1024(sum, red);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = sum;
 }
 
 // exclusive offsets in depth-sorted order; the last block publishes R and the overflow flag
-__global__ void __launch_bounds__(kScanThreads) sorted_offsets_kernel(int P, const uint32_t* __restrict__ ids_sorted,
-                                                                     const uint32_t* __restrict__ tiles,
+__global__ void __launch_bounds__(kScanThreads) sorted_offsets_kernel(int P, const uint32_t* __restrict__ tiles_sorted,
                                                                      const uint32_t* __restrict__ block_sums,
                                                                      uint32_t* __restrict__ offsets,
                                                                      unsigned long long* __restrict__ counters,
@@ -749,7 +747,7 @@ __global__ void __launch_bounds__(kScanThreads) sorted_offsets_kernel(int P, con
   uint32_t tsum = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    v[k] = base + k < P ? tiles[ids_sorted[base + k]] : 0u;
+    v[k] = base + k < P ? tiles_sorted[base + k] : 0u;
     tsum += v[k];
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -810,7 +808,7 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
   bool active = false;
   if (k < P && fits) {
     gid = ids_sorted[k];
-    active = tiles[gid] != 0;
+    active = tiles[k] != 0;  // `tiles` is in depth-sorted order here
     off = offsets[k];
   }
   uint64_t mask = 0ull;
@@ -1635,13 +1633,16 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     const uint32_t* ids_sorted;
     {
       StageTimer tm(kStScan, stream);
+      // the last pass also delivers tiles-per-Gaussian in sorted order (ws.offsets is free on this path), so the
+      // scan and the emit pass read it contiguously instead of gathering tiles[ids_sorted[k]]
+      uint32_t* tiles_sorted = ws.offsets;
       const int which = radix_sort_pairs(ws.depth_a, ws.ids_a, ws.depth_b, ws.ids_b, (uint32_t)P, nullptr, 0, (size_t)P, 32, rs,
-                                         nullptr, stream, &nl, /*histogram_ready=*/false);
+                                         nullptr, stream, &nl, /*histogram_ready=*/false, ws.tiles, tiles_sorted);
       ids_sorted = which ? ws.ids_b : ws.ids_a;
       const int sblocks = (P + kScanBlock - 1) / kScanBlock;
-      sorted_block_sums_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, ids_sorted, ws.tiles, ws.block_sums);
-      sorted_offsets_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, ids_sorted, ws.tiles, ws.block_sums, ws.sorted_offsets,
-                                                                 ws.counters, cap);
+      sorted_block_sums_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, tiles_sorted, ws.block_sums);
+      sorted_offsets_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, tiles_sorted, ws.block_sums, ws.sorted_offsets, ws.counters,
+                                                                 cap);
       nl += 2;
     }
     if ((rc = check_launch("depth sort / offsets", stream, dbg))) return rc;
@@ -1654,7 +1655,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     {
       StageTimer tm(kStEmit, stream);
       radix_prepare(rs, (size_t)cap, tile_bits, stream);
-      emit_sorted_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ids_sorted, ws.sorted_offsets, ws.recA, ws.recB, ws.tiles,
+      emit_sorted_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ids_sorted, ws.sorted_offsets, ws.recA, ws.recB, ws.offsets,
                                                               pp.radii, ws.masks, ws.rects, gx, gy, a->flags, ws.counters, tk_a, tv_a,
                                                               radix_ghist(rs), (tile_bits + 7) / 8);
       init_ranges_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream>>>(ws.ranges, (uint32_t)ntiles);
