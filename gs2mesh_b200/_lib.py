@@ -19,7 +19,7 @@ RASTER_DEBUG_SYNC = 4
 RASTER_CUB_SORT = 8
 RASTER_ASYNC = 16
 RASTER_FAST_EXP = 32
-RENDER_IMPLS = {"block": 1, "warp": 2, "compact": 3, "dual": 4, "solo": 5}
+RENDER_IMPLS = {"block": 1, "warp": 2, "compact": 3, "dual": 4}
 SH_MODES = {"scalar": 1, "vec": 2, "padded": 3}
 
 

@@ -1213,27 +1213,22 @@ constexpr int kSlotBytes = 48;               // A (16) | B (16) | green, blue (8
 constexpr int kSlotsPerBuf = 33;             // 32 hits + sentinel
 // kPix = pixels per lane: 1 -> 8 warps per tile, each an 8x4 block; 2 -> 4 warps per tile, each an 8x8 block whose
 // lanes own (x, y) and (x, y + 4): the list walk, the footprint test and the record loads are shared by 64 pixels.
-// kSolo: one warp per CTA (grid = 8x8 pixel blocks instead of tiles): a block's registers and shared memory are released
-// as soon as ITS pixels are done instead of when the slowest of the tile's four warps is.
-template <bool kFastExp, int kPix, bool kSolo = false>
-__global__ void __launch_bounds__(kSolo ? 32 : kTilePixels / kPix, kSolo ? 32 : (kPix == 1 ? 5 : 8))
+template <bool kFastExp, int kPix>
+__global__ void __launch_bounds__(kTilePixels / kPix, kPix == 1 ? 5 : 8)
     render_compact_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
                           const float4* __restrict__ recA, const float4* __restrict__ recB, const float2* __restrict__ recC,
                           const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
                           float* __restrict__ out_T, int64_t capacity) {
-  static_assert(!kSolo || kPix == 2, "solo CTAs cover one 8x8 block");
-  constexpr int kWarps = kSolo ? 1 : 8 / kPix;
+  constexpr int kWarps = 8 / kPix;
   __shared__ __align__(16) unsigned char slots[kWarps][2][kSlotsPerBuf * kSlotBytes];
   const uint32_t tiles_x = (W + kTile - 1) / kTile;
-  const int lane = threadIdx.x & 31;
-  const int warp = kSolo ? (int)((blockIdx.x & 1u) | ((blockIdx.y & 1u) << 1)) : (int)(threadIdx.x >> 5);  // sub-block of the tile
-  const uint32_t tile_x = kSolo ? blockIdx.x >> 1 : blockIdx.x, tile_y = kSolo ? blockIdx.y >> 1 : blockIdx.y;
-  const uint32_t a0 = smem_u32(&slots[kSolo ? 0 : warp][0][0]);
-  const uint32_t blk_x = tile_x * kTile + (warp & 1) * 8, blk_y = tile_y * kTile + (warp >> 1) * (4 * kPix);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t a0 = smem_u32(&slots[warp][0][0]);
+  const uint32_t blk_x = blockIdx.x * kTile + (warp & 1) * 8, blk_y = blockIdx.y * kTile + (warp >> 1) * (4 * kPix);
   const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
   const float pfx = (float)pix_x;
   const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 4 * kPix - 1);
-  uint2 range = ranges[tile_y * tiles_x + tile_x];
+  uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
   if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);
   const int total = range.y - range.x;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -1689,7 +1684,6 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
       if (e && e[0] == 'b') return 0;
       if (e && e[0] == 'c') return 2;
       if (e && e[0] == 'd') return 3;  // "dual": compact, two pixels per lane
-      if (e && e[0] == 's') return 4;  // "solo": dual with one warp per CTA
       if (e && e[0] == 'w') return 1;
       return kDefaultRenderImpl;
     }();
@@ -1699,14 +1693,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   __VA_ARGS__<<<dim3(gx, gy), THREADS, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, \
                                                     a->out_color, a->out_depth, a->out_final_T, cap)
 #define GSB_LAUNCH_RENDER(KERNEL) GSB_LAUNCH_RENDER_T(kTilePixels, KERNEL)
-    if (impl == 4) {
-      if (fast)
-        render_compact_kernel<true, 2, true><<<dim3(gx * 2, gy * 2), 32, 0, stream>>>(
-            ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, a->out_color, a->out_depth, a->out_final_T, cap);
-      else
-        render_compact_kernel<false, 2, true><<<dim3(gx * 2, gy * 2), 32, 0, stream>>>(
-            ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, a->out_color, a->out_depth, a->out_final_T, cap);
-    } else if (impl == 3) {
+    if (impl == 3) {
       if (fast)
         GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<true, 2>);
       else

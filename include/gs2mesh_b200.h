@@ -82,8 +82,7 @@ int gsb_profile_collect(double* total_ms, uint64_t* samples, int n_stages);
 /* A/B overrides of the library defaults, for tests and profiling (0 in a field = library default, which the
  * environment variables GSB_RENDER_IMPL / GSB_PRE_SH may also change):
  *   bits 8..10  blend kernel: 1 block (one barrier per 256-record batch), 2 warp (per-warp bit scan), 3 compact
- *               (per-warp compacted hit list, 8x4 pixels per warp), 4 dual (compact, 8x8 pixels per warp; default),
- *               5 solo (dual with one warp per CTA)
+ *               (per-warp compacted hit list, 8x4 pixels per warp), 4 dual (compact, 8x8 pixels per warp; default)
  *   bits 12..13 SH staging of full-degree blocks: 1 scalar reads, 2 16-byte reads (default), 3 per-lane bulk copies
  *               into padded slots + 16-byte reads
  * All variants produce the same transmittance bit for bit; colours differ by accumulation rounding only. */
