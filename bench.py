@@ -488,8 +488,8 @@ def run_reference(args, cfg, rank, local, world):
                            "renderer_utils.py:378-390 + Open3D-0.17-equivalent CPU TSDF; rank 0 only; PNG encode and DLNR excluded",
                    "reference_rasterizer_ms_per_view": round(float(np.mean(raster_ms)), 4) if raster_ms else None},
         "clocks": clocks,
-        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "reference+port",
-                         "sample": f"{done} stereo pairs: GPU reference rasterizer + CPU TSDF port on {cores} threads"},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{done} stereo pairs: reference rasterizer (unmodified sources, sm_100a build, GPU) + Open3D-0.17-equivalent CPU TSDF port on {cores} threads"},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -1,19 +1,17 @@
 #!/bin/bash
-# scratch: GPU run 23 - solo (one warp per CTA) blend variant: parity + A/B
+# scratch: GPU run 24 - ncu capture of the TSDF-side kernels + C2/C3/C4 with the final defaults
 mkdir -p gpurun_out
-T=gpurun_out/run23
-timeout 300 python -m pytest tests/test_gpu_raster.py tests/test_gpu_pipeline.py -m gpu -x -q > ${T}_tests.log 2>&1
-echo "tests exit $? : $(tail -1 ${T}_tests.log)"
-GSB_RENDER_IMPL=s timeout 300 python -m pytest tests/test_gpu_raster.py tests/test_gpu_pipeline.py -m gpu -x -q > ${T}_tests_solo.log 2>&1
-echo "tests[solo] exit $? : $(tail -1 ${T}_tests_solo.log)"
-run_bench() {  # name, extra bench args (quoted), env...
-  local name=$1; local extra=$2; shift; shift
-  env "$@" timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline $extra > ${T}_bench_$name.log 2>&1
+T=gpurun_out/run24
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'integrate_kernel|mark_bricks|prepare_depth|to_u8_kernel' -s 24 -c 16 \
+    -o gpurun_out/r01m_prof_tsdf python bench.py --steps 3 --warmup 3 --no-cpu-baseline > ${T}_ncu_tsdf.log 2>&1
+tail -2 ${T}_ncu_tsdf.log | cut -c1-200
+run_bench() {  # name, extra bench args
+  local name=$1; local extra=$2
+  timeout 400 python bench.py --warmup 5 --no-cpu-baseline $extra > ${T}_bench_$name.log 2>&1
   grep -h '^{"metric' ${T}_bench_$name.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('bench[$name]', d['value'], d['e2e']['value'], {k:round(v['avg_ms'],4) for k,v in d['kernels'].items()})" || tail -3 ${T}_bench_$name.log
 }
-run_bench dual "" GSB_RENDER_IMPL=d
-run_bench solo "" GSB_RENDER_IMPL=s
-run_bench C3_dual "--config C3 --steps 60" GSB_RENDER_IMPL=d
-run_bench C3_solo "--config C3 --steps 60" GSB_RENDER_IMPL=s
+run_bench C2 "--config C2 --steps 49"
+run_bench C3 "--config C3 --steps 100"
+run_bench C4 "--config C4 --steps 60"
