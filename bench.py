@@ -326,7 +326,9 @@ def run_ours(args, cfg, rank, local, world):
         "to_u8": 15 * W * H,
         "prepare_depth": 12 * W * H,
         "mark_bricks": 4 * W * H / 16,
-        "integrate": 8 * 4096 * mean["bricks"] + 8 * mean["V_upd"] + 32 * mean["V_upd"] + 7 * W * H,
+        # (tsdf, weight) and the float4 colour of every UPDATED voxel are read and written, the depth and
+        # rgb frames are read once; voxels the frame does not update are never touched
+        "integrate": 16 * mean["V_upd"] + 32 * mean["V_upd"] + 7 * W * H,
     }
     traffic = {}
     try:
