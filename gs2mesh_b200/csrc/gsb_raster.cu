@@ -10,16 +10,20 @@
 //                contiguous in every reference tensor ([P,3] xyz / scales, [P,4] quaternions,
 //                [P] opacities, [P,M,3] SH = 6 KB per warp) and is staged into shared memory
 //                with 1-D bulk TMA copies (cp.async.bulk + mbarrier).  The 6 KB SH block is
-//                only fetched when at least one Gaussian of the warp survives culling.
-//                Results are written as three coalesced record planes:
+//                only fetched when at least one Gaussian of the warp survives culling, and is
+//                read back with 16-byte loads.  Results are written as three coalesced record planes:
 //                  recA = (px, py, z_view, opacity)  recB = (conic a, b, c, red)  recC = (green, blue)
 //   binning      exact (Gaussian,tile) test: a pair is kept only if the tile's pixel lattice can
 //                reach alpha >= 1/255 -- the image is bit-identical to rectangle binning
 //                (rasterizer_impl.cu:88-107) with far fewer instances to sort and blend.
-//   sort         stable LSD radix sort on (tile << 32 | depth bits), value = Gaussian index.
-//   render       per 16x16 tile; the batch staged in shared memory carries colour and depth
-//                too, so the blend loop touches no global memory; also accumulates the
-//                expected-depth channel (sum z*alpha*T) the TSDF stage consumes.
+//   sort         the reference's order inside a tile is (depth bits, Gaussian index) ascending
+//                (stable radix sort of tile << 32 | depth keys emitted in index order).  Here: stable
+//                LSD radix sort of the P (depth bits, index) pairs, instances emitted in that order,
+//                then a stable sort of the R instances on the tile id alone (gsb_radix.cuh).
+//   render       per 16x16 tile, four warps that never wait for each other: each streams the tile's
+//                list, keeps the records its 8x8 pixel block can see (exact footprint test) in a
+//                private compacted shared-memory list and blends them branch-free, two pixels per lane;
+//                also accumulates the expected-depth channel (sum z*alpha*T) the TSDF stage consumes.
 //
 // All kernels run on the caller's stream.
 #include <algorithm>
