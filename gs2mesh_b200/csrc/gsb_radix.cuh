@@ -314,7 +314,12 @@ inline int radix_items_for(size_t max_items) {
     const int v = e ? atoi(e) : kRdxDefaultPItems;
     return (v == 4 || v == 8) ? v : 16;
   }();
-  return max_items <= kRdxSmallSort ? p_items : kRdxItems;
+  static const int r_items = [] {
+    const char* e = getenv("GSB_RADIX_R_ITEMS");  // A/B switch for the instance sorts: 4 | 8 | 16
+    const int v = e ? atoi(e) : kRdxItems;
+    return (v == 4 || v == 8) ? v : 16;
+  }();
+  return max_items <= kRdxSmallSort ? p_items : r_items;
 }
 inline size_t radix_blocks_for(size_t max_items) {
   const size_t block = (size_t)kRdxThreads * radix_items_for(max_items);
