@@ -29,6 +29,7 @@ constexpr int kRdxMaxPasses = 4;
 constexpr int kRdxWindow = 8;                          // predecessors inspected per look-back round
 constexpr int kRdxDefaultPItems = 8;                   // items per thread of small sorts; GSB_RADIX_P_ITEMS overrides
 constexpr size_t kRdxSmallSort = 1u << 22;             // sorts of up to 4M items count as "small" (the P-sized depth sort)
+constexpr int kRdxDefaultEvenSplit = 0;                // GSB_RADIX_SPLIT=even|byte overrides (A/B switch)
 constexpr int kRdxDefaultWindowed = 1;                 // GSB_RADIX_LOOKBACK=serial|window overrides (A/B switch)
 
 // status word of (block, digit): [31:30] 0 = not ready, 1 = block aggregate, 2 = inclusive prefix
@@ -47,9 +48,10 @@ __device__ __forceinline__ uint32_t radix_count(uint32_t n_host, const unsigned 
 template <int kItems>
 __global__ void __launch_bounds__(kRdxThreads) radix_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n_host,
                                                                      const unsigned long long* __restrict__ counters,
-                                                                     int64_t capacity, int passes,
+                                                                     int64_t capacity, int passes, int digit_bits,
                                                                      uint32_t* __restrict__ ghist) {
   __shared__ uint32_t hist[kRdxMaxPasses][kRdxBins];
+  const uint32_t dmask = (1u << digit_bits) - 1u;
   const uint32_t n = radix_count(n_host, counters, capacity);
   const uint32_t base = blockIdx.x * (kRdxThreads * kItems);
   if (base >= n) return;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kRdxThreads) radix_histogram_kernel(const uint
       // upper byte: when all 32 lanes agree on a digit one lane adds 32 instead of 32 serialised atomics.
       const uint32_t key = kreg[k];
       for (int p = 0; p < passes; ++p) {
-        const uint32_t dgt = (key >> (8 * p)) & (kRdxBins - 1);
+        const uint32_t dgt = (key >> (digit_bits * p)) & dmask;
         int same;
         __match_all_sync(0xffffffffu, dgt, &same);
         if (same) {
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(kRdxThreads) radix_histogram_kernel(const uint
       }
     } else if (i < n) {
       const uint32_t key = kreg[k];
-      for (int p = 0; p < passes; ++p) atomicAdd(&hist[p][(key >> (8 * p)) & (kRdxBins - 1)], 1u);
+      for (int p = 0; p < passes; ++p) atomicAdd(&hist[p][(key >> (digit_bits * p)) & dmask], 1u);
     }
   }
   __syncthreads();
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
                                                                 uint32_t* __restrict__ keys_out,
                                                                 uint32_t* __restrict__ vals_out, uint32_t n_host,
                                                                 const unsigned long long* __restrict__ counters,
-                                                                int64_t capacity, int shift,
+                                                                int64_t capacity, int shift, uint32_t dmask,
                                                                 const uint32_t* __restrict__ ghist,
                                                                 uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
                                                                 uint2* __restrict__ ranges, int window, int write_keys,
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const bool ok = seg + k * 32 + lane < n;
-    const uint32_t d = ok ? ((key[k] >> shift) & (kRdxBins - 1)) : (uint32_t)kRdxBins;  // 256 = "no item"
+    const uint32_t d = ok ? ((key[k] >> shift) & dmask) : (uint32_t)kRdxBins;  // 256 = "no item"
     peers[k] = __match_any_sync(0xffffffffu, d);
   }
   // (c) one shared-memory atomic per group, by its lowest lane, rows in order: the value it returns is the number of
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
     const bool ok = seg + k * 32 + lane < n;
     uint32_t before = 0;
     if (ok && (peers[k] & lt_mask) == 0)
-      before = atomicAdd(&warp_hist[warp][(key[k] >> shift) & (kRdxBins - 1)], (uint32_t)__popc(peers[k]));
+      before = atomicAdd(&warp_hist[warp][(key[k] >> shift) & dmask], (uint32_t)__popc(peers[k]));
     lrank[k] = before;
     __syncwarp();
   }
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
   for (int k = 0; k < kItems; ++k) {
     const uint32_t i = seg + k * 32 + lane;
     if (i < n) {
-      const uint32_t d = (key[k] >> shift) & (kRdxBins - 1);
+      const uint32_t d = (key[k] >> shift) & dmask;
       const uint32_t slot = digit_start[d] + warp_hist[warp][d] + lrank[k];
       s_key[slot] = key[k];
       s_val[slot] = val[k];
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
   // ---- phase 4: write runs (consecutive slots of one digit go to consecutive addresses)
   for (uint32_t sidx = threadIdx.x; sidx < count; sidx += kRdxThreads) {
     const uint32_t kk = s_key[sidx];
-    const uint32_t d = (kk >> shift) & (kRdxBins - 1);
+    const uint32_t d = (kk >> shift) & dmask;
     const uint32_t dst = global_off[d] + (sidx - digit_start[d]);
     if (write_keys) keys_out[dst] = kk;  // nobody reads the keys of a sort's last pass
     const uint32_t vv = s_val[sidx];
@@ -326,6 +328,19 @@ inline size_t radix_blocks_for(size_t max_items) {
   return (max_items + block - 1) / block;
 }
 
+// Bits per digit of a sort over `bits` key bits: the passes share the bits evenly (13 tile-id bits -> 7 + 6 instead
+// of 8 + 5: fewer, longer same-digit runs per block in the first pass).  GSB_RADIX_SPLIT=byte restores 8-bit digits.
+inline int radix_digit_bits(int bits) {
+  static const int even = [] {
+    const char* e = getenv("GSB_RADIX_SPLIT");
+    if (e && e[0] == 'b') return 0;
+    if (e && e[0] == 'e') return 1;
+    return kRdxDefaultEvenSplit;
+  }();
+  const int passes = (bits + 7) / 8;
+  return even ? (bits + passes - 1) / passes : 8;
+}
+
 // Scratch words one sort needs for `max_items` items (sized for the smallest block either sort may use).
 inline size_t radix_scratch_words(size_t max_items) {
   const size_t nblocks = (max_items + kRdxThreads * 4 - 1) / (kRdxThreads * 4);
@@ -356,12 +371,13 @@ inline int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
   const uint32_t nblocks = (uint32_t)radix_blocks_for(max_items);
   if (nblocks == 0) return 0;
   const int passes = (bits + 7) / 8;
+  const int db = radix_digit_bits(bits);
   uint32_t* ghist = scratch;                                    // [kRdxMaxPasses][256]
   uint32_t* tickets = ghist + kRdxMaxPasses * kRdxBins;          // [64]
   uint32_t* status = tickets + 64;                               // [passes][nblocks][256]
   if (!histogram_ready) {
     radix_prepare(scratch, max_items, bits, stream);
-    radix_histogram_kernel<kItems><<<nblocks, kRdxThreads, 0, stream>>>(keys_a, n_host, counters, capacity, passes, ghist);
+    radix_histogram_kernel<kItems><<<nblocks, kRdxThreads, 0, stream>>>(keys_a, n_host, counters, capacity, passes, db, ghist);
     *launches += 1;
   }
   int cur = 0;
@@ -371,7 +387,8 @@ inline int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
     uint32_t* kout = cur ? keys_a : keys_b;
     uint32_t* vout = cur ? vals_a : vals_b;
     radix_pass_kernel<kItems><<<nblocks, kRdxThreads, 0, stream>>>(
-        kin, vin, kout, vout, n_host, counters, capacity, 8 * p, ghist + p * kRdxBins, status + (size_t)p * nblocks * kRdxBins,
+        kin, vin, kout, vout, n_host, counters, capacity, db * p, (1u << db) - 1u, ghist + p * kRdxBins,
+        status + (size_t)p * nblocks * kRdxBins,
         tickets + p, p == passes - 1 ? ranges_on_last_pass : nullptr, radix_lookback_window(), p != passes - 1,
         gather_src, p == passes - 1 ? gather_dst : nullptr);
     *launches += 1;

@@ -796,14 +796,14 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
                                                           const uint32_t* __restrict__ rects, uint32_t gx, uint32_t gy,
                                                           uint32_t flags, const unsigned long long* __restrict__ counters,
                                                           uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
-                                                          uint32_t* __restrict__ ghist, int hist_passes) {
+                                                          uint32_t* __restrict__ ghist, int hist_passes, int digit_bits) {
   // digit histograms of the tile ids this block emits (what the tile sort's passes need), so the
   // sort does not have to read the instance stream once more just to count
   __shared__ uint32_t shist[kRdxMaxPasses][kRdxBins];
   for (int p = 0; p < hist_passes; ++p) shist[p][threadIdx.x] = 0;
   __syncthreads();
   auto tally = [&](uint32_t tile) {
-    for (int p = 0; p < hist_passes; ++p) atomicAdd(&shist[p][(tile >> (8 * p)) & (kRdxBins - 1)], 1u);
+    for (int p = 0; p < hist_passes; ++p) atomicAdd(&shist[p][(tile >> (digit_bits * p)) & ((1u << digit_bits) - 1u)], 1u);
   };
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -1661,7 +1661,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
       radix_prepare(rs, (size_t)cap, tile_bits, stream);
       emit_sorted_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ids_sorted, ws.sorted_offsets, ws.recA, ws.recB, ws.offsets,
                                                               pp.radii, ws.masks, ws.rects, gx, gy, a->flags, ws.counters, tk_a, tv_a,
-                                                              radix_ghist(rs), (tile_bits + 7) / 8);
+                                                              radix_ghist(rs), (tile_bits + 7) / 8, radix_digit_bits(tile_bits));
       init_ranges_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream>>>(ws.ranges, (uint32_t)ntiles);
       nl += 2;
     }

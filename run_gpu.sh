@@ -1,17 +1,14 @@
 #!/bin/bash
-# scratch: GPU run 24 - ncu capture of the TSDF-side kernels + C2/C3/C4 with the final defaults
+# scratch: GPU run 25 (last of the round) - final-state verification + even digit split / R block size A/B
 mkdir -p gpurun_out
-T=gpurun_out/run24
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'integrate_kernel|mark_bricks|prepare_depth|to_u8_kernel' -s 24 -c 16 \
-    -o gpurun_out/r01m_prof_tsdf python bench.py --steps 3 --warmup 3 --no-cpu-baseline > ${T}_ncu_tsdf.log 2>&1
-tail -2 ${T}_ncu_tsdf.log | cut -c1-200
-run_bench() {  # name, extra bench args
-  local name=$1; local extra=$2
-  timeout 400 python bench.py --warmup 5 --no-cpu-baseline $extra > ${T}_bench_$name.log 2>&1
-  grep -h '^{"metric' ${T}_bench_$name.log | python -c "
+T=gpurun_out/run25
+timeout 200 python -m pytest tests -m gpu -x -q > ${T}_tests.log 2>&1
+echo "tests exit $? : $(tail -1 ${T}_tests.log)"
+show() { grep -h '^{"metric' $1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('bench[$name]', d['value'], d['e2e']['value'], {k:round(v['avg_ms'],4) for k,v in d['kernels'].items()})" || tail -3 ${T}_bench_$name.log
-}
-run_bench C2 "--config C2 --steps 49"
-run_bench C3 "--config C3 --steps 100"
-run_bench C4 "--config C4 --steps 60"
+d=json.loads(sys.stdin.read()); print('$2', d['value'], d['e2e']['value'], {k:round(v['avg_ms'],4) for k,v in d.get('kernels',{}).items()})" || tail -3 $1; }
+timeout 200 python bench.py --cpu-budget 8 > ${T}_bench_final.log 2>&1; show ${T}_bench_final.log final
+GSB_RADIX_SPLIT=even timeout 200 python -m pytest tests/test_gpu_raster.py tests/test_gpu_pipeline.py -m gpu -x -q > ${T}_tests_even.log 2>&1
+echo "tests[even] exit $? : $(tail -1 ${T}_tests_even.log)"
+GSB_RADIX_SPLIT=even timeout 100 python bench.py --no-cpu-baseline --steps 100 > ${T}_bench_even.log 2>&1; show ${T}_bench_even.log even
+GSB_RADIX_R_ITEMS=8 timeout 100 python bench.py --no-cpu-baseline --steps 100 > ${T}_bench_r8.log 2>&1; show ${T}_bench_r8.log r8
