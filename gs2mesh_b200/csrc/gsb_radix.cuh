@@ -29,7 +29,7 @@ constexpr int kRdxMaxPasses = 4;
 constexpr int kRdxWindow = 8;                          // predecessors inspected per look-back round
 constexpr int kRdxDefaultPItems = 8;                   // items per thread of small sorts; GSB_RADIX_P_ITEMS overrides
 constexpr size_t kRdxSmallSort = 1u << 22;             // sorts of up to 4M items count as "small" (the P-sized depth sort)
-constexpr int kRdxDefaultEvenSplit = 0;                // GSB_RADIX_SPLIT=even|byte overrides (A/B switch)
+constexpr int kRdxDefaultEvenSplit = 1;                // GSB_RADIX_SPLIT=even|byte overrides (A/B switch)
 constexpr int kRdxDefaultWindowed = 1;                 // GSB_RADIX_LOOKBACK=serial|window overrides (A/B switch)
 
 // status word of (block, digit): [31:30] 0 = not ready, 1 = block aggregate, 2 = inclusive prefix
