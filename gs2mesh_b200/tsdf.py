@@ -295,9 +295,22 @@ class TSDF:
         return TSDFVolume(voxel_length, float(self._arg("TSDF_sdf_trunc", 0.04)), origin, count, with_color=True,
                           device=self.device)
 
+    @staticmethod
+    def _view_list(value):
+        """`--TSDF_valid` / `--TSDF_skip` are declared `type=str` in the reference (argument_utils.py:76-77) yet used with
+        `camera_number in ...` (tsdf_utils.py:61-63), which only works for lists handed in programmatically.  Both are
+        accepted here: a list / tuple / set of ints, or a string such as "0,5,10" or "[0, 5, 10]"."""
+        if value is None:
+            return None
+        if isinstance(value, str):
+            import re
+
+            return {int(tok) for tok in re.findall(r"-?\d+", value)}
+        return {int(v) for v in value}
+
     def _selected(self, camera_number):
-        valid = self._arg("TSDF_valid", None)
-        skip = self._arg("TSDF_skip", None)
+        valid = self._view_list(self._arg("TSDF_valid", None))
+        skip = self._view_list(self._arg("TSDF_skip", None))
         if camera_number % int(self._arg("TSDF_dilate", 1)) != 0:
             return False
         if valid is not None and camera_number not in valid:

@@ -111,3 +111,19 @@ def test_tsdf_utils_call_sequence_against_oracle(oracle, gsb_lib, cuda_device, t
         bad = o3d.geometry.RGBDImage.create_from_color_and_depth(o3d.geometry.Image(rgb[:, :10]), o3d.geometry.Image(depth[:, :10]),
                                                                  convert_rgb_to_intensity=False)
         volume.integrate(bad, intrinsic, np.eye(4))
+
+
+def test_stage_view_selection_accepts_lists_and_strings():
+    """tsdf_utils.py:58-63: TSDF_dilate / TSDF_valid / TSDF_skip pick the views; the reference declares the two lists as
+    strings (argument_utils.py:76-77), so both spellings are accepted."""
+    from types import SimpleNamespace
+
+    from gs2mesh_b200.tsdf import TSDF
+
+    rend = SimpleNamespace(device="cuda", baseline=0.1)
+    mk = lambda **kw: TSDF(rend, None, SimpleNamespace(**kw), "t")
+    assert [i for i in range(8) if mk(TSDF_dilate=3)._selected(i)] == [0, 3, 6]
+    assert [i for i in range(8) if mk(TSDF_valid=[1, 2, 5])._selected(i)] == [1, 2, 5]
+    assert [i for i in range(8) if mk(TSDF_valid="[1, 2, 5]", TSDF_skip="2")._selected(i)] == [1, 5]
+    assert [i for i in range(6) if mk(TSDF_skip=(0, 4), TSDF_dilate=2)._selected(i)] == [2]
+    assert all(mk()._selected(i) for i in range(4))
