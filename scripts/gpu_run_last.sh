@@ -1,5 +1,6 @@
 #!/bin/bash
-# scratch: GPU run 25 (last of the round) - final-state verification + even digit split / R block size A/B
+# Last single-GPU gpurun script of round 1 (final-state verification + A/B of the tile-sort digit split); run from the repo root:
+#   gpurun --timeout 600 -- "bash scripts/gpu_run_last.sh"
 mkdir -p gpurun_out
 T=gpurun_out/run25
 timeout 200 python -m pytest tests -m gpu -x -q > ${T}_tests.log 2>&1
