@@ -68,10 +68,13 @@ def shrink_rect(r, px, py, f):
     return int(nx0), int(ny0), int(nx1), int(ny1)
 
 
-def blended_somewhere(px, py, a, b, c, opacity, tx, ty):
-    """forward.cu:336-346 over the 256 pixels of tile (tx, ty), in float32 like the kernel."""
-    xs = (np.arange(TILE) + tx * TILE).astype(F)[None, :]
-    ys = (np.arange(TILE) + ty * TILE).astype(F)[:, None]
+def blended_somewhere(px, py, a, b, c, opacity, tx, ty, box=None):
+    """forward.cu:336-346 over the 256 pixels of tile (tx, ty) -- or over the pixel box (x0, y0, x1, y1) -- in float32
+    like the kernel."""
+    if box is None:
+        box = (tx * TILE, ty * TILE, tx * TILE + TILE - 1, ty * TILE + TILE - 1)
+    xs = np.arange(box[0], box[2] + 1).astype(F)[None, :]
+    ys = np.arange(box[1], box[3] + 1).astype(F)[:, None]
     dx, dy = F(px) - xs, F(py) - ys
     power = F(-0.5) * (F(a) * dx * dx + F(c) * dy * dy) - F(b) * dx * dy
     alpha = np.minimum(F(0.99), F(opacity) * np.exp(power.astype(F)))
@@ -132,3 +135,29 @@ def test_reference_rectangle_always_covers_the_footprint():
         f = make_footprint(a, b, c, F(2.0) * F(np.log(F(255.0) * opacity)))
         cand = shrink_rect(ref, px, py, f)
         assert ref[0] <= cand[0] <= cand[2] <= ref[2] and ref[1] <= cand[1] <= cand[3] <= ref[3]
+
+
+def test_per_warp_block_test_of_the_blend_kernels_is_conservative():
+    """The blend kernels apply the same rule to a warp's 8x8 (dual) or 8x4 (compact) pixel block, with
+    two_tau = 2 ln(255 opacity) + 1e-3 from the fast logarithm: a record the block test rejects has no pixel in the block
+    the reference loop would blend."""
+    rng = np.random.default_rng(11)
+    rejected = hit = 0
+    for _ in range(1200):
+        px, py, a, b, c, opacity, radius = random_gaussian(rng)
+        f = make_footprint(a, b, c, F(F(2.0) * F(np.log(F(255.0) * opacity)) + F(1e-3)))
+        ref = tile_rect(px, py, radius, 20, 15)
+        for ty in range(ref[1], ref[3]):
+            for tx in range(ref[0], ref[2]):
+                for bw, bh in ((8, 8), (8, 4)):
+                    for by in range(0, TILE, bh):
+                        for bx in range(0, TILE, bw):
+                            x0, y0 = tx * TILE + bx, ty * TILE + by
+                            keep = rect_can_contribute(px, py, f, F(x0), F(y0), F(x0 + bw - 1), F(y0 + bh - 1))
+                            if keep:
+                                hit += 1
+                                continue
+                            rejected += 1
+                            assert not blended_somewhere(px, py, a, b, c, opacity, tx, ty, box=(x0, y0, x0 + bw - 1, y0 + bh - 1)), \
+                                dict(px=px, py=py, conic=(a, b, c), opacity=opacity, block=(x0, y0, bw, bh))
+    assert rejected > 50_000 and hit > 10_000
