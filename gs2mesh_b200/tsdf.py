@@ -201,6 +201,13 @@ class TSDFVolume:
         """View [n_bricks, 4096, 2] of the brick store (no copy)."""
         return self.tsdf_weight.view(self.n_bricks, BRICK_VOXELS, 2)
 
+    def brick_at(self, index):
+        """[4096, 2] (tsdf, weight) view of the brick with integer lattice index (bx, by, bz) (Open3D's volume-unit index)."""
+        b = [int(index[k]) - self.brick_origin[k] for k in range(3)]
+        if any(b[k] < 0 or b[k] >= self.brick_count[k] for k in range(3)):
+            raise KeyError(f"brick {tuple(int(v) for v in index)} is outside the window")
+        return self.bricks()[(b[0] * self.brick_count[1] + b[1]) * self.brick_count[2] + b[2]]
+
     def dense(self):
         """(tsdf, weight) as dense [X,Y,Z] grids in Open3D UniformTSDFVolume index order."""
         rx, ry, rz = self.resolution

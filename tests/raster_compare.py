@@ -10,13 +10,24 @@ import numpy as np
 TOL = 1e-4
 
 
+REL_FLOOR = 0.05  # colours live in [0,1]: "relative" below this magnitude is measured against the floor
+
+
 def compare_images(a, b):
+    """frac_bad / max_err: |a-b| / max(1, |b|) (the round-1 criterion, absolute for colours in [0,1]);
+    frac_bad_rel / max_err_rel: TRUE relative error |a-b| / max(REL_FLOOR, |b|) -- north_star's "1e-4 relative fp32" read
+    per pixel, with a floor so that black pixels (b ~ 0, rounding noise ~1e-8) do not divide by zero."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
-    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    diff = np.abs(a - b)
+    err = diff / np.maximum(1.0, np.abs(b))
+    rel = diff / np.maximum(REL_FLOOR, np.abs(b))
     bad = err > TOL
-    return dict(frac_bad=float(bad.mean()), max_err=float(err.max()) if err.size else 0.0, n_bad=int(bad.sum()),
-                median=float(np.median(err)) if err.size else 0.0)
+    bad_rel = rel > TOL
+    n = max(err.size, 1)
+    return dict(frac_bad=float(bad.sum() / n), max_err=float(err.max()) if err.size else 0.0, n_bad=int(bad.sum()),
+                median=float(np.median(err)) if err.size else 0.0, frac_bad_rel=float(bad_rel.sum() / n),
+                max_err_rel=float(rel.max()) if rel.size else 0.0, p9999_rel=float(np.quantile(rel, 0.9999)) if rel.size else 0.0)
 
 
 def load_golden_case(path):

@@ -216,8 +216,40 @@ def test_full_size_properties(gsb_lib, cuda_device):
     assert float(tw[:, 0].abs().max()) <= 1.0 and float(tw[:, 0].min()) < -0.5  # truncated to [-1, 1], surface crossed
 
 
-def test_full_size_parity_vs_reference_binary_and_oracle(oracle, gsb_lib, cuda_device):
-    """BASELINE config C1 at full size: the rendered frame against the UNMODIFIED reference rasterizer (sm_100a
+FULL_SIZE_CASES = {
+    "C1": dict(scene.CONFIGS["C1"]),
+    "C2": dict(scene.CONFIGS["C2"]),  # frontal cap, off-centre principal point (823.2, 619.1), 500k Gaussians
+    "C3": dict(scene.CONFIGS["C3"]),  # 2M Gaussians into 960x540 (2040 tiles, ragged last tile row)
+    "C3full": dict(scene.CONFIGS["C3"], width=1920, height=1080),
+    "C4": dict(scene.CONFIGS["C4"]),  # 3M Gaussians, 1920x1080 (1080 = 67.5 tile rows), 1024^3 lattice
+}
+# outlier budgets of the full-size comparison against the reference binary: <= 10x the worst value observed on B200
+# over C1..C4 (profiles/r02_parity_observed.json), plus a ceiling on the size of any single outlier
+FULL_SIZE_BUDGET = 2e-4
+FULL_SIZE_MAX_ERR = 0.25
+
+
+def _record_observed(name, payload):
+    """Observed parity numbers go to gpurun_out/parity_observed.json (copied to profiles/ by hand)."""
+    import json
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_observed.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    data = {}
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                data = json.load(f)
+        except Exception:
+            data = {}
+    data.setdefault(name, {}).update(payload)
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
+@pytest.mark.parametrize("case", list(FULL_SIZE_CASES))
+def test_full_size_parity_vs_reference_binary_and_oracle(oracle, gsb_lib, cuda_device, case):
+    """BASELINE configs C1..C4 at full size: the rendered frame against the UNMODIFIED reference rasterizer (sm_100a
     build) on the same tensors, and the fused TSDF bricks against the Open3D restatement on the same depth."""
     import torch
 
@@ -226,54 +258,59 @@ def test_full_size_parity_vs_reference_binary_and_oracle(oracle, gsb_lib, cuda_d
     from gs2mesh_b200.tsdf import TSDF
     from tests.raster_compare import compare_images
 
-    cfg = scene.CONFIGS["C1"]
+    cfg = FULL_SIZE_CASES[case]
     W, H = cfg["width"], cfg["height"]
     cloud = scene.make_gaussians(cfg["num_points"], seed=1)
-    rigs, baseline = scene.make_stereo_cameras(8, W, H)
+    rigs, baseline = scene.make_stereo_cameras(8, W, H, layout=cfg["layout"], principal_point=cfg.get("principal_point"))
+    res = cfg["tsdf_res"]
 
     class A(Args):
-        TSDF_voxel = 2
-        TSDF_sdf_trunc = 0.04
+        TSDF_voxel = 2.0 * 512 / res
+        TSDF_sdf_trunc = max(0.04, 3 * 2.0 / res)
+        TSDF_min_depth_baselines = cfg["min_db"]
+        TSDF_max_depth_baselines = cfg["max_db"]
         TSDF_skip = None
 
     r = Renderer.from_scene(rigs, baseline, cloud, args=A(), device=str(cuda_device))
     r.prepare_renderer()
+    observed = {}
     if oracle.ref_available():
         for side in (0, 1):
             rec = r._camera_table[3, side]
             vt = r._views[3][side]
             ref = oracle.ref_forward_torch(r.means3D, r.opacity, rec[0:16], rec[16:32], rec[32:35], W, H, vt.tan_fovx, vt.tan_fovy,
                                            r.background, shs=r.shs, scales=r.scales, rotations=r.rotations, sh_degree=3)
-            for flags in (_lib.RASTER_EXACT_TILE_CULL, _lib.RASTER_EXACT_TILE_CULL | _lib.RASTER_FAST_EXP):
+            for tag, flags in (("expf", _lib.RASTER_EXACT_TILE_CULL), ("ex2", _lib.RASTER_EXACT_TILE_CULL | _lib.RASTER_FAST_EXP)):
                 ours = r.render_view(3, side, want_depth=True, want_counts=True, flags=flags)
                 cmp = compare_images(ours["color"].cpu().numpy(), ref["color"].cpu().numpy())
-                assert cmp["frac_bad"] <= 2e-4 and cmp["median"] <= 1e-6, (side, flags, cmp)
                 cmpT = compare_images(ours["final_T"].cpu().numpy(), ref["final_T"].cpu().numpy())
-                assert cmpT["frac_bad"] <= 2e-4, (side, flags, cmpT)
+                observed[f"side{side}_{tag}"] = dict(color=cmp, final_T=cmpT, num_rendered_ref=int(ref["num_rendered"]),
+                                                     instances_binned=int(ours["counts"][0]))
+                _record_observed(case, observed)
+                assert cmp["frac_bad"] <= FULL_SIZE_BUDGET and cmp["median"] <= 1e-6, (side, flags, cmp)
+                assert cmp["max_err"] <= FULL_SIZE_MAX_ERR, (side, flags, cmp)
+                assert cmpT["frac_bad"] <= FULL_SIZE_BUDGET, (side, flags, cmpT)
                 assert int(ours["counts"][1]) == ref["num_rendered"]  # the reference's instance count, exactly
 
     pair = r.render_image_pair(3, to_host=False)
-    stage = TSDF(r, None, A(), "c1", window_resolution=512)
+    stage = TSDF(r, None, A(), case, window_resolution=res)
     stage.integrate(pair["depth"], pair["left_u8"], rigs[3]["left"], final_T=pair["final_T"])
     vol = stage.volume
     torch.cuda.synchronize()
     alpha = 1.0 - pair["final_T"].cpu().numpy()
     d = np.where(alpha > 0.5, pair["depth"].cpu().numpy() / np.maximum(alpha, 1e-30), 0).astype(np.float32)
     d = np.where(d < np.float32(A.TSDF_min_depth_baselines * baseline), 0, d).astype(np.float32)
-    ovol = oracle.OracleTSDFVolume(2.0 / 512, 0.04, with_color=True)
+    ovol = oracle.OracleTSDFVolume(2.0 / res, A.TSDF_sdf_trunc, with_color=True)
     c = rigs[3]["left"]
     n_units = ovol.integrate(d, pair["left_u8"].cpu().numpy(), W, H, c["fx"], c["fy"], c["cx"], c["cy"], np.linalg.inv(c["extrinsic"]),
-                             depth_scale=1.0, depth_trunc=baseline * A.TSDF_max_depth_baselines, threads=8)
+                             depth_scale=1.0, depth_trunc=baseline * A.TSDF_max_depth_baselines, threads=os.cpu_count() or 8)
     touched, outside, _ = vol.last_stats()
+    _record_observed(case, dict(tsdf=dict(units=int(n_units), touched=int(touched), outside=int(outside))))
     assert outside == 0 and touched == n_units
     units = ovol.unit_indices()
-    bricks = vol.bricks()
-    b0 = np.array(vol.brick_origin)
-    nb = vol.brick_count
-    step = max(1, len(units) // 300)  # compare ~300 of the ~2500 touched bricks bit for bit
+    step = max(1, len(units) // 300)  # compare ~300 of the touched bricks bit for bit
     for i in range(0, len(units), step):
         t, w, _ = ovol.unit_data(i)
-        b = units[i] - b0
-        got = bricks[int((b[0] * nb[1] + b[1]) * nb[2] + b[2])].cpu().numpy()
+        got = vol.brick_at(units[i]).cpu().numpy()
         np.testing.assert_array_equal(got[:, 1], w)
         np.testing.assert_array_equal(got[:, 0], t)

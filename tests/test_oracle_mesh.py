@@ -54,3 +54,29 @@ def test_vertex_lies_on_its_edge_with_open3d_interpolation(oracle):
         want = (o + np.array(B0) * 16 + 0.5) * VL
         want[k[3]] += f0 * VL / (f0 + f1)
         np.testing.assert_allclose(v, want, atol=1e-12)
+
+
+def test_open3d_golden_mesh(oracle):
+    """extract_triangle_mesh() of the real open3d==0.17.0 wheel == the marching-cubes restatement (fixture written by
+    tests/golden/make_tsdf_golden.py; skipped while the wheel is unobtainable, see tests/test_oracle_tsdf.py)."""
+    import pytest
+
+    from tests import test_oracle_tsdf as t
+    from tests.golden import make_tsdf_golden as g
+
+    for case in t.GOLDEN_CASES:
+        z = t._load_golden(case)
+        got = g.oracle_readback(case, g.oracle_volume(case, g.frames_from_npz(z)))
+        assert len(got["mesh_triangles"]) == len(z["mesh_triangles"]) > 500
+        assert len(got["mesh_vertices"]) == len(z["mesh_vertices"])
+        q = g.CASES[case]["voxel"] / 512 / 1024
+        wv, wc = t._sorted_rows(z["mesh_vertices"], z["mesh_colors"], quantum=q)
+        gv, gc = t._sorted_rows(got["mesh_vertices"], got["mesh_colors"], quantum=q)
+        np.testing.assert_allclose(gv, wv, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(gc, wc, rtol=0, atol=1e-12)
+        # triangles as vertex-position triples, order-insensitive
+        wt = np.sort(np.round(z["mesh_vertices"][z["mesh_triangles"]].reshape(-1, 9) / q).astype(np.int64), axis=0)
+        gt = np.sort(np.round(got["mesh_vertices"][got["mesh_triangles"]].reshape(-1, 9) / q).astype(np.int64), axis=0)
+        np.testing.assert_array_equal(gt, wt)
+        np.testing.assert_allclose(got["mesh_vertices_scaled"][np.lexsort(got["mesh_vertices"].T[::-1])],
+                                   z["mesh_vertices_scaled"][np.lexsort(z["mesh_vertices"].T[::-1])], rtol=0, atol=1e-12)

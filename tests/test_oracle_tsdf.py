@@ -1,5 +1,7 @@
 """Known-answer tests of the TSDF oracle (Open3D-0.17 restatement; parity unpinned, see
 oracle/tsdf_oracle.cpp header).  KATs 6-9 of SURVEY.md section 8(c)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -147,3 +149,58 @@ def test_mask_morphology_matches_cv2(oracle):
     m = _blob_mask(rng, 48, 60)
     closing = cv2.morphologyEx((~m).astype(np.uint8), cv2.MORPH_CLOSE, np.ones((10, 10), np.uint8))
     np.testing.assert_array_equal(oracle.filter_object_mask(m, 10, 5, invert=True), cv2.erode(closing, np.ones((5, 5), np.uint8)) > 0.5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fixture-backed pin against the REAL open3d==0.17.0 wheel (tests/golden/make_tsdf_golden.py writes the fixtures).
+# The wheel could not be obtained in round 2 (profiles/r02_open3d_attempt_*.log), so these skip until somebody with the
+# wheel runs the generator; GSB_TSDF_GOLDEN_DIR points the tests at a directory produced with `--backend oracle` to check
+# the comparison code itself.
+GOLDEN_DIR = os.environ.get("GSB_TSDF_GOLDEN_DIR", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+GOLDEN_CASES = ["centred", "offcentre", "scaled_shifted"]
+
+
+def _load_golden(case):
+    path = os.path.join(GOLDEN_DIR, f"tsdf_o3d_{case}.npz")
+    if not os.path.exists(path):
+        pytest.skip("no open3d==0.17.0 fixture: the wheel is unobtainable here (profiles/r02_open3d_attempt_*.log) -- "
+                    "TSDF parity stays unpinned until tests/golden/make_tsdf_golden.py has been run with the wheel")
+    return np.load(path, allow_pickle=False)
+
+
+def _sorted_rows(points, *cols, quantum):
+    key = np.round(np.asarray(points) / quantum).astype(np.int64)
+    order = np.lexsort((key[:, 2], key[:, 1], key[:, 0]))
+    return (np.asarray(points)[order],) + tuple(np.asarray(c)[order] for c in cols)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_open3d_golden_voxel_values(oracle, case):
+    """extract_voxel_point_cloud() of the wheel == the restatement: same voxel set (block discovery T1, truncation band T2) and
+    bit-identical tsdf values.  Settles the two DOUBT marks of oracle/tsdf_oracle.cpp (Eigen 4x4 * 4x1 summation order,
+    sdf * (1/trunc))."""
+    from tests.golden import make_tsdf_golden as g
+
+    z = _load_golden(case)
+    vol = g.oracle_volume(case, g.frames_from_npz(z))
+    got = g.oracle_readback(case, vol)
+    vl = g.CASES[case]["voxel"] / 512
+    wp, wv = _sorted_rows(z["voxel_points"], z["voxel_tsdf01"], quantum=vl / 4)
+    gp, gv = _sorted_rows(got["voxel_points"], got["voxel_tsdf01"], quantum=vl / 4)
+    assert len(wp) == len(gp) and len(wp) > 1000
+    np.testing.assert_allclose(gp, wp, rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(gv, wv)  # (tsdf + 1) / 2 in fp64 is exact for |tsdf| < 0.98: bit-identical tsdf
+
+
+def test_golden_generator_inputs_are_reproducible():
+    """The fixtures carry their inputs; the generator's seeded frames must reproduce them (runs without the wheel)."""
+    from tests.golden import make_tsdf_golden as g
+
+    for case in GOLDEN_CASES:
+        a, b = g.make_frames(case), g.make_frames(case)
+        assert all(np.array_equal(x["depth"], y["depth"]) and np.array_equal(x["rgb"], y["rgb"]) for x, y in zip(a, b))
+        assert all((f["depth"] > 0).mean() > 0.15 for f in a)
+        vol = g.oracle_volume(case, a)
+        assert vol.num_units > 50
+        if case == "scaled_shifted":  # scene centred at (5,-3,2) / TSDF_scale 0.1: units far from the origin
+            assert np.abs(vol.unit_indices()).max() > 40
