@@ -168,6 +168,12 @@ def build_scene(cfg, total_views, seed=1):
     return cloud, rigs, baseline
 
 
+def shared_config(args, cfg, total_views, world, pairs_per_rank):
+    """`config` is identical in the `ours` and the `reference` line of one (N, K, W) run; arm-specific facts go to `details`."""
+    return {"workload": workload_name(args.config, cfg, total_views), "pairs_per_rank": pairs_per_rank,
+            "sharding": f"views round-robin x{world}", "scaling": args.scaling}
+
+
 def workload_name(name, cfg, total_views):
     return (f"{name}: synthetic {cfg['num_points']}-Gaussian {'360' if cfg['layout'] == 'ring' else 'frontal-cap'} scene, "
             f"{total_views} stereo pairs @{cfg['width']}x{cfg['height']}, {cfg['tsdf_res']}^3 TSDF lattice (voxel 2/{cfg['tsdf_res']})")
@@ -179,8 +185,13 @@ def run_ours(args, cfg, rank, local, world):
     from gs2mesh_b200.renderer import Renderer
     from gs2mesh_b200.tsdf import TSDF, shard_views
 
-    K, Wm = args.steps, args.warmup
-    total_views = K * world
+    Wm = args.warmup
+    if args.scaling == "strong":  # total work fixed: --steps pairs split over the ranks (round-robin)
+        total_views = args.steps
+        K = len(range(rank, total_views, world))
+    else:
+        K = args.steps
+        total_views = K * world
     cloud, rigs, baseline = build_scene(cfg, total_views)
     bargs = BenchArgs(cfg)
     dev = f"cuda:{local}"
@@ -222,7 +233,6 @@ def run_ours(args, cfg, rank, local, world):
         step(i)
         stats["bricks"].append(vol.last_stats()[0])
         stats["V_upd"].append(float(vol.tsdf_weight.view(-1, 2)[:, 1].sum(dtype=torch.float64).item()) - w_before)
-    outside = vol.last_stats()[1]
     vol.reset()
     mean = {k: float(np.mean(v)) for k, v in stats.items()}
 
@@ -230,7 +240,7 @@ def run_ours(args, cfg, rank, local, world):
     for i in (mine * ((Wm // max(len(mine), 1)) + 1))[:Wm]:
         step(i)
     if world > 1:
-        vol.reduce_across_ranks(dst=0, sparse=not args.dense_reduce)
+        vol.reduce_across_ranks(dst=0)
     vol.reset()
     barrier(world)
     _lib.profile_enable(False)
@@ -247,22 +257,24 @@ def run_ours(args, cfg, rank, local, world):
     evr = torch.cuda.Event(enable_timing=True)
     evr.record()
     if world > 1:
-        vol.reduce_across_ranks(dst=0, sparse=not args.dense_reduce)
+        vol.reduce_across_ranks(dst=0)
     ev1.record()
     barrier(world)
     reduce_ms = max_over_ranks(evr.elapsed_time(ev1), world)
+    pool_after = vol.pool_stats()
+    assert pool_after["dropped_total"] == 0, "the brick pool overflowed during the timed region"
     renderer.check_status(mine)  # no asynchronously rendered frame overflowed its scratch
     clocks = sampler.stop()
     launches = int(_lib.lib().gsb_kernel_launch_count() - launches0)
     elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1), world)
-    value = world * K / (elapsed_ms / 1e3)
+    value = total_views / (elapsed_ms / 1e3)
 
     # ---- per-kernel durations: the same steps again with the two eyes serialised on one stream, every
     #      stage bracketed by CUDA events on the launching stream (in the timed loop above the eyes overlap
     #      on two streams, so a bracketed stage would also contain the other eye's kernels)
     vol.reset()
     renderer.overlap_eyes = False
-    n_prof = min(K, 25)
+    n_prof = max(1, min(K, 25))
     for i in mine[:2]:
         step(i)
     _lib.profile_collect()
@@ -302,10 +314,10 @@ def run_ours(args, cfg, rank, local, world):
         stage.integrate(host_depth, out["host_left_u8"], rigs[i]["left"])
     renderer.check_status(views)
     if world > 1:
-        vol.reduce_across_ranks(dst=0, sparse=not args.dense_reduce)
+        vol.reduce_across_ranks(dst=0)
     barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-    e2e_value = world * K_e2e / e2e_s
+    e2e_value = total_views / e2e_s
     h2d = 4 * W * H + 3 * W * H + 16 * 8
     d2h = 2 * 3 * W * H + 4 * W * H
 
@@ -316,8 +328,12 @@ def run_ours(args, cfg, rank, local, world):
     peak, peak_kind = measured_peak_gbs()
     P = cfg["num_points"]
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    pre_per_step = prof.get("preprocess", (0, 0))[1] / n_prof  # 1 = one fused launch per pair, 2 = one per eye
+    eyes_per_pre = 2 if pre_per_step < 1.5 else 1
     bytes_per_launch = {  # algorithmic bytes per launch, SURVEY.md 8(d) / DESIGN.md
-        "preprocess": 12 * P + 224 * mean["Pv"] + 8 * P + 40 * mean["Pv"],
+        # fused pair launch: parameters read once ("a fused L/R preprocess may legitimately read params once"),
+        # records written per eye
+        "preprocess": 12 * P + 224 * mean["Pv"] + eyes_per_pre * (8 * P + 40 * mean["Pv"]),
         "depth_sort": 16 * P + 8 * P,
         "emit": 8 * mean["R"] + 36 * mean["Pv"] + 8 * P,
         "tile_sort": 16 * mean["R"],
@@ -328,7 +344,8 @@ def run_ours(args, cfg, rank, local, world):
         "mark_bricks": 4 * W * H / 16,
         # (tsdf, weight) and the float4 colour of every UPDATED voxel are read and written, the depth and
         # rgb frames are read once; voxels the frame does not update are never touched
-        "integrate": 16 * mean["V_upd"] + 32 * mean["V_upd"] + 7 * W * H,
+        # SURVEY 8(d) with 3 x f32 colour: 16 + 24 = 40 B per updated voxel (the store pads colour to float4: 48 B move)
+        "integrate": 40 * mean["V_upd"] + 7 * W * H,
     }
     traffic = {}
     try:
@@ -342,7 +359,8 @@ def run_ours(args, cfg, rank, local, world):
             continue
         avg = ms / n
         gbs = bytes_per_launch[name] / (avg * 1e-3) / 1e9
-        kernels[name] = {"avg_ms": round(avg, 5), "launches": n, "share": round(ms / (serial_ms_per_step * n_prof), 4),
+        kernels[name] = {"avg_ms": round(avg, 5), "launches": n, "launches_per_step": round(n / n_prof, 3),
+                         "share": round(ms / (serial_ms_per_step * n_prof), 4),
                          "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
     dom = max(kernels, key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "peak_kind": f"of {peak_kind}",
@@ -361,23 +379,29 @@ def run_ours(args, cfg, rank, local, world):
 
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": round(elapsed_ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(elapsed_ms / max(K, 1), 4), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, cfg, total_views), "pairs_per_rank": K, "sharding": f"views round-robin x{world}",
-                   "volume_merge": None if world == 1 else {"kind": "whole volume" if args.dense_reduce else "touched bricks only",
-                                                            "ms": round(reduce_ms, 3)},
-                   "l2": f"inputs larger than L2: {236 * cfg['num_points'] / 1e6:.0f} MB of Gaussian parameters re-read per view + brick volume window per view",
-                   "tsdf_colour": "fused (float4 running mean)", "exact_tile_cull": True,
-                   "pairs_in_flight": int(renderer.pairs_in_flight),
-                   "caller_stream_priority": int(torch.cuda.current_stream().priority),
-                   "per_view": {k: round(v, 1) for k, v in mean.items()}, "points_outside_tsdf_window": int(outside)},
+        "config": shared_config(args, cfg, total_views, world, K),
+        "details": {"volume_merge": None if world == 1 else {"kind": "gsb_tsdf_reduce: union of the ranks' bricks, one ncclReduce to rank 0",
+                                                             "ms": round(reduce_ms, 3)},
+                    "l2": f"inputs larger than L2: {236 * cfg['num_points'] / 1e6:.0f} MB of Gaussian parameters re-read per pair + brick store per view",
+                    "tsdf_colour": "fused (float4 running mean)", "exact_tile_cull": True,
+                    "pair_mode": os.environ.get("GSB_PAIR_MODE", "fused"),
+                    "pairs_sharing_one_depth_sort": round(float(np.mean([renderer._shared_depth[i] for i in mine])), 3) if mine else None,
+                    "pairs_in_flight": int(renderer.pairs_in_flight),
+                    "caller_stream_priority": int(torch.cuda.current_stream().priority),
+                    "per_view": {k: round(v, 1) for k, v in mean.items()},
+                    "tsdf_volume": {"kind": "unbounded hashed brick pool", "bricks_open_after_timed_region": int(pool_after["bricks"]),
+                                    "bricks_dropped": int(pool_after["dropped_total"]), "pool_bricks": int(vol.pool_bricks)}},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": K_e2e},
         "gpu_launches": launches,
         "roofline": roofline,
         "kernels": kernels,
         "kernels_note": f"per-kernel CUDA-event durations from {n_prof} steps with the eyes serialised on one stream "
-                        f"({round(serial_ms_per_step, 4)} ms/step); the timed region overlaps the two eyes on two streams",
+                        f"({round(serial_ms_per_step, 4)} ms/step); the timed region overlaps the two eyes on two streams.  "
+                        "preprocess is ONE launch per stereo pair (both eyes), depth_sort one per pair when the eyes share "
+                        "their view depths, else one per eye (launches_per_step)",
         "cpu_baseline": cpu_baseline,
     }
     return line
@@ -409,13 +433,37 @@ def cpu_tsdf_baseline(renderer, vol, stage, rigs, mine, cfg, bargs, baseline, bu
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def emit_depth_frames(args, cfg, local):
+    """Child process of the reference arm (untimed set-up): the depth frames that stand in for the out-of-scope stereo
+    network's output, rendered with this repository's rasterizer and written to a .npz.  Running it in a separate process
+    keeps libgs2mesh_b200.so out of the process that times the reference."""
+    from gs2mesh_b200.renderer import Renderer
+    from gs2mesh_b200.tsdf import TSDFVolume
+
+    n_sample = int(os.environ["GSB_BENCH_NSAMPLE"])
+    total_views = int(os.environ["GSB_BENCH_TOTAL_VIEWS"])
+    cloud, rigs, baseline = build_scene(cfg, total_views)
+    bargs = BenchArgs(cfg)
+    W, H = cfg["width"], cfg["height"]
+    dev = torch.device("cuda", local)
+    helper = Renderer.from_scene(rigs, baseline, cloud, output_dir_root=None, args=bargs, device=str(dev))
+    helper.prepare_renderer()
+    hv = TSDFVolume(2.0 / cfg["tsdf_res"], bargs.TSDF_sdf_trunc, with_color=False, device=dev, pool_bricks=16)
+    frames = []
+    for i in range(n_sample):
+        out = helper.render_image_pair(i, to_host=False)
+        frames.append(hv.prepare_depth(out["depth"], W, H, final_T=out["final_T"],
+                                       min_depth=bargs.TSDF_min_depth_baselines * baseline).cpu().numpy())
+    np.savez(args.emit_depth_frames, depth=np.stack(frames))
+
+
 def run_reference(args, cfg, rank, local, world):
     if rank != 0:
         return None
     from oracle import oracle as orc
 
     K, Wm = args.steps, args.warmup
-    total_views = K * world
+    total_views = K if args.scaling == "strong" else K * world
     cloud, rigs, baseline = build_scene(cfg, total_views)
     bargs = BenchArgs(cfg)
     W, H = cfg["width"], cfg["height"]
@@ -425,31 +473,27 @@ def run_reference(args, cfg, rank, local, world):
     if not have_ref:
         return {"impl": "reference", "unavailable": "oracle/_ref/libref_dgr.so (reference rasterizer built for sm_100a) is missing"}
 
-    from gs2mesh_b200 import camera as cam
+    from gs2mesh_b200 import camera as cam  # host-side pose maths only (numpy); does not load the CUDA library
 
     up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
     g = dict(xyz=up(cloud.xyz), sh=up(cloud.features), op=up(cloud.opacity).reshape(-1), sc=up(cloud.scaling), ro=up(cloud.rotation))
     bg = torch.zeros(3, device=dev)
 
-    # Setup only (untimed): depth frames standing in for the stereo network's output.
-    from gs2mesh_b200.renderer import Renderer
-    from gs2mesh_b200.tsdf import TSDFVolume
-
+    # Set-up only (untimed, in a CHILD process): depth frames standing in for the stereo network's output.
     n_sample = min(K + Wm, total_views)
-    helper = Renderer.from_scene(rigs, baseline, cloud, output_dir_root=None, args=bargs, device=str(dev))
-    helper.prepare_renderer()
-    hv = TSDFVolume(2.0 / cfg["tsdf_res"], bargs.TSDF_sdf_trunc, (0, 0, 0), (1, 1, 1), with_color=False, device=dev)
-    depth_frames = {}
-    for i in range(n_sample):
-        out = helper.render_image_pair(i, to_host=False)
-        depth_frames[i] = hv.prepare_depth(out["depth"], W, H, final_T=out["final_T"],
-                                           min_depth=bargs.TSDF_min_depth_baselines * baseline).cpu().numpy()
-    del helper, hv
-    torch.cuda.empty_cache()
+    tmp = tempfile.mktemp(prefix="gsb_depth_frames_", suffix=".npz")
+    env = dict(os.environ, GSB_BENCH_NSAMPLE=str(n_sample), GSB_BENCH_TOTAL_VIEWS=str(total_views))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--config", args.config, "--emit-depth-frames", tmp, "--gpus", "1"],
+                   check=True, env=env, stdout=sys.stderr)
+    depth_frames = np.load(tmp)["depth"]
+    os.unlink(tmp)
+    assert "libgs2mesh_b200" not in open("/proc/self/maps").read(), "the reference process must not map the product library"
 
     ovol = orc.OracleTSDFVolume(2.0 / cfg["tsdf_res"], bargs.TSDF_sdf_trunc, with_color=True)
 
-    raster_ms = []
+    raster_ms, raster_wall_ms = [], []
 
     def step(i):
         frames = []
@@ -458,11 +502,13 @@ def run_reference(args, cfg, rank, local, world):
             vt = cam.view_transforms_from_camera(c)
             view, proj, pos = up(vt.world_view), up(vt.full_proj), up(vt.cam_center)  # cameras.py:54-57 uploads per view
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
             e0.record()
             res = orc.ref_forward_torch(g["xyz"], g["op"], view, proj, pos, W, H, vt.tan_fovx, vt.tan_fovy, bg, shs=g["sh"],
                                         scales=g["sc"], rotations=g["ro"], sh_degree=3)
             e1.record()
             e1.synchronize()
+            raster_wall_ms.append(1e3 * (time.perf_counter() - t0))
             raster_ms.append(e0.elapsed_time(e1))
             rendering = (res["color"].permute(1, 2, 0) * 255).cpu().numpy()  # :389
             frames.append(np.clip(np.rint(rendering), 0, 255).astype(np.uint8))  # imwrite's float->u8
@@ -475,6 +521,7 @@ def run_reference(args, cfg, rank, local, world):
         step(i)
     torch.cuda.synchronize()
     raster_ms.clear()
+    raster_wall_ms.clear()
     sampler = ClockSampler(local)
     sampler.start()
     t0 = time.perf_counter()
@@ -488,12 +535,19 @@ def run_reference(args, cfg, rank, local, world):
     value = done / dt
     return {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": done, "warmup": Wm,
-        "ms_per_step": round(1e3 * dt / max(done, 1), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(1e3 * dt / max(done, 1), 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, cfg, total_views),
-                   "note": "reference rasterizer (oracle/_ref, sm_100a build of the unmodified sources) x2 per pair as called by "
-                           "renderer_utils.py:378-390 + Open3D-0.17-equivalent CPU TSDF; rank 0 only; PNG encode and DLNR excluded",
-                   "reference_rasterizer_ms_per_view": round(float(np.mean(raster_ms)), 4) if raster_ms else None},
+        "config": shared_config(args, cfg, total_views, world, K if args.scaling == "weak" else len(range(0, total_views, world))),
+        "details": {"note": "reference rasterizer (oracle/_ref, sm_100a build of the unmodified sources) x2 per pair as called by "
+                            "renderer_utils.py:378-390 + Open3D-0.17-equivalent CPU TSDF; rank 0 only; PNG encode and DLNR excluded; "
+                            "the stand-in depth frames were rendered by a child process (this process never maps libgs2mesh_b200.so)",
+                    "reference_rasterizer_ms_per_view": {
+                        "cuda_events_around_the_call": round(float(np.mean(raster_ms)), 4) if raster_ms else None,
+                        "host_wall": round(float(np.mean(raster_wall_ms)), 4) if raster_wall_ms else None,
+                        "note": "as called: the reference blocks on a 4-byte D2H in the middle of every frame "
+                                "(rasterizer_impl.cu:281) and grows three scratch buffers through callbacks, so its per-view time "
+                                "follows the host's launch / copy latency (2.5 ms on one box, 5.0 ms on another in round 1), "
+                                "not only its kernels"}},
         "clocks": clocks,
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{done} stereo pairs: reference rasterizer (unmodified sources, sm_100a build, GPU) + Open3D-0.17-equivalent CPU TSDF port on {cores} threads"},
@@ -510,8 +564,10 @@ def main():
     ap.add_argument("--config", default="C1")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dense-reduce", action="store_true", help="merge the whole volume instead of the touched bricks only")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (driver contract): --steps pairs PER RANK; strong: --steps pairs in total, split over the ranks")
+    ap.add_argument("--emit-depth-frames", default=None, help=argparse.SUPPRESS)  # child process of the reference arm
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -521,11 +577,19 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: gs2mesh_b200 has no CPU fallback")
     rank, local, world = setup_dist(args.gpus)
-    import __graft_entry__ as ge
-
     if rank == 0:
-        ge.build()
+        if args.impl == "reference" and not args.emit_depth_frames:
+            from oracle import oracle as orc
+
+            orc.build()  # the checker only: the reference process never loads the product library
+        else:
+            import __graft_entry__ as ge
+
+            ge.build()
     barrier(world)
+    if args.emit_depth_frames:
+        emit_depth_frames(args, cfg, local)
+        return
     if args.impl == "reference":
         args.steps = min(args.steps, 200)  # bounded: ~0.25 s of CPU TSDF per step at C1
         line = run_reference(args, cfg, rank, local, world)

@@ -19,7 +19,8 @@ RASTER_DEBUG_SYNC = 4
 RASTER_CUB_SORT = 8
 RASTER_ASYNC = 16
 RASTER_FAST_EXP = 32
-RENDER_IMPLS = {"block": 1, "warp": 2, "compact": 3, "dual": 4}
+RASTER_PAIR_SHARED_DEPTH = 64
+RENDER_IMPLS = {"block": 1, "warp": 2, "compact": 3, "dual": 4, "table": 5}
 SH_MODES = {"scalar": 1, "vec": 2, "padded": 3}
 
 
@@ -51,8 +52,9 @@ class GsbRasterArgs(C.Structure):
 
 class GsbVolumeDesc(C.Structure):
     _fields_ = [
-        ("brick_origin", C.c_int32 * 3), ("brick_count", C.c_int32 * 3), ("voxel_length", C.c_double), ("sdf_trunc", C.c_double),
-        ("tsdf_weight", _vp), ("color", _vp), ("brick_stamp", _vp), ("brick_list", _vp), ("counters", _vp),
+        ("voxel_length", C.c_double), ("sdf_trunc", C.c_double), ("pool_bricks", C.c_uint32), ("hash_slots", C.c_uint32),
+        ("tsdf_weight", _vp), ("color", _vp), ("brick_index", _vp), ("hash_keys", _vp), ("hash_vals", _vp), ("hash_stamp", _vp),
+        ("brick_list", _vp), ("counters", _vp),
     ]
 
 
@@ -67,6 +69,7 @@ SIGNATURES = {
     "gsb_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "gsb_raster_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
     "gsb_raster_forward": (C.c_int, [C.POINTER(GsbRasterArgs), _vp]),
+    "gsb_raster_forward_pair": (C.c_int, [C.POINTER(GsbRasterArgs), C.POINTER(GsbRasterArgs), _vp, _vp]),
     "gsb_raster_required_instances": (C.c_int64, []),
     "gsb_raster_mark_visible": (C.c_int, [C.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "gsb_image_to_u8": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp]),
@@ -76,14 +79,22 @@ SIGNATURES = {
     "gsb_mask_morphology": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "gsb_tsdf_integrate": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
                                      C.POINTER(C.c_double), _vp]),
+    "gsb_tsdf_touch": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), _vp]),
     "gsb_tsdf_to_sums": (C.c_int, [_vp, _vp]),
     "gsb_tsdf_from_sums": (C.c_int, [_vp, _vp]),
     "gsb_tsdf_sums_bricks": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, _vp]),
-    "gsb_tsdf_export_dense": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "gsb_tsdf_find_bricks": (C.c_int, [_vp, _vp, C.c_uint32, C.c_int, _vp, _vp, _vp]),
+    "gsb_tsdf_export_dense": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _vp]),
     "gsb_tsdf_last_stats": (C.c_int, [_vp, _vp, _vp]),
-    "gsb_mesh_count": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp]),
-    "gsb_mesh_emit": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _vp]),
-    "gsb_mesh_vertices": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp]),
+    "gsb_tsdf_reduce_scratch_bytes": (C.c_size_t, [_vp, C.c_int, C.c_uint32]),
+    "gsb_tsdf_reduce": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
+    "gsb_tsdf_reduce_required_bytes": (C.c_size_t, []),
+    "gsb_comm_unique_id": (C.c_int, [_vp]),
+    "gsb_comm_create": (_vp, [_vp, C.c_int, C.c_int]),
+    "gsb_comm_destroy": (None, [_vp]),
+    "gsb_mesh_count": (C.c_int, [_vp, C.POINTER(C.c_int32), _vp, C.c_uint32, _vp, _vp]),
+    "gsb_mesh_emit": (C.c_int, [_vp, C.POINTER(C.c_int32), _vp, C.c_uint32, _vp, _vp, _vp]),
+    "gsb_mesh_vertices": (C.c_int, [_vp, C.POINTER(C.c_int32), _vp, C.c_int64, _vp, _vp, _vp]),
     "gsb_mesh_vertex_normals": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, _vp]),
 }
 

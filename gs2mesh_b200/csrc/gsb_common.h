@@ -16,7 +16,6 @@
 struct GsbVolume {
   GsbVolumeDesc d;
   uint32_t frame = 0;
-  size_t n_bricks = 0;
 };
 
 namespace gsb {
@@ -117,6 +116,48 @@ struct StageTimer {
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// Brick hash of the TSDF volume (Open3D's unordered_map<Vector3i, VolumeUnit>): open addressing, linear probing,
+// 64-bit keys = three 21-bit biased lattice indices.  An entry's position in the table identifies the brick inside a
+// frame (work list, frame stamp); hash_vals[position] is its slot in the brick pool.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned long long kHashEmpty = ~0ull;
+constexpr uint32_t kSlotNone = 0xffffffffu;   // key present, no pool slot (pool exhausted) / not found
+constexpr int kBrickBias = 1 << 20;           // lattice indices in [-2^20, 2^20)
+
+__host__ __device__ inline bool brick_key_ok(int bx, int by, int bz) {
+  return bx >= -kBrickBias && bx < kBrickBias && by >= -kBrickBias && by < kBrickBias && bz >= -kBrickBias && bz < kBrickBias;
+}
+__host__ __device__ inline unsigned long long brick_key(int bx, int by, int bz) {
+  return ((unsigned long long)(uint32_t)(bx + kBrickBias) << 42) | ((unsigned long long)(uint32_t)(by + kBrickBias) << 21) |
+         (unsigned long long)(uint32_t)(bz + kBrickBias);
+}
+__host__ __device__ inline void brick_unkey(unsigned long long key, int& bx, int& by, int& bz) {
+  bx = (int)((key >> 42) & 0x1fffffu) - kBrickBias;
+  by = (int)((key >> 21) & 0x1fffffu) - kBrickBias;
+  bz = (int)(key & 0x1fffffu) - kBrickBias;
+}
+__host__ __device__ inline uint32_t brick_hash(unsigned long long key, uint32_t mask) {
+  key ^= key >> 33;  // splitmix64 finaliser
+  key *= 0xff51afd7ed558ccdull;
+  key ^= key >> 33;
+  key *= 0xc4ceb9fe1a85ec53ull;
+  key ^= key >> 33;
+  return (uint32_t)key & mask;
+}
+#ifdef __CUDACC__
+// position of `key` in the table, or kSlotNone
+__device__ inline uint32_t brick_find(const unsigned long long* __restrict__ keys, uint32_t mask, unsigned long long key) {
+  uint32_t h = brick_hash(key, mask);
+  for (uint32_t probe = 0; probe <= mask; ++probe, h = (h + 1) & mask) {
+    const unsigned long long k = keys[h];
+    if (k == key) return h;
+    if (k == kHashEmpty) return kSlotNone;
+  }
+  return kSlotNone;
+}
+#endif
 
 // Carves consecutive 256-byte aligned regions out of one caller-owned block.
 struct Carver {

@@ -22,17 +22,33 @@ constexpr int kHalo = GSB_BRICK + 1;  // 17
 struct VolView {
   const float2* tw;
   const float4* color;
-  int nb[3];
-  int b0[3];
+  const unsigned long long* keys;  // brick hash
+  const uint32_t* vals;
+  const int4* index;               // lattice index of every pool slot
+  uint32_t mask, pool;
+  int nb[3];                       // key window: brick count
+  int b0[3];                       // key window: first brick
   double voxel_length;
 };
 
+// pool slot of the brick with lattice index (bx,by,bz), or kSlotNone (Open3D: volume_units_.find() == end())
+__device__ __forceinline__ uint32_t slot_of_brick(const VolView& v, int bx, int by, int bz) {
+  if (!brick_key_ok(bx, by, bz)) return kSlotNone;
+  const uint32_t h = brick_find(v.keys, v.mask, brick_key(bx, by, bz));
+  if (h == kSlotNone) return kSlotNone;
+  const uint32_t s = v.vals[h];
+  return s < v.pool ? s : kSlotNone;
+}
+
+// (gx,gy,gz) = voxel coordinates relative to the key window's first voxel; a brick that was never opened -> weight 0
+__device__ __forceinline__ size_t voxel_address(const VolView& v, int gx, int gy, int gz) {
+  const uint32_t slot = slot_of_brick(v, v.b0[0] + (gx >> 4), v.b0[1] + (gy >> 4), v.b0[2] + (gz >> 4));
+  if (slot == kSlotNone) return (size_t)-1;
+  return (size_t)slot * GSB_BRICK_VOXELS + ((gx & 15) * 16 + (gy & 15)) * 16 + (gz & 15);
+}
 __device__ __forceinline__ float2 load_voxel(const VolView& v, int gx, int gy, int gz) {
-  // (gx,gy,gz) = voxel coordinates relative to the window's first voxel; outside -> weight 0
-  if (gx < 0 || gy < 0 || gz < 0 || gx >= v.nb[0] * GSB_BRICK || gy >= v.nb[1] * GSB_BRICK || gz >= v.nb[2] * GSB_BRICK)
-    return make_float2(0.f, 0.f);
-  const size_t brick = ((size_t)(gx >> 4) * v.nb[1] + (gy >> 4)) * v.nb[2] + (gz >> 4);
-  return v.tw[brick * GSB_BRICK_VOXELS + ((gx & 15) * 16 + (gy & 15)) * 16 + (gz & 15)];
+  const size_t a = voxel_address(v, gx, gy, gz);
+  return a == (size_t)-1 ? make_float2(0.f, 0.f) : v.tw[a];
 }
 
 __device__ __forceinline__ int cube_case(const float2* s, int x, int y, int z) {
@@ -53,12 +69,22 @@ __global__ void __launch_bounds__(256) mc_brick_kernel(const VolView v, const ui
                                                        long long* __restrict__ edge_keys) {
   __shared__ float2 s[kHalo * kHalo * kHalo];
   __shared__ uint32_t s_count;
+  __shared__ uint32_t s_nb[8];  // pool slots of the brick and its +1 neighbours (bit 2: x+1, bit 1: y+1, bit 0: z+1)
   const uint32_t brick = bricks[blockIdx.x];
-  const int bz = brick % v.nb[2], by = (brick / v.nb[2]) % v.nb[1], bx = brick / (v.nb[2] * v.nb[1]);
+  const int4 bi = v.index[brick];
+  // window-relative brick coordinates (the edge keys are relative to the key window)
+  const int bx = bi.x - v.b0[0], by = bi.y - v.b0[1], bz = bi.z - v.b0[2];
   if (threadIdx.x == 0) s_count = 0;
+  if (threadIdx.x < 8)
+    s_nb[threadIdx.x] = threadIdx.x == 0 ? brick
+                                         : slot_of_brick(v, bi.x + ((threadIdx.x >> 2) & 1), bi.y + ((threadIdx.x >> 1) & 1),
+                                                         bi.z + (threadIdx.x & 1));
+  __syncthreads();
   for (int i = threadIdx.x; i < kHalo * kHalo * kHalo; i += blockDim.x) {
     const int z = i % kHalo, y = (i / kHalo) % kHalo, x = i / (kHalo * kHalo);
-    s[i] = load_voxel(v, bx * 16 + x, by * 16 + y, bz * 16 + z);
+    const uint32_t slot = s_nb[((x >> 4) << 2) | ((y >> 4) << 1) | (z >> 4)];
+    s[i] = slot == kSlotNone ? make_float2(0.f, 0.f)
+                             : v.tw[(size_t)slot * GSB_BRICK_VOXELS + ((x & 15) * 16 + (y & 15)) * 16 + (z & 15)];
   }
   __syncthreads();
   const long long base = mode ? tri_offsets[blockIdx.x] : 0;
@@ -113,12 +139,9 @@ __global__ void __launch_bounds__(256) mc_vertices_kernel(const VolView v, const
   xyz[3 * i + 1] = p[1];
   xyz[3 * i + 2] = p[2];
   if (rgb != nullptr && v.color != nullptr) {
-    const size_t ia = (((size_t)(gx >> 4) * v.nb[1] + (gy >> 4)) * v.nb[2] + (gz >> 4)) * GSB_BRICK_VOXELS +
-                      ((gx & 15) * 16 + (gy & 15)) * 16 + (gz & 15);
-    const int hx = gx + dx, hy = gy + dy, hz = gz + dz;
-    const size_t ib = (((size_t)(hx >> 4) * v.nb[1] + (hy >> 4)) * v.nb[2] + (hz >> 4)) * GSB_BRICK_VOXELS +
-                      ((hx & 15) * 16 + (hy & 15)) * 16 + (hz & 15);
-    const float4 c0 = v.color[ia], c1 = v.color[ib];
+    const size_t ia = voxel_address(v, gx, gy, gz), ib = voxel_address(v, gx + dx, gy + dy, gz + dz);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 c0 = ia == (size_t)-1 ? zero : v.color[ia], c1 = ib == (size_t)-1 ? zero : v.color[ib];
     const double inv = 1.0 / (f0 + f1);
     rgb[3 * i] = (float)((f1 * ((double)c0.x / 255.0) + f0 * ((double)c1.x / 255.0)) * inv);
     rgb[3 * i + 1] = (float)((f1 * ((double)c0.y / 255.0) + f0 * ((double)c1.y / 255.0)) * inv);
@@ -162,16 +185,30 @@ __global__ void __launch_bounds__(256) mesh_normalize_kernel(double* __restrict_
   }
 }
 
-VolView view_of(const GsbVolume* vol) {
+VolView view_of(const GsbVolume* vol, const int32_t* window) {
   VolView v;
   v.tw = reinterpret_cast<const float2*>(vol->d.tsdf_weight);
   v.color = reinterpret_cast<const float4*>(vol->d.color);
+  v.keys = reinterpret_cast<const unsigned long long*>(vol->d.hash_keys);
+  v.vals = vol->d.hash_vals;
+  v.index = reinterpret_cast<const int4*>(vol->d.brick_index);
+  v.mask = vol->d.hash_slots - 1u;
+  v.pool = vol->d.pool_bricks;
   for (int k = 0; k < 3; ++k) {
-    v.nb[k] = vol->d.brick_count[k];
-    v.b0[k] = vol->d.brick_origin[k];
+    v.b0[k] = window[k];
+    v.nb[k] = window[3 + k];
   }
   v.voxel_length = vol->d.voxel_length;
   return v;
+}
+
+bool window_ok(const int32_t* w) {
+  if (!w) return false;
+  for (int k = 0; k < 3; ++k)
+    if (w[3 + k] <= 0 || w[3 + k] > (1 << 21)) return false;
+  // keys = ((gx*NY + gy)*NZ + gz)*3 + axis must fit 63 bits
+  const double vox = 16.0 * 16.0 * 16.0 * (double)w[3] * (double)w[4] * (double)w[5] * 3.0;
+  return vox < 9.0e18;
 }
 
 }  // namespace
@@ -181,32 +218,35 @@ using namespace gsb;
 
 extern "C" {
 
-int gsb_mesh_count(const GsbVolume* vol, const uint32_t* bricks, uint32_t n_bricks, uint32_t* tri_counts, void* stream_v) {
+int gsb_mesh_count(const GsbVolume* vol, const int32_t* window, const uint32_t* bricks, uint32_t n_bricks, uint32_t* tri_counts,
+                   void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!vol || (n_bricks && (!bricks || !tri_counts))) return fail(GSB_ERR_INVALID, "mesh_count: bad arguments");
+  if (!vol || !window_ok(window) || (n_bricks && (!bricks || !tri_counts))) return fail(GSB_ERR_INVALID, "mesh_count: bad arguments");
   if (n_bricks == 0) return GSB_OK;
-  mc_brick_kernel<<<n_bricks, 256, 0, stream>>>(view_of(vol), bricks, 0, tri_counts, nullptr, nullptr);
+  mc_brick_kernel<<<n_bricks, 256, 0, stream>>>(view_of(vol, window), bricks, 0, tri_counts, nullptr, nullptr);
   count_launch();
   return check_launch("mc_brick_kernel(count)", stream, false);
 }
 
-int gsb_mesh_emit(const GsbVolume* vol, const uint32_t* bricks, uint32_t n_bricks, const int64_t* tri_offsets, int64_t* edge_keys,
-                  void* stream_v) {
+int gsb_mesh_emit(const GsbVolume* vol, const int32_t* window, const uint32_t* bricks, uint32_t n_bricks, const int64_t* tri_offsets,
+                  int64_t* edge_keys, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!vol || (n_bricks && (!bricks || !tri_offsets || !edge_keys))) return fail(GSB_ERR_INVALID, "mesh_emit: bad arguments");
+  if (!vol || !window_ok(window) || (n_bricks && (!bricks || !tri_offsets || !edge_keys)))
+    return fail(GSB_ERR_INVALID, "mesh_emit: bad arguments");
   if (n_bricks == 0) return GSB_OK;
-  mc_brick_kernel<<<n_bricks, 256, 0, stream>>>(view_of(vol), bricks, 1, nullptr, reinterpret_cast<const long long*>(tri_offsets),
+  mc_brick_kernel<<<n_bricks, 256, 0, stream>>>(view_of(vol, window), bricks, 1, nullptr, reinterpret_cast<const long long*>(tri_offsets),
                                                 reinterpret_cast<long long*>(edge_keys));
   count_launch();
   return check_launch("mc_brick_kernel(emit)", stream, false);
 }
 
-int gsb_mesh_vertices(const GsbVolume* vol, const int64_t* keys, int64_t n, double* xyz, float* rgb, void* stream_v) {
+int gsb_mesh_vertices(const GsbVolume* vol, const int32_t* window, const int64_t* keys, int64_t n, double* xyz, float* rgb,
+                      void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!vol || n < 0 || (n && (!keys || !xyz))) return fail(GSB_ERR_INVALID, "mesh_vertices: bad arguments");
+  if (!vol || !window_ok(window) || n < 0 || (n && (!keys || !xyz))) return fail(GSB_ERR_INVALID, "mesh_vertices: bad arguments");
   if (n == 0) return GSB_OK;
-  mc_vertices_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(view_of(vol), reinterpret_cast<const long long*>(keys), n, xyz,
-                                                                     rgb);
+  mc_vertices_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(view_of(vol, window), reinterpret_cast<const long long*>(keys),
+                                                                     n, xyz, rgb);
   count_launch();
   return check_launch("mc_vertices_kernel", stream, false);
 }

@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
                                                                 uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
                                                                 uint2* __restrict__ ranges, int window, int write_keys,
                                                                 const uint32_t* __restrict__ gather_src,
-                                                                uint32_t* __restrict__ gather_dst) {
+                                                                uint32_t* __restrict__ gather_dst,
+                                                                const uint32_t* __restrict__ gather_src2,
+                                                                uint32_t* __restrict__ gather_dst2) {
   constexpr int kBlock = kRdxThreads * kItems;
   __shared__ uint32_t s_key[kBlock];
   __shared__ uint32_t s_val[kBlock];
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
     const uint32_t i = seg + k * 32 + lane;
     const bool ok = i < n;
     key[k] = ok ? keys_in[i] : 0xffffffffu;
-    val[k] = ok ? vals_in[i] : 0u;
+    val[k] = ok ? (vals_in != nullptr ? vals_in[i] : i) : 0u;  // no payload array: the payload is the item's index
   }
   // (b) same-digit groups of each 32-item row (independent votes, pipelined)
   uint32_t peers[kItems];
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(kRdxThreads, kItems >= 16 ? 3 : (kItems >= 8 ?
     const uint32_t vv = s_val[sidx];
     vals_out[dst] = vv;
     if (gather_dst != nullptr) gather_dst[dst] = gather_src[vv];  // a per-value attribute, delivered in sorted order
+    if (gather_dst2 != nullptr) gather_dst2[dst] = gather_src2[vv];
     if (ranges != nullptr) {
       // slots are in ascending tile order inside the block (stable LSD => low digit sorted within high digit)
       if (sidx == 0 || s_key[sidx - 1] != kk) atomicMin(&ranges[kk].x, dst);
@@ -358,8 +361,9 @@ inline void radix_prepare(uint32_t* scratch, size_t max_items, int bits, cudaStr
   cudaMemsetAsync(scratch, 0, words * sizeof(uint32_t), stream);
 }
 
-// Enqueues ceil(bits/8) stable passes sorting (keys, vals) by key bits [0, bits).  gather_dst != NULL: the last pass
-// also writes gather_dst[j] = gather_src[value of sorted item j].  `a`/`b` are
+// Enqueues ceil(bits/8) stable passes sorting (keys, vals) by key bits [0, bits).  identity_payload: the payload of item i
+// is i (the first pass synthesises it instead of reading vals_a).  gather_dst != NULL: the last pass also writes
+// gather_dst[j] = gather_src[value of sorted item j] (likewise gather_dst2 / gather_src2).  `a`/`b` are
 // ping-pong buffers; returns which buffer holds the result (0 = a, 1 = b).  n is either the host
 // value (counters == NULL) or read on the device from counters[1] (clamped by capacity).
 // histogram_ready: the caller already ran radix_prepare() and filled the digit histograms.
@@ -367,7 +371,8 @@ template <int kItems>
 inline int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_host,
                               const unsigned long long* counters, int64_t capacity, size_t max_items, int bits,
                               uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches,
-                              bool histogram_ready, const uint32_t* gather_src, uint32_t* gather_dst) {
+                              bool histogram_ready, const uint32_t* gather_src, uint32_t* gather_dst,
+                              const uint32_t* gather_src2, uint32_t* gather_dst2, bool identity_payload) {
   const uint32_t nblocks = (uint32_t)radix_blocks_for(max_items);
   if (nblocks == 0) return 0;
   const int passes = (bits + 7) / 8;
@@ -383,14 +388,14 @@ inline int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
     const uint32_t* kin = cur ? keys_b : keys_a;
-    const uint32_t* vin = cur ? vals_b : vals_a;
+    const uint32_t* vin = (p == 0 && identity_payload) ? nullptr : (cur ? vals_b : vals_a);
     uint32_t* kout = cur ? keys_a : keys_b;
     uint32_t* vout = cur ? vals_a : vals_b;
     radix_pass_kernel<kItems><<<nblocks, kRdxThreads, 0, stream>>>(
         kin, vin, kout, vout, n_host, counters, capacity, db * p, (1u << db) - 1u, ghist + p * kRdxBins,
         status + (size_t)p * nblocks * kRdxBins,
         tickets + p, p == passes - 1 ? ranges_on_last_pass : nullptr, radix_lookback_window(), p != passes - 1,
-        gather_src, p == passes - 1 ? gather_dst : nullptr);
+        gather_src, p == passes - 1 ? gather_dst : nullptr, gather_src2, p == passes - 1 ? gather_dst2 : nullptr);
     *launches += 1;
     cur ^= 1;
   }
@@ -400,10 +405,13 @@ inline int radix_sort_pairs_t(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys
 inline int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n_host,
                             const unsigned long long* counters, int64_t capacity, size_t max_items, int bits,
                             uint32_t* scratch, uint2* ranges_on_last_pass, cudaStream_t stream, uint64_t* launches,
-                            bool histogram_ready, const uint32_t* gather_src = nullptr, uint32_t* gather_dst = nullptr) {
+                            bool histogram_ready, const uint32_t* gather_src = nullptr, uint32_t* gather_dst = nullptr,
+                            const uint32_t* gather_src2 = nullptr, uint32_t* gather_dst2 = nullptr,
+                            bool identity_payload = false) {
 #define GSB_RADIX_CALL(ITEMS)                                                                                              \
   radix_sort_pairs_t<ITEMS>(keys_a, vals_a, keys_b, vals_b, n_host, counters, capacity, max_items, bits, scratch,          \
-                            ranges_on_last_pass, stream, launches, histogram_ready, gather_src, gather_dst)
+                            ranges_on_last_pass, stream, launches, histogram_ready, gather_src, gather_dst, gather_src2,   \
+                            gather_dst2, identity_payload)
   switch (radix_items_for(max_items)) {
     case 4: return GSB_RADIX_CALL(4);
     case 8: return GSB_RADIX_CALL(8);

@@ -364,6 +364,21 @@ __device__ __forceinline__ void eval_sh(int D, Acc sh, float3 dir, float res[3])
   }
 }
 
+struct PreEye {  // what differs between the two eyes of a stereo pair (renderer_utils.py:378-389)
+  const float* view;
+  const float* proj;
+  const float* campos;
+  float tan_fovx, tan_fovy, focal_x, focal_y;
+  float4* recA;
+  float4* recB;
+  float2* recC;
+  uint32_t* tiles;
+  int* radii;
+  unsigned long long* counters;   // [0] += sum of reference tile rectangles, [3] |= 1 if the eyes' view depths differ
+  uint64_t* masks;                // kept-tile bitmask of candidate rectangles with <= 64 tiles
+  uint32_t* rects;                // packed candidate rectangle the mask refers to (kRectLarge: none)
+  uint32_t* depth_keys;           // view-depth sort key per Gaussian, or NULL (validation path / shared with the other eye)
+};
 struct PreParams {
   int P, D, M, W, H;
   const float* means3D;
@@ -374,25 +389,14 @@ struct PreParams {
   const float* rotations;
   const float* cov3D;
   float scale_modifier;
-  const float* view;
-  const float* proj;
-  const float* campos;
-  float tan_fovx, tan_fovy, focal_x, focal_y;
   uint32_t gx, gy;
   uint32_t flags;
   int use_tma;
   int sh_mode;  // staging of full-degree SH blocks (M = 16): 0 linear + scalar reads, 1 linear + 16-byte reads,
                 // 2 one 192-byte bulk copy per lane into padded slots + 16-byte reads (bank-conflict free)
-  float4* recA;
-  float4* recB;
-  float2* recC;
-  uint32_t* tiles;
-  int* radii;
-  unsigned long long* ref_count;  // sum of reference tile rectangles
-  uint32_t* depth_keys;           // view-depth sort key per Gaussian (0xffffffff = not binned)
-  uint32_t* ids;                  // identity permutation, the sort's payload
-  uint64_t* masks;                // kept-tile bitmask of candidate rectangles with <= 64 tiles
-  uint32_t* rects;                // packed candidate rectangle the mask refers to (kRectLarge: none)
+  int binned;        // 0: validation path (no depth keys, no tile masks)
+  int shared_depth;  // stereo pair whose eyes see every Gaussian at the same view depth: one key array (eye 0's), verified
+  PreEye eye[2];
 };
 
 constexpr int kDefaultShMode = 1;                // GSB_PRE_SH overrides (A/B switch)
@@ -407,7 +411,15 @@ struct WarpStage {  // one warp's staged parameter block; every member offset is
   uint64_t pad[15];
 };
 
-__global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams p) {
+// kEyes = 1: one view.  kEyes = 2: the two eyes of a stereo pair in ONE pass over the Gaussian parameters -- the 236-byte
+// parameter block of every Gaussian (positions, scales, rotations, opacities, 192 B of SH) is staged once, the 3-D
+// covariance is computed once, and projection / binning / SH shading run per eye from the staged block.  The eyes of a
+// rig share the camera rotation and differ by a translation along the camera x axis (transformation_utils.py:219-223),
+// so a Gaussian's view depth is THE SAME float in both eyes whenever the z rows of the two view matrices are bitwise
+// equal; then one depth key per Gaussian (and one depth sort) serves both eyes.  The kernel verifies that and raises
+// counters[3] otherwise (the caller then renders the eyes separately).
+template <int kEyes>
+__global__ void __launch_bounds__(kPreThreads, kEyes == 1 ? 6 : 4) preprocess_kernel(const PreParams p) {
   __shared__ __align__(128) WarpStage stage[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpStage& st = stage[warp];
@@ -445,130 +457,152 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
   }
 
   const bool valid = lane < count;
-  bool visible = false;
-  float px = 0.f, py = 0.f, zv = 0.f, opacity = 0.f, ca = 0.f, cb = 0.f, cc = 0.f;
+  bool visible[kEyes], front[kEyes];
+  float px[kEyes], py[kEyes], zv[kEyes], ca[kEyes], cb[kEyes], cc[kEyes];
+  int radius[kEyes];
+  uint32_t ntiles[kEyes], nref[kEyes];
   float3 pos = make_float3(0.f, 0.f, 0.f);
-  int radius = 0;
-  uint32_t ntiles = 0, nref = 0;
-
+  float3 tv[kEyes];
+  float opacity = 0.f;
+  bool any_front = false;
+#pragma unroll
+  for (int e = 0; e < kEyes; ++e) {
+    visible[e] = front[e] = false;
+    px[e] = py[e] = zv[e] = ca[e] = cb[e] = cc[e] = 0.f;
+    radius[e] = 0;
+    ntiles[e] = nref[e] = 0;
+    tv[e] = make_float3(0.f, 0.f, 0.f);
+  }
   if (valid) {
     pos = make_float3(st.xyz[lane * 3], st.xyz[lane * 3 + 1], st.xyz[lane * 3 + 2]);
-    const float* vm = p.view;
-    const float* pm = p.proj;
-    // auxiliary.h:139-164 (in_frustum): view-space point, near cull at 0.2
-    float3 t = make_float3(vm[0] * pos.x + vm[4] * pos.y + vm[8] * pos.z + vm[12],
-                           vm[1] * pos.x + vm[5] * pos.y + vm[9] * pos.z + vm[13],
-                           vm[2] * pos.x + vm[6] * pos.y + vm[10] * pos.z + vm[14]);
-    if (t.z > 0.2f) {
-      zv = t.z;
-      const float hx = pm[0] * pos.x + pm[4] * pos.y + pm[8] * pos.z + pm[12];
-      const float hy = pm[1] * pos.x + pm[5] * pos.y + pm[9] * pos.z + pm[13];
-      const float hw = pm[3] * pos.x + pm[7] * pos.y + pm[11] * pos.z + pm[15];
-      const float p_w = 1.0f / (hw + 0.0000001f);
-      const float projx = hx * p_w, projy = hy * p_w;
-
-      // forward.cu:118-152: Sigma = (S R)^T (S R); quaternion is w-first and NOT renormalised
-      float c3[6];
-      if (has_sr) {
-        const float4 q = reinterpret_cast<const float4*>(st.rot)[lane];
-        const float r = q.x, x = q.y, y = q.z, z = q.w;
-        Mat3 S;
+    opacity = st.opac[lane];
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+    for (int e = 0; e < kEyes; ++e) {
+      const float* vm = p.eye[e].view;
+      // auxiliary.h:139-164 (in_frustum): view-space point, near cull at 0.2
+      tv[e] = make_float3(vm[0] * pos.x + vm[4] * pos.y + vm[8] * pos.z + vm[12],
+                          vm[1] * pos.x + vm[5] * pos.y + vm[9] * pos.z + vm[13],
+                          vm[2] * pos.x + vm[6] * pos.y + vm[10] * pos.z + vm[14]);
+      front[e] = tv[e].z > 0.2f;
+      any_front = any_front || front[e];
+    }
+  }
+  // forward.cu:118-152: Sigma = (S R)^T (S R); quaternion is w-first and NOT renormalised.  View independent: once per pair.
+  float c3[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (any_front) {
+    if (has_sr) {
+      const float4 q = reinterpret_cast<const float4*>(st.rot)[lane];
+      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      Mat3 S;
 #pragma unroll
-          for (int i = 0; i < 3; ++i) S.m[j][i] = 0.f;
-        S.m[0][0] = p.scale_modifier * st.scale[lane * 3];
-        S.m[1][1] = p.scale_modifier * st.scale[lane * 3 + 1];
-        S.m[2][2] = p.scale_modifier * st.scale[lane * 3 + 2];
-        Mat3 R;
-        R.m[0][0] = 1.f - 2.f * (y * y + z * z);
-        R.m[0][1] = 2.f * (x * y - r * z);
-        R.m[0][2] = 2.f * (x * z + r * y);
-        R.m[1][0] = 2.f * (x * y + r * z);
-        R.m[1][1] = 1.f - 2.f * (x * x + z * z);
-        R.m[1][2] = 2.f * (y * z - r * x);
-        R.m[2][0] = 2.f * (x * z - r * y);
-        R.m[2][1] = 2.f * (y * z + r * x);
-        R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-        const Mat3 Mx = mat_mul(S, R);
-        const Mat3 Sg = mat_mul(mat_t(Mx), Mx);
-        c3[0] = Sg.m[0][0];
-        c3[1] = Sg.m[0][1];
-        c3[2] = Sg.m[0][2];
-        c3[3] = Sg.m[1][1];
-        c3[4] = Sg.m[1][2];
-        c3[5] = Sg.m[2][2];
-      } else {
+      for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) c3[k] = p.cov3D[(size_t)idx * 6 + k];
-      }
+        for (int i = 0; i < 3; ++i) S.m[j][i] = 0.f;
+      S.m[0][0] = p.scale_modifier * st.scale[lane * 3];
+      S.m[1][1] = p.scale_modifier * st.scale[lane * 3 + 1];
+      S.m[2][2] = p.scale_modifier * st.scale[lane * 3 + 2];
+      Mat3 R;
+      R.m[0][0] = 1.f - 2.f * (y * y + z * z);
+      R.m[0][1] = 2.f * (x * y - r * z);
+      R.m[0][2] = 2.f * (x * z + r * y);
+      R.m[1][0] = 2.f * (x * y + r * z);
+      R.m[1][1] = 1.f - 2.f * (x * x + z * z);
+      R.m[1][2] = 2.f * (y * z - r * x);
+      R.m[2][0] = 2.f * (x * z - r * y);
+      R.m[2][1] = 2.f * (y * z + r * x);
+      R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+      const Mat3 Mx = mat_mul(S, R);
+      const Mat3 Sg = mat_mul(mat_t(Mx), Mx);
+      c3[0] = Sg.m[0][0];
+      c3[1] = Sg.m[0][1];
+      c3[2] = Sg.m[0][2];
+      c3[3] = Sg.m[1][1];
+      c3[4] = Sg.m[1][2];
+      c3[5] = Sg.m[2][2];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) c3[k] = p.cov3D[(size_t)idx * 6 + k];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < kEyes; ++e) {
+    if (!front[e]) continue;
+    const float* vm = p.eye[e].view;
+    const float* pm = p.eye[e].proj;
+    float3 t = tv[e];
+    zv[e] = t.z;
+    const float hx = pm[0] * pos.x + pm[4] * pos.y + pm[8] * pos.z + pm[12];
+    const float hy = pm[1] * pos.x + pm[5] * pos.y + pm[9] * pos.z + pm[13];
+    const float hw = pm[3] * pos.x + pm[7] * pos.y + pm[11] * pos.z + pm[15];
+    const float p_w = 1.0f / (hw + 0.0000001f);
+    const float projx = hx * p_w, projy = hy * p_w;
 
-      // forward.cu:74-113: EWA projection with the 1.3*tan(fov) guard band and +0.3 low-pass
-      const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
-      const float txtz = t.x / t.z, tytz = t.y / t.z;
-      t.x = min(limx, max(-limx, txtz)) * t.z;
-      t.y = min(limy, max(-limy, tytz)) * t.z;
-      Mat3 J;
-      J.m[0][0] = p.focal_x / t.z;
-      J.m[0][1] = 0.f;
-      J.m[0][2] = -(p.focal_x * t.x) / (t.z * t.z);
-      J.m[1][0] = 0.f;
-      J.m[1][1] = p.focal_y / t.z;
-      J.m[1][2] = -(p.focal_y * t.y) / (t.z * t.z);
-      J.m[2][0] = 0.f;
-      J.m[2][1] = 0.f;
-      J.m[2][2] = 0.f;
-      Mat3 Wm;
-      Wm.m[0][0] = vm[0];
-      Wm.m[0][1] = vm[4];
-      Wm.m[0][2] = vm[8];
-      Wm.m[1][0] = vm[1];
-      Wm.m[1][1] = vm[5];
-      Wm.m[1][2] = vm[9];
-      Wm.m[2][0] = vm[2];
-      Wm.m[2][1] = vm[6];
-      Wm.m[2][2] = vm[10];
-      const Mat3 T = mat_mul(Wm, J);
-      Mat3 V;
-      V.m[0][0] = c3[0];
-      V.m[0][1] = c3[1];
-      V.m[0][2] = c3[2];
-      V.m[1][0] = c3[1];
-      V.m[1][1] = c3[3];
-      V.m[1][2] = c3[4];
-      V.m[2][0] = c3[2];
-      V.m[2][1] = c3[4];
-      V.m[2][2] = c3[5];
-      const Mat3 cov = mat_mul(mat_mul(mat_t(T), mat_t(V)), T);
-      const float cxx = cov.m[0][0] + 0.3f, cxy = cov.m[0][1], cyy = cov.m[1][1] + 0.3f;
+    // forward.cu:74-113: EWA projection with the 1.3*tan(fov) guard band and +0.3 low-pass
+    const float limx = 1.3f * p.eye[e].tan_fovx, limy = 1.3f * p.eye[e].tan_fovy;
+    const float txtz = t.x / t.z, tytz = t.y / t.z;
+    t.x = min(limx, max(-limx, txtz)) * t.z;
+    t.y = min(limy, max(-limy, tytz)) * t.z;
+    Mat3 J;
+    J.m[0][0] = p.eye[e].focal_x / t.z;
+    J.m[0][1] = 0.f;
+    J.m[0][2] = -(p.eye[e].focal_x * t.x) / (t.z * t.z);
+    J.m[1][0] = 0.f;
+    J.m[1][1] = p.eye[e].focal_y / t.z;
+    J.m[1][2] = -(p.eye[e].focal_y * t.y) / (t.z * t.z);
+    J.m[2][0] = 0.f;
+    J.m[2][1] = 0.f;
+    J.m[2][2] = 0.f;
+    Mat3 Wm;
+    Wm.m[0][0] = vm[0];
+    Wm.m[0][1] = vm[4];
+    Wm.m[0][2] = vm[8];
+    Wm.m[1][0] = vm[1];
+    Wm.m[1][1] = vm[5];
+    Wm.m[1][2] = vm[9];
+    Wm.m[2][0] = vm[2];
+    Wm.m[2][1] = vm[6];
+    Wm.m[2][2] = vm[10];
+    const Mat3 T = mat_mul(Wm, J);
+    Mat3 V;
+    V.m[0][0] = c3[0];
+    V.m[0][1] = c3[1];
+    V.m[0][2] = c3[2];
+    V.m[1][0] = c3[1];
+    V.m[1][1] = c3[3];
+    V.m[1][2] = c3[4];
+    V.m[2][0] = c3[2];
+    V.m[2][1] = c3[4];
+    V.m[2][2] = c3[5];
+    const Mat3 cov = mat_mul(mat_mul(mat_t(T), mat_t(V)), T);
+    const float cxx = cov.m[0][0] + 0.3f, cxy = cov.m[0][1], cyy = cov.m[1][1] + 0.3f;
 
-      const float det = (cxx * cyy - cxy * cxy);
-      if (det != 0.0f) {
-        const float det_inv = 1.f / det;
-        ca = cyy * det_inv;
-        cb = -cxy * det_inv;
-        cc = cxx * det_inv;
-        const float mid = 0.5f * (cxx + cyy);
-        const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
-        const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
-        const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
-        // auxiliary.h:41-44: ndc2Pix is evaluated in double
-        px = (float)(((projx + 1.0) * p.W - 1.0) * 0.5);
-        py = (float)(((projy + 1.0) * p.H - 1.0) * 0.5);
-        const TileRect rc = tile_rect(px, py, (int)my_radius, p.gx, p.gy);
-        nref = (rc.x1 - rc.x0) * (rc.y1 - rc.y0);
-        if (nref != 0) {
-          visible = true;
-          radius = (int)my_radius;
-          opacity = st.opac[lane];
-        }
+    const float det = (cxx * cyy - cxy * cxy);
+    if (det != 0.0f) {
+      const float det_inv = 1.f / det;
+      ca[e] = cyy * det_inv;
+      cb[e] = -cxy * det_inv;
+      cc[e] = cxx * det_inv;
+      const float mid = 0.5f * (cxx + cyy);
+      const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+      const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+      const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+      // auxiliary.h:41-44: ndc2Pix is evaluated in double
+      px[e] = (float)(((projx + 1.0) * p.W - 1.0) * 0.5);
+      py[e] = (float)(((projy + 1.0) * p.H - 1.0) * 0.5);
+      const TileRect rc = tile_rect(px[e], py[e], (int)my_radius, p.gx, p.gy);
+      nref[e] = (rc.x1 - rc.x0) * (rc.y1 - rc.y0);
+      if (nref[e] != 0) {
+        visible[e] = true;
+        radius[e] = (int)my_radius;
       }
     }
   }
-  // binning, pass 1: how many tiles this Gaussian is binned into
-  // The 6 KB SH block is only fetched when some lane survived culling; the bulk copy is issued NOW
-  // so that it lands while the warp is busy binning.
-  const bool any_visible = __any_sync(0xffffffffu, visible);
+  // The 6 KB SH block is only fetched when some lane survived culling in some eye; the bulk copy is issued NOW so that it
+  // lands while the warp is busy binning.
+  bool vis_any = false;
+#pragma unroll
+  for (int e = 0; e < kEyes; ++e) vis_any = vis_any || visible[e];
+  const bool any_visible = __any_sync(0xffffffffu, vis_any);
   const int shf = p.M * 3;  // SH floats per Gaussian
   const bool need_sh = p.colors == nullptr && any_visible;
   const bool tma_sh = need_sh && full_tma && (shf * 4) % 16 == 0 && shf <= kMaxShFloats;
@@ -583,17 +617,24 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
       tma_load_1d(st.sh, p.shs + (size_t)base * shf, (uint32_t)(32 * shf * 4), &st.bar);
     }
   }
-  // the staged rotations / positions / scales are dead by now: their 1280 bytes carry the lanes'
-  // footprints during binning (32 x 2 float4 = 1024 bytes)
-  __syncwarp();
-  uint64_t tile_mask = 0ull;
-  uint32_t rect_word = kRectLarge;
-  ntiles = bin_gaussians_warp(visible, px, py, ca, cb, cc, opacity, radius, p.gx, p.gy,
-                              (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, reinterpret_cast<float4*>(st.rot), tile_mask,
-                              rect_word);
+  // binning, pass 1: how many tiles this Gaussian is binned into.  The staged rotations / positions / scales are dead by
+  // now: their 1280 bytes carry the lanes' footprints during binning (32 x 2 float4 = 1024 bytes)
+  uint64_t tile_mask[kEyes];
+  uint32_t rect_word[kEyes];
+#pragma unroll
+  for (int e = 0; e < kEyes; ++e) {
+    __syncwarp();
+    tile_mask[e] = 0ull;
+    rect_word[e] = kRectLarge;
+    ntiles[e] = bin_gaussians_warp(visible[e], px[e], py[e], ca[e], cb[e], cc[e], opacity, radius[e], p.gx, p.gy,
+                                   (p.flags & GSB_RASTER_EXACT_TILE_CULL) != 0, reinterpret_cast<float4*>(st.rot), tile_mask[e],
+                                   rect_word[e]);
+  }
 
   // ---- stage 2: colour ------------------------------------------------------------------------
-  float cr = 0.f, cg = 0.f, cbl = 0.f;
+  float cr[kEyes], cg[kEyes], cbl[kEyes];
+#pragma unroll
+  for (int e = 0; e < kEyes; ++e) cr[e] = cg[e] = cbl[e] = 0.f;
   if (p.colors == nullptr) {
     if (any_visible) {
       if (tma_sh) {
@@ -602,17 +643,10 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
         for (int k = lane; k < count * shf; k += 32) st.sh[(k / shf) * sh_stride + k % shf] = p.shs[(size_t)base * shf + k];
         __syncwarp();
       }
-      if (visible) {
-        const float3 cam = make_float3(p.campos[0], p.campos[1], p.campos[2]);
-        float3 dir = make_float3(pos.x - cam.x, pos.y - cam.y, pos.z - cam.z);
-        const float len = sqrt(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-        dir.x = dir.x / len;
-        dir.y = dir.y / len;
-        dir.z = dir.z / len;
-        float res[3];
+      if (vis_any) {
         const float* sh = st.sh + lane * sh_stride;
-        if (sh_mode != 0) {  // 12 x 16-byte reads, then the same arithmetic from registers
-          float shreg[kMaxShFloats];
+        float shreg[kMaxShFloats];
+        if (sh_mode != 0) {  // 12 x 16-byte reads, then the arithmetic from registers (both eyes share the reads)
           const float4* s4 = reinterpret_cast<const float4*>(sh);
 #pragma unroll
           for (int k = 0; k < kMaxShFloats / 4; ++k) {
@@ -622,43 +656,75 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreParams
             shreg[4 * k + 2] = v4.z;
             shreg[4 * k + 3] = v4.w;
           }
-          eval_sh(p.D, [&](int i) { return shreg[i]; }, dir, res);
-        } else {
-          eval_sh(p.D, [&](int i) { return sh[i]; }, dir, res);
         }
-        cr = res[0];
-        cg = res[1];
-        cbl = res[2];
+#pragma unroll
+        for (int e = 0; e < kEyes; ++e) {
+          if (!visible[e]) continue;
+          const float* cp = p.eye[e].campos;
+          const float3 cam = make_float3(cp[0], cp[1], cp[2]);
+          float3 dir = make_float3(pos.x - cam.x, pos.y - cam.y, pos.z - cam.z);
+          const float len = sqrt(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+          dir.x = dir.x / len;
+          dir.y = dir.y / len;
+          dir.z = dir.z / len;
+          float res[3];
+          if (sh_mode != 0)
+            eval_sh(p.D, [&](int i) { return shreg[i]; }, dir, res);
+          else
+            eval_sh(p.D, [&](int i) { return sh[i]; }, dir, res);
+          cr[e] = res[0];
+          cg[e] = res[1];
+          cbl[e] = res[2];
+        }
       }
     }
-  } else if (visible) {
-    cr = p.colors[(size_t)idx * 3];
-    cg = p.colors[(size_t)idx * 3 + 1];
-    cbl = p.colors[(size_t)idx * 3 + 2];
+  } else {
+#pragma unroll
+    for (int e = 0; e < kEyes; ++e)
+      if (visible[e]) {
+        cr[e] = p.colors[(size_t)idx * 3];
+        cg[e] = p.colors[(size_t)idx * 3 + 1];
+        cbl[e] = p.colors[(size_t)idx * 3 + 2];
+      }
   }
 
   // ---- outputs --------------------------------------------------------------------------------
-  if (valid) {
-    if (visible) {
-      p.recA[idx] = make_float4(px, py, zv, opacity);
-      p.recB[idx] = make_float4(ca, cb, cc, cr);
-      p.recC[idx] = make_float2(cg, cbl);
-    }
-    p.tiles[idx] = ntiles;
-    p.radii[idx] = radius;
-    if (p.depth_keys) {
-      p.depth_keys[idx] = ntiles ? __float_as_uint(zv) : 0xffffffffu;  // z_view > 0.2: bit order == float order
-      p.ids[idx] = (uint32_t)idx;
-      if (ntiles) {
-        p.masks[idx] = tile_mask;
-        p.rects[idx] = rect_word;
+#pragma unroll
+  for (int e = 0; e < kEyes; ++e) {
+    const PreEye& o = p.eye[e];
+    if (valid) {
+      if (visible[e]) {
+        o.recA[idx] = make_float4(px[e], py[e], zv[e], opacity);
+        o.recB[idx] = make_float4(ca[e], cb[e], cc[e], cr[e]);
+        o.recC[idx] = make_float2(cg[e], cbl[e]);
+      }
+      o.tiles[idx] = ntiles[e];
+      o.radii[idx] = radius[e];
+      if (p.binned && ntiles[e]) {
+        o.masks[idx] = tile_mask[e];
+        o.rects[idx] = rect_word[e];
       }
     }
-  }
-  unsigned long long wsum = nref;
+    unsigned long long wsum = nref[e];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-  if (lane == 0 && wsum) atomicAdd(p.ref_count, wsum);
+    for (int off = 16; off > 0; off >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, off);
+    if (lane == 0 && wsum) atomicAdd(&o.counters[0], wsum);
+  }
+  if (p.binned) {
+    // Depth key = the bits of z_view (z > 0.2: bit order == float order).  A Gaussian that is binned nowhere emits no
+    // instance, so where it lands in the depth order is irrelevant (key 0).
+    if (kEyes == 2 && p.shared_depth) {
+      if (valid) p.eye[0].depth_keys[idx] = any_front ? __float_as_uint(tv[0].z) : 0u;
+      const bool differ = valid && any_front && __float_as_uint(tv[0].z) != __float_as_uint(tv[kEyes - 1].z);
+      if (__any_sync(0xffffffffu, differ) && lane == 0) {
+        atomicOr(&p.eye[0].counters[3], 1ull);
+        atomicOr(&p.eye[kEyes - 1].counters[3], 1ull);
+      }
+    } else if (valid) {
+#pragma unroll
+      for (int e = 0; e < kEyes; ++e) p.eye[e].depth_keys[idx] = front[e] ? __float_as_uint(tv[e].z) : 0u;
+    }
+  }
 }
 
 // rasterizer_impl.cu:70-111: one (key, value) per kept (Gaussian, tile) pair, written at the
@@ -706,115 +772,98 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const float4
 // counters (unsigned long long[8]): [0] reference instance count  [1] binned instances R
 //                                   [2] overflow flag (R > capacity)
 // ---------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 8;
-constexpr int kScanBlock = kScanThreads * kScanItems;
+constexpr int kEmitThreads = 256;
 
-__device__ __forceinline__ uint32_t block_reduce_sum_1024(uint32_t v, uint32_t* smem32) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) smem32[threadIdx.x >> 5] = v;
-  __syncthreads();
-  uint32_t t = smem32[threadIdx.x & 31];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  __syncthreads();
-  return t;  // every thread holds the block total
-}
-
-// tiles-per-Gaussian in depth-sorted order (written by the depth sort's last pass): per-block sums
-__global__ void __launch_bounds__(kScanThreads) sorted_block_sums_kernel(int P, const uint32_t* __restrict__ tiles_sorted,
-                                                                        uint32_t* __restrict__ block_sums) {
-  __shared__ uint32_t red[32];
-  uint32_t sum = 0;
-  const int base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k)
-    if (base + k < P) sum += tiles_sorted[base + k];
-  sum = block_reduce_sum_1024(sum, red);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = sum;
-}
-
-// exclusive offsets in depth-sorted order; the last block publishes R and the overflow flag
-__global__ void __launch_bounds__(kScanThreads) sorted_offsets_kernel(int P, const uint32_t* __restrict__ tiles_sorted,
-                                                                     const uint32_t* __restrict__ block_sums,
-                                                                     uint32_t* __restrict__ offsets,
-                                                                     unsigned long long* __restrict__ counters,
-                                                                     int64_t capacity) {
-  __shared__ uint32_t red[32];
-  __shared__ uint32_t warp_sums[32];
-  uint32_t prev = 0;
-  for (int b = threadIdx.x; b < (int)blockIdx.x; b += kScanThreads) prev += block_sums[b];
-  const uint32_t block_base = block_reduce_sum_1024(prev, red);
-  const int base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
-  uint32_t v[kScanItems];
-  uint32_t tsum = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    v[k] = base + k < P ? tiles_sorted[base + k] : 0u;
-    tsum += v[k];
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t incl = tsum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += u;
-  }
-  if (lane == 31) warp_sums[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t ws = warp_sums[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t u = __shfl_up_sync(0xffffffffu, ws, o);
-      if (lane >= o) ws += u;
-    }
-    warp_sums[lane] = ws;
-  }
-  __syncthreads();
-  uint32_t run = block_base + (warp ? warp_sums[warp - 1] : 0u) + incl - tsum;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    if (base + k < P) offsets[base + k] = run;
-    run += v[k];
-  }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) {
-    counters[1] = run;
-    if ((int64_t)run > capacity) counters[2] = 1;
-  }
-}
-
-// thread k = k-th Gaussian in depth order; the warp writes the (tile id, Gaussian id) instances of
-// its 32 Gaussians.  Rectangles with a stored bitmask are replayed from it, flattened across the
-// warp (every lane busy, stores run along the output); larger ones are re-tested cooperatively.
-__global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t* __restrict__ ids_sorted,
-                                                          const uint32_t* __restrict__ offsets,
-                                                          const float4* __restrict__ recA, const float4* __restrict__ recB,
-                                                          const uint32_t* __restrict__ tiles, const int* __restrict__ radii,
-                                                          const uint64_t* __restrict__ masks,
-                                                          const uint32_t* __restrict__ rects, uint32_t gx, uint32_t gy,
-                                                          uint32_t flags, const unsigned long long* __restrict__ counters,
-                                                          uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
-                                                          uint32_t* __restrict__ ghist, int hist_passes, int digit_bits) {
+// thread k = k-th Gaussian in depth order.  ONE kernel turns the tiles-per-Gaussian counts (delivered in depth order by the
+// depth sort's last pass) into instance offsets AND writes the instances:
+//   * exclusive scan: per-block scan + chained look-back over per-block status words (blocks take tickets in arrival
+//     order, so every predecessor of a block is already running; a full warp inspects 32 predecessors per round);
+//   * the warp writes the (tile id, Gaussian id) instances of its 32 Gaussians.  Rectangles with a stored bitmask are
+//     replayed from it, flattened across the warp (every lane busy, stores run along the output); larger ones are
+//     re-tested cooperatively.
+// The last block publishes R (counters[1]) and the overflow flag (counters[2]); stores beyond `capacity` are dropped.
+// status words: [31:30] 0 = not ready, 1 = block aggregate, 2 = inclusive prefix | 30-bit value (capacity < 2^30).
+__global__ void __launch_bounds__(kEmitThreads) emit_scan_kernel(int P, const uint32_t* __restrict__ ids_sorted,
+                                                                  const uint32_t* __restrict__ tiles_sorted,
+                                                                  const float4* __restrict__ recA, const float4* __restrict__ recB,
+                                                                  const int* __restrict__ radii, const uint64_t* __restrict__ masks,
+                                                                  const uint32_t* __restrict__ rects, uint32_t gx, uint32_t gy,
+                                                                  uint32_t flags, int64_t capacity,
+                                                                  unsigned long long* __restrict__ counters,
+                                                                  uint32_t* __restrict__ scan_status, uint32_t* __restrict__ scan_ticket,
+                                                                  uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
+                                                                  uint32_t* __restrict__ ghist, int hist_passes, int digit_bits) {
   // digit histograms of the tile ids this block emits (what the tile sort's passes need), so the
   // sort does not have to read the instance stream once more just to count
   __shared__ uint32_t shist[kRdxMaxPasses][kRdxBins];
+  __shared__ uint32_t warp_tot[kEmitThreads / 32];
+  __shared__ uint32_t s_bid, s_prefix;
   for (int p = 0; p < hist_passes; ++p) shist[p][threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_bid = atomicAdd(scan_ticket, 1u);
   __syncthreads();
   auto tally = [&](uint32_t tile) {
     for (int p = 0; p < hist_passes; ++p) atomicAdd(&shist[p][(tile >> (digit_bits * p)) & ((1u << digit_bits) - 1u)], 1u);
   };
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const bool fits = counters[2] == 0;
-  uint32_t gid = 0, off = 0, rect = kRectLarge;
-  bool active = false;
-  if (k < P && fits) {
-    gid = ids_sorted[k];
-    active = tiles[k] != 0;  // `tiles` is in depth-sorted order here
-    off = offsets[k];
+  const uint32_t bid = s_bid;
+  const int k = (int)(bid * kEmitThreads + threadIdx.x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t cnt = k < P ? tiles_sorted[k] : 0u;
+  // ---- block-level exclusive scan of the counts
+  uint32_t incl_cnt = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl_cnt, o);
+    if (lane >= o) incl_cnt += v;
   }
+  if (lane == 31) warp_tot[warp] = incl_cnt;
+  __syncthreads();
+  uint32_t wbase = 0, block_total = 0;
+#pragma unroll
+  for (int w = 0; w < kEmitThreads / 32; ++w) {
+    const uint32_t t = warp_tot[w];
+    if (w < warp) wbase += t;
+    block_total += t;
+  }
+  // ---- block prefix: chained look-back, one warp, 32 predecessors per round
+  if (warp == 0) {
+    uint32_t* my = scan_status + bid;
+    // values saturate at 2^30 - 1 (> any admissible capacity), so an oversized frame still raises the overflow flag
+    if (lane == 0) st_status(my, (bid == 0 ? kStIncl : kStAgg) | min(block_total, kStVal));
+    uint32_t prev = 0;
+    if (bid > 0) {
+      for (int64_t b = (int64_t)bid - 1;; b -= 32) {
+        const int64_t src = b - lane;
+        uint32_t v = src >= 0 ? ld_status(scan_status + src) : kStIncl;  // before block 0: prefix 0
+        for (uint32_t spin = 0; (v >> 30) == 0; ++spin) {
+          if (spin > (1u << 24)) __trap();  // a predecessor never published: fail loudly instead of hanging
+          v = ld_status(scan_status + src);
+        }
+        const unsigned closed = __ballot_sync(0xffffffffu, (v >> 30) == 2);
+        const int first = closed ? __ffs(closed) - 1 : 31;  // nearest predecessor holding an inclusive prefix
+        unsigned long long part = lane <= first ? (unsigned long long)(v & kStVal) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        prev = (uint32_t)min(part + prev, (unsigned long long)kStVal);
+        if (closed) break;
+      }
+      if (lane == 0) st_status(my, kStIncl | (uint32_t)min((unsigned long long)prev + block_total, (unsigned long long)kStVal));
+    }
+    if (lane == 0) {
+      s_prefix = prev;
+      if (bid == gridDim.x - 1) {  // blocks are numbered in arrival order: the last ticket covers the last Gaussians
+        const unsigned long long total = (unsigned long long)prev + block_total;
+        counters[1] = total;
+        if ((int64_t)total > capacity) counters[2] = 1;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t off = s_prefix + wbase + incl_cnt - cnt;
+  const int64_t cap = capacity;
+
+  uint32_t gid = 0, rect = kRectLarge;
+  const bool active = cnt != 0;
+  if (active) gid = ids_sorted[k];
   uint64_t mask = 0ull;
   if (active) rect = rects[gid];
   const bool small = active && rect != kRectLarge;
@@ -855,9 +904,12 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
         // kk / ow for kk < 64, ow <= 64: (kk + 0.5) / ow is never within rounding distance of an integer
         const uint32_t row = (uint32_t)__float2int_rd(__fdividef((float)kk + 0.5f, (float)ow));
         const uint32_t tile = (((orect >> 13) & 0x1fffu) + row) * gx + (orect & 0x1fffu) + (kk - row * ow);
-        tile_keys[ooff + ordinal] = tile;
-        tile_vals[ooff + ordinal] = ogid;
-        tally(tile);
+        const uint32_t dst = ooff + ordinal;
+        if ((int64_t)dst < cap) {
+          tile_keys[dst] = tile;
+          tile_vals[dst] = ogid;
+          tally(tile);
+        }
       }
     }
   }
@@ -893,19 +945,21 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(int P, const uint32_t*
     const uint32_t sx0 = __shfl_sync(0xffffffffu, rc.x0, src), sy0 = __shfl_sync(0xffffffffu, rc.y0, src);
     const uint32_t sw = __shfl_sync(0xffffffffu, w, src), sarea = __shfl_sync(0xffffffffu, area, src);
     const uint32_t soff = __shfl_sync(0xffffffffu, off, src), sgid = __shfl_sync(0xffffffffu, gid, src);
-    uint32_t cnt = 0;
+    uint32_t done = 0;
     for (uint32_t base = 0; base < sarea; base += 32) {
       const uint32_t kk = base + lane;
       const uint32_t tx = sx0 + kk % sw, ty = sy0 + kk / sw;
       const bool keep = kk < sarea && (!stest || tile_can_contribute(spx, spy, sa, sb, sc, sna, snc, st, tx, ty));
       const unsigned votes = __ballot_sync(0xffffffffu, keep);
       if (keep) {
-        const uint32_t dst = soff + cnt + __popc(votes & lt_mask);
-        tile_keys[dst] = ty * gx + tx;
-        tile_vals[dst] = sgid;
-        tally(ty * gx + tx);
+        const uint32_t dst = soff + done + __popc(votes & lt_mask);
+        if ((int64_t)dst < cap) {
+          tile_keys[dst] = ty * gx + tx;
+          tile_vals[dst] = sgid;
+          tally(ty * gx + tx);
+        }
       }
-      cnt += __popc(votes);
+      done += __popc(votes);
     }
   }
   __syncthreads();
@@ -1212,7 +1266,7 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // two records per trip.  Thresholds are decided on exactly the same alpha / T values as in
 // render_warp_kernel; colours accumulate as fma(c, alpha*T, C) instead of fma(c*alpha, T, C)
 // (<= 1 ulp per term).
-constexpr int kDefaultRenderImpl = 3;        // 0 block, 1 warp, 2 compact, 3 compact with two pixels per lane (GSB_RENDER_IMPL overrides)
+constexpr int kDefaultRenderImpl = 4;        // 0 block, 1 warp, 2 compact, 3 compact with two pixels per lane (GSB_RENDER_IMPL overrides)
 constexpr int kSlotBytes = 48;               // A (16) | B (16) | green, blue (8) | pad (8)
 constexpr int kSlotsPerBuf = 33;             // 32 hits + sentinel
 // kPix = pixels per lane: 1 -> 8 warps per tile, each an 8x4 block; 2 -> 4 warps per tile, each an 8x8 block whose
@@ -1335,13 +1389,213 @@ __global__ void __launch_bounds__(kTilePixels / kPix, kPix == 1 ? 5 : 8)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Table variant of render_compact_kernel<true, 2> (default): same per-warp compacted hit list, but the blend loop is
+// cut from 29 to ~16 issue slots per (record, pixel) by moving everything that does not depend on the pixel out of it.
+// Measured on B200 (profiles/r02a_ubench_pipes.log): FFMA 1/clk, FFMA2/FMUL2/FADD2 0.5/clk, FSETP/FSEL/FMNMX 0.5/clk and
+// MUFU.EX2 0.125/clk per SM sub-partition -- the old loop (116 slots per 2 records x 2 pixels, 38 of them on the
+// half-rate ALU pipe) was bound by issue, then by the ALU pipe.  Here:
+//  * the exponent is evaluated in the log2 domain as  e = u'(x) + v(x)*dy(y) + w(y)  with
+//        u'(x) = -0.5 log2e a dx^2 + log2(opacity),  v(x) = -log2e b dx,  w(y) = -0.5 log2e c dy^2 ;
+//    the lane that compacts a record writes u', v for the warp block's 8 columns and dy, w for its 8 rows into the
+//    record's slot (once per record and warp), so a pixel pair costs one FFMA2 + one FADD2, and alpha = ex2(e)
+//    needs no opacity multiply;
+//  * both pixels of a lane (rows y and y+4) ride in the two halves of packed f32x2 instructions;
+//  * the three thresholds of forward.cu:336-353 are three FSETPs with two predicate outputs each; the colour / depth
+//    accumulation and the transmittance update are PREDICATED scalar FFMA/FMULs (FMA pipe) instead of FSELs (ALU pipe);
+//  * "done" lives in the sign of T: a saturated pixel keeps its transmittance with the sign bit set, every later
+//    test_T = T*(1-alpha) is negative, i.e. < 1e-4, so nothing is accumulated any more; |T| is written out.
+// The exponent's rounding differs from the reference's expression by a few ulp of its largest term (as any
+// re-association does); gated on the full-size parity tests against the reference binary (tests/test_gpu_pipeline.py).
+constexpr int kTabSlotBytes = 160;  // X table 8 x (u',v) | Y table 4 x (dy0,dy1,w0,w1) | (r,g,b,z) | (thr,0,0,0)
+constexpr int kTabSlots = 33;       // 32 hits + sentinel
+constexpr int kTabX = 0, kTabY = 64, kTabC = 128, kTabThr = 144;
+
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// One record against the lane's two pixels.  (u, v) = this lane's column entry, (dy0, dy1, w0, w1) = its row entry,
+// thr = log2(opacity) (e > thr <=> power > 0), TT = packed (T0, T1) with the sign bit as the "done" flag.
+// Written in PTX so that the thresholds are exactly three compares per pixel with chained predicates, the accumulation
+// and the transmittance update are predicated FMA-pipe instructions, and T stays in one aligned register pair.
+// NaNs fall through the tests like in the reference (leu / geu are true for unordered operands).
+__device__ __forceinline__ void blend_record_tab(float u, float v, float dy0, float dy1, float w0, float w1, float thr, float r,
+                                                 float g, float b, float z, unsigned long long& TT, float& C00, float& C10,
+                                                 float& C20, float& Dz0, float& C01, float& C11, float& C21, float& Dz1) {
+  asm volatile(
+      "{\n"
+      ".reg .b64 DY, WY, U2, V2, E, AL, OMA, TN, WW, M1, P1;\n"
+      ".reg .f32 e0, e1, x0, x1, a0, a1, tn0, tn1, ww0, ww1, o0, o1, t0, t1;\n"
+      ".reg .pred p1a, p2a, oka, sata, p1b, p2b, okb, satb;\n"
+      "mov.b64 DY, {%9, %10};\n"
+      "mov.b64 WY, {%11, %12};\n"
+      "mov.b64 U2, {%13, %13};\n"
+      "mov.b64 V2, {%14, %14};\n"
+      "fma.rn.f32x2 E, V2, DY, U2;\n"             // u'(x) + v(x) * dy(y)
+      "add.rn.f32x2 E, E, WY;\n"                  //   + w(y): log2-domain exponent incl. log2(opacity)
+      "mov.b64 {e0, e1}, E;\n"
+      "ex2.approx.ftz.f32 x0, e0;\n"
+      "ex2.approx.ftz.f32 x1, e1;\n"
+      "min.f32 a0, x0, 0f3F7D70A4;\n"             // forward.cu:341  alpha = min(0.99f, ...)
+      "min.f32 a1, x1, 0f3F7D70A4;\n"
+      "mov.b64 AL, {a0, a1};\n"
+      "mov.b64 M1, 0xBF800000BF800000;\n"
+      "mov.b64 P1, 0x3F8000003F800000;\n"
+      "fma.rn.f32x2 OMA, AL, M1, P1;\n"           // 1 - alpha (exactly rounded, like the reference's subtraction)
+      "mul.rn.f32x2 TN, %0, OMA;\n"               // test_T = T * (1 - alpha)
+      "mul.rn.f32x2 WW, AL, %0;\n"                // alpha * T
+      "mov.b64 {tn0, tn1}, TN;\n"
+      "mov.b64 {ww0, ww1}, WW;\n"
+      "mov.b64 {o0, o1}, OMA;\n"
+      "mov.b64 {t0, t1}, %0;\n"
+      "setp.leu.f32 p1a, e0, %15;\n"                    // forward.cu:336  if (power > 0.0f) continue;
+      "setp.leu.f32 p1b, e1, %15;\n"
+      "setp.geu.and.f32 p2a, a0, 0f3B808081, p1a;\n"    // forward.cu:344  if (alpha < 1.0f / 255.0f) continue;
+      "setp.geu.and.f32 p2b, a1, 0f3B808081, p1b;\n"
+      "setp.geu.and.f32 oka, tn0, 0f38D1B717, p2a;\n"   // forward.cu:347  if (test_T < 0.0001f) { done = true; continue; }
+      "setp.geu.and.f32 okb, tn1, 0f38D1B717, p2b;\n"
+      "setp.lt.and.f32 sata, tn0, 0f38D1B717, p2a;\n"
+      "setp.lt.and.f32 satb, tn1, 0f38D1B717, p2b;\n"
+      "@oka fma.rn.f32 %1, %16, ww0, %1;\n"
+      "@oka fma.rn.f32 %2, %17, ww0, %2;\n"
+      "@oka fma.rn.f32 %3, %18, ww0, %3;\n"
+      "@oka fma.rn.f32 %4, %19, ww0, %4;\n"
+      "@okb fma.rn.f32 %5, %16, ww1, %5;\n"
+      "@okb fma.rn.f32 %6, %17, ww1, %6;\n"
+      "@okb fma.rn.f32 %7, %18, ww1, %7;\n"
+      "@okb fma.rn.f32 %8, %19, ww1, %8;\n"
+      "@oka mul.rn.f32 t0, t0, o0;\n"             // T = test_T (same operands, same rounding)
+      "@okb mul.rn.f32 t1, t1, o1;\n"
+      "@sata or.b32 t0, t0, 0x80000000;\n"        // done: keep |T|, set the sign
+      "@satb or.b32 t1, t1, 0x80000000;\n"
+      "mov.b64 %0, {t0, t1};\n"
+      "}\n"
+      : "+l"(TT), "+f"(C00), "+f"(C10), "+f"(C20), "+f"(Dz0), "+f"(C01), "+f"(C11), "+f"(C21), "+f"(Dz1)
+      : "f"(dy0), "f"(dy1), "f"(w0), "f"(w1), "f"(u), "f"(v), "f"(thr), "f"(r), "f"(g), "f"(b), "f"(z));
+}
+
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
+__global__ void __launch_bounds__(kTilePixels / 2, 7)
+    render_table_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
+                        const float4* __restrict__ recA, const float4* __restrict__ recB, const float2* __restrict__ recC,
+                        const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
+                        float* __restrict__ out_T, int64_t capacity) {
+  constexpr int kWarps = 4;
+  __shared__ __align__(16) unsigned char slots[kWarps][kTabSlots * kTabSlotBytes];
+  const uint32_t tiles_x = (W + kTile - 1) / kTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t a0 = smem_u32(&slots[warp][0]);
+  const uint32_t blk_x = blockIdx.x * kTile + (warp & 1) * 8, blk_y = blockIdx.y * kTile + (warp >> 1) * 8;
+  const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
+  const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 7);
+  const uint32_t xoff = kTabX + (lane & 7) * 8, yoff = kTabY + (lane >> 3) * 16;
+  uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
+  if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);
+  const int total = range.y - range.x;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const bool inside0 = pix_x < (uint32_t)W && pix_y < (uint32_t)H, inside1 = pix_x < (uint32_t)W && pix_y + 4 < (uint32_t)H;
+  // the sign of T is the pixel's "done" flag
+  unsigned long long TT = pack_f32x2(inside0 ? 1.0f : -1.0f, inside1 ? 1.0f : -1.0f);
+  float C00 = 0.f, C10 = 0.f, C20 = 0.f, Dz0 = 0.f, C01 = 0.f, C11 = 0.f, C21 = 0.f, Dz1 = 0.f;
+
+  float4 cA = make_float4(0.f, 0.f, 0.f, 0.f), cB = cA, nA = cA, nB = cA;
+  float2 cC = make_float2(0.f, 0.f), nC = cC;
+  if (lane < total) {
+    const uint32_t g = point_list[range.x + lane];
+    cA = recA[g];
+    cB = recB[g];
+    cC = recC[g];
+  }
+  // per-lane bases of the column / row entries; `off` (byte offset of the record's slot) is warp-uniform
+  const uint32_t xbase = a0 + xoff, ybase = a0 + yoff;
+  auto blend = [&](uint32_t off) {
+    const float2 X = lds64(xbase + off);       // u', v of this lane's column
+    const float4 Y = lds128(ybase + off);      // dy, w of this lane's two rows
+    const float4 Q = lds128(a0 + kTabC + off);  // r, g, b, z
+    const float thr = lds32(a0 + kTabThr + off);
+    blend_record_tab(X.x, X.y, Y.x, Y.y, Y.z, Y.w, thr, Q.x, Q.y, Q.z, Q.w, TT, C00, C10, C20, Dz0, C01, C11, C21, Dz1);
+  };
+  for (int c0 = 0; c0 < total; c0 += 32) {
+    if (__all_sync(0xffffffffu, (TT & 0x8000000080000000ull) == 0x8000000080000000ull)) break;  // both pixels done
+    const int nxt = c0 + 32 + lane;
+    if (nxt < total) {  // next chunk's gathers fly while this one is tested and blended
+      const uint32_t g = point_list[range.x + nxt];
+      nA = recA[g];
+      nB = recB[g];
+      nC = recC[g];
+    }
+    bool hit = false;
+    if (c0 + lane < total) {
+      const Footprint fp = make_footprint(cB.x, cB.y, cB.z, 2.f * __logf(255.f * cA.w) + 1e-3f);
+      hit = rect_can_contribute(cA.x, cA.y, fp, bx0, by0, bx1, by1);
+    }
+    const unsigned votes = __ballot_sync(0xffffffffu, hit);
+    const int n = __popc(votes);
+    if (hit) {  // this lane's record goes to slot `rank`: per-column and per-row terms of the exponent, colour, depth
+      const uint32_t dst = a0 + __popc(votes & lt_mask) * kTabSlotBytes;
+      const float ap = -0.72134752044448170f * cB.x, bp = -1.4426950408889634f * cB.y, cp = -0.72134752044448170f * cB.z;
+      const float l2o = __log2f(cA.w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dx = cA.x - (bx0 + (float)i);
+        sts64(dst + kTabX + 8 * i, make_float2(fmaf(ap * dx, dx, l2o), bp * dx));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float dy0 = cA.y - (by0 + (float)j), dy1 = cA.y - (by0 + (float)(j + 4));
+        sts128(dst + kTabY + 16 * j, make_float4(dy0, dy1, cp * dy0 * dy0, cp * dy1 * dy1));
+      }
+      sts128(dst + kTabC, make_float4(cB.w, cC.x, cC.y, cA.z));
+      sts128(dst + kTabThr, make_float4(l2o, 0.f, 0.f, 0.f));
+    }
+    if (lane < kTabSlotBytes / 16) {  // sentinel after the last hit: u' = -1e30 -> alpha 0 -> skipped
+      const float big = lane < 4 ? -1.0e30f : 0.f;  // quads 0..3 = the X table: (u', v, u', v)
+      sts128(a0 + n * kTabSlotBytes + 16 * lane, make_float4(big, 0.f, big, 0.f));
+    }
+    __syncwarp();  // the list is visible to every lane of the warp
+    const uint32_t end = (uint32_t)n * kTabSlotBytes;
+    for (uint32_t off = 0; off < end; off += 2 * kTabSlotBytes) {
+      blend(off);
+      blend(off + kTabSlotBytes);
+    }
+    __syncwarp();  // every lane is done reading before the next chunk overwrites the slots
+    cA = nA;
+    cB = nB;
+    cC = nC;
+  }
+  const size_t plane = (size_t)H * W;
+  const float Tf0 = fabsf(__uint_as_float((uint32_t)TT)), Tf1 = fabsf(__uint_as_float((uint32_t)(TT >> 32)));
+  if (inside0) {
+    const size_t pid = (size_t)pix_y * W + pix_x;
+    out_color[pid] = C00 + Tf0 * bg[0];
+    out_color[plane + pid] = C10 + Tf0 * bg[1];
+    out_color[2 * plane + pid] = C20 + Tf0 * bg[2];
+    if (out_depth) out_depth[pid] = Dz0;
+    if (out_T) out_T[pid] = Tf0;
+  }
+  if (inside1) {
+    const size_t pid = (size_t)(pix_y + 4) * W + pix_x;
+    out_color[pid] = C01 + Tf1 * bg[0];
+    out_color[plane + pid] = C11 + Tf1 * bg[1];
+    out_color[2 * plane + pid] = C21 + Tf1 * bg[2];
+    if (out_depth) out_depth[pid] = Dz1;
+    if (out_T) out_T[pid] = Tf1;
+  }
+}
+
 __global__ void write_counts_kernel(const uint32_t* __restrict__ offsets, int P, const unsigned long long* counters,
                                     int64_t* out) {
   // offsets != NULL: validation path (instance total = last element of the per-Gaussian scan)
   out[0] = offsets ? (P > 0 ? (int64_t)offsets[P - 1] : 0) : (int64_t)counters[1];
   out[1] = (int64_t)counters[0];
   out[2] = (int64_t)counters[2];
-  out[3] = 0;
+  out[3] = (int64_t)counters[3];
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means,
@@ -1397,7 +1651,7 @@ struct Workspace {
   uint32_t* sorted_offsets;
   uint64_t* masks;
   uint32_t* rects;
-  uint32_t* block_sums;
+  uint32_t* scan_status;  // emit_scan_kernel: [0] ticket, [64..] per-block status words
   uint32_t* radix_scratch;
   uint64_t* keys_in;
   uint64_t* keys_out;
@@ -1430,7 +1684,7 @@ Workspace carve(void* base, int32_t P, int32_t W, int32_t H, int64_t R) {
   w.sorted_offsets = c.take<uint32_t>(Pn);
   w.masks = c.take<uint64_t>(Pn);
   w.rects = c.take<uint32_t>(Pn);
-  w.block_sums = c.take<uint32_t>((Pn + kScanBlock - 1) / kScanBlock + 1);
+  w.scan_status = c.take<uint32_t>((Pn + kEmitThreads - 1) / kEmitThreads + 64);
   w.radix_scratch = c.take<uint32_t>(radix_scratch_words(std::max(Pn, Rn)));
   w.keys_in = c.take<uint64_t>(Rn);
   w.keys_out = c.take<uint64_t>(Rn);
@@ -1490,8 +1744,32 @@ size_t gsb_raster_workspace_bytes(int32_t P, int32_t width, int32_t height, int6
   return carve(nullptr, P, width, height, max_instances).total;
 }
 
-int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+struct Frame {  // one eye's call, validated and carved
+  const GsbRasterArgs* a;
+  Workspace ws;
+  uint32_t gx, gy;
+  size_t ntiles;
+  int64_t cap;
+  bool dbg, use_cub;
+  int* radii;
+};
+
+static int render_frame_impl(const Frame& f, const uint32_t* point_list, cudaStream_t stream);
+
+// One event per device for ordering the right eye's stream behind the shared part of a pair (a stream wait captures the
+// event's state when it is enqueued, so the event can be re-recorded by the next pair).
+static cudaEvent_t pair_event() {
+  static std::mutex mu;
+  static cudaEvent_t events[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  cudaEvent_t& e = events[dev & 63];
+  if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
+
+static int validate_frame(const GsbRasterArgs* a, Frame& f) {
   if (!a) return fail(GSB_ERR_INVALID, "args is NULL");
   if (a->P < 0 || a->width <= 0 || a->height <= 0) return fail(GSB_ERR_INVALID, "bad P / image size");
   if (a->width > 8191 * kTile || a->height > 8191 * kTile)  // packed candidate rectangles hold 13-bit tile coordinates
@@ -1501,7 +1779,6 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   // DGR/diff_gaussian_rasterization/__init__.py:191-195
   if ((a->shs == nullptr) == (a->colors_precomp == nullptr))
     return fail(GSB_ERR_INVALID, "Please provide excatly one of either SHs or precomputed colors!");
-  const bool has_sr = a->scales != nullptr && a->rotations != nullptr;
   if (((a->scales == nullptr || a->rotations == nullptr) && a->cov3D_precomp == nullptr) ||
       ((a->scales != nullptr || a->rotations != nullptr) && a->cov3D_precomp != nullptr))
     return fail(GSB_ERR_INVALID,
@@ -1511,30 +1788,39 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     return fail(GSB_ERR_INVALID, "SH degree %d needs %d coefficients, tensor has %d (max 16)", a->sh_degree,
                 (a->sh_degree + 1) * (a->sh_degree + 1), a->sh_coeffs);
   if (!a->workspace) return fail(GSB_ERR_WORKSPACE, "workspace is NULL");
-  const int P = a->P, W = a->width, H = a->height;
-  const int64_t cap = a->max_instances;
-  Workspace ws = carve(a->workspace, P, W, H, cap);
-  if (ws.total > a->workspace_bytes)
-    return fail(GSB_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", a->workspace_bytes, ws.total);
-  const bool dbg = a->flags & GSB_RASTER_DEBUG_SYNC;
-  const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
-  const size_t npix = (size_t)W * H;
-  int rc;
+  if (a->max_instances >= (int64_t)kStVal)  // the emit pass's scan words hold 30-bit instance counts
+    return fail(GSB_ERR_INVALID, "max_instances must be below 2^30 - 1");
+  f.a = a;
+  f.cap = a->max_instances;
+  f.ws = carve(a->workspace, a->P, a->width, a->height, f.cap);
+  if (f.ws.total > a->workspace_bytes)
+    return fail(GSB_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", a->workspace_bytes, f.ws.total);
+  f.dbg = (a->flags & GSB_RASTER_DEBUG_SYNC) != 0;
+  f.use_cub = (a->flags & GSB_RASTER_CUB_SORT) != 0;
+  f.gx = (a->width + kTile - 1) / kTile;
+  f.gy = (a->height + kTile - 1) / kTile;
+  f.ntiles = (size_t)f.gx * f.gy;
+  f.radii = a->radii ? a->radii : f.ws.radii;
+  return GSB_OK;
+}
 
-  if (P == 0) {  // rasterize_points.cu:77: outputs stay zero-filled
-    GSB_CUDA_OK(cudaMemsetAsync(a->out_color, 0, 3 * npix * sizeof(float), stream));
-    if (a->out_depth) GSB_CUDA_OK(cudaMemsetAsync(a->out_depth, 0, npix * sizeof(float), stream));
-    if (a->out_final_T) GSB_CUDA_OK(cudaMemsetAsync(a->out_final_T, 0, npix * sizeof(float), stream));
-    if (a->num_rendered) GSB_CUDA_OK(cudaMemsetAsync(a->num_rendered, 0, 4 * sizeof(int64_t), stream));
-    return GSB_OK;
-  }
+static int empty_frame(const GsbRasterArgs* a, cudaStream_t stream) {  // rasterize_points.cu:77: outputs stay zero-filled
+  const size_t npix = (size_t)a->width * a->height;
+  GSB_CUDA_OK(cudaMemsetAsync(a->out_color, 0, 3 * npix * sizeof(float), stream));
+  if (a->out_depth) GSB_CUDA_OK(cudaMemsetAsync(a->out_depth, 0, npix * sizeof(float), stream));
+  if (a->out_final_T) GSB_CUDA_OK(cudaMemsetAsync(a->out_final_T, 0, npix * sizeof(float), stream));
+  if (a->num_rendered) GSB_CUDA_OK(cudaMemsetAsync(a->num_rendered, 0, 4 * sizeof(int64_t), stream));
+  return GSB_OK;
+}
 
-  PreParams pp{};
-  pp.P = P;
+static void fill_common(const Frame& f, PreParams& pp) {
+  const GsbRasterArgs* a = f.a;
+  const bool has_sr = a->scales != nullptr && a->rotations != nullptr;
+  pp.P = a->P;
   pp.D = a->sh_degree;
   pp.M = a->sh_coeffs;
-  pp.W = W;
-  pp.H = H;
+  pp.W = a->width;
+  pp.H = a->height;
   pp.means3D = a->means3D;
   pp.shs = a->shs;
   pp.colors = a->colors_precomp;
@@ -1543,15 +1829,8 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   pp.rotations = a->rotations;
   pp.cov3D = a->cov3D_precomp;
   pp.scale_modifier = a->scale_modifier;
-  pp.view = a->viewmatrix;
-  pp.proj = a->projmatrix;
-  pp.campos = a->cam_pos;
-  pp.tan_fovx = a->tan_fovx;
-  pp.tan_fovy = a->tan_fovy;
-  pp.focal_y = H / (2.0f * a->tan_fovy);  // rasterizer_impl.cu:222-223
-  pp.focal_x = W / (2.0f * a->tan_fovx);
-  pp.gx = gx;
-  pp.gy = gy;
+  pp.gx = f.gx;
+  pp.gy = f.gy;
   pp.flags = a->flags;
   pp.use_tma = !(a->flags & GSB_RASTER_NO_TMA) && aligned16(a->means3D) && aligned16(a->opacities) &&
                (!has_sr || (aligned16(a->scales) && aligned16(a->rotations))) && (!a->shs || aligned16(a->shs));
@@ -1563,122 +1842,95 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
     return kDefaultShMode;
   }();
   pp.sh_mode = ((a->flags >> 12) & 3u) ? (int)((a->flags >> 12) & 3u) - 1 : sh_mode_default;
-  pp.recA = ws.recA;
-  pp.recB = ws.recB;
-  pp.recC = ws.recC;
-  pp.tiles = ws.tiles;
-  pp.radii = a->radii ? a->radii : ws.radii;
-  pp.ref_count = ws.counters;
+}
 
-  const bool use_cub = (a->flags & GSB_RASTER_CUB_SORT) != 0;
-  const size_t ntiles = (size_t)gx * gy;
-  pp.depth_keys = use_cub ? nullptr : ws.depth_a;
-  pp.ids = use_cub ? nullptr : ws.ids_a;
-  pp.masks = ws.masks;
-  pp.rects = ws.rects;
-  GSB_CUDA_OK(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream));
-  const int pre_blocks = (P + kPreThreads - 1) / kPreThreads;
+static void fill_eye(const Frame& f, PreEye& e) {
+  const GsbRasterArgs* a = f.a;
+  e.view = a->viewmatrix;
+  e.proj = a->projmatrix;
+  e.campos = a->cam_pos;
+  e.tan_fovx = a->tan_fovx;
+  e.tan_fovy = a->tan_fovy;
+  e.focal_y = a->height / (2.0f * a->tan_fovy);  // rasterizer_impl.cu:222-223
+  e.focal_x = a->width / (2.0f * a->tan_fovx);
+  e.recA = f.ws.recA;
+  e.recB = f.ws.recB;
+  e.recC = f.ws.recC;
+  e.tiles = f.ws.tiles;
+  e.radii = f.radii;
+  e.counters = f.ws.counters;
+  e.masks = f.ws.masks;
+  e.rects = f.ws.rects;
+  e.depth_keys = f.ws.depth_a;
+}
+
+// Stable sort of the P (depth bits, Gaussian index) pairs in `f`'s buffers; the last pass also delivers tiles-per-Gaussian in
+// depth order for `f` (into f.ws.offsets) and, for a stereo pair, for `g` (into g->ws.offsets).
+static int depth_sort(const Frame& f, const Frame* g, cudaStream_t stream, const uint32_t** ids_sorted) {
+  uint64_t nl = 0;
+  const int P = f.a->P;
   {
-    StageTimer tm(kStPreprocess, stream);
-    preprocess_kernel<<<pre_blocks, kPreThreads, 0, stream>>>(pp);
+    StageTimer tm(kStScan, stream);
+    const int which = radix_sort_pairs(f.ws.depth_a, f.ws.ids_a, f.ws.depth_b, f.ws.ids_b, (uint32_t)P, nullptr, 0, (size_t)P, 32,
+                                       f.ws.radix_scratch, nullptr, stream, &nl, /*histogram_ready=*/false, f.ws.tiles, f.ws.offsets,
+                                       g ? g->ws.tiles : nullptr, g ? g->ws.offsets : nullptr, /*identity_payload=*/true);
+    *ids_sorted = which ? f.ws.ids_b : f.ws.ids_a;
   }
-  count_launch();
-  if ((rc = check_launch("preprocess_kernel", stream, dbg))) return rc;
+  count_launch(nl);
+  return check_launch("depth sort", stream, f.dbg);
+}
 
-  const uint32_t* point_list = nullptr;
-  if (use_cub) {
-    // ---- validation path: the reference's own pipeline shape (P-sized scan, emit in Gaussian order,
-    //      global radix sort of (tile | depth) keys, boundary detection), incl. its host round trip
-    {
-      StageTimer tm(kStScan, stream);
-      GSB_CUDA_OK(cub::DeviceScan::InclusiveSum(ws.scan_temp, ws.scan_temp_bytes, ws.tiles, ws.offsets, P, stream));
-    }
-    if (a->num_rendered) {
-      write_counts_kernel<<<1, 1, 0, stream>>>(ws.offsets, P, ws.counters, a->num_rendered);
-      count_launch();
-    }
-    uint32_t R32 = 0;
-    GSB_CUDA_OK(cudaMemcpyAsync(&R32, ws.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    GSB_CUDA_OK(cudaStreamSynchronize(stream));
-    const int64_t R = (int64_t)R32;
-    g_required_instances = R;
-    if (R > cap)
-      return fail(GSB_ERR_WORKSPACE, "frame needs %lld instances, workspace sized for %lld", (long long)R, (long long)cap);
-    if (R > 0) {
-      {
-        StageTimer tm(kStEmit, stream);
-        emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ws.recA, ws.recB, ws.tiles, ws.offsets, pp.radii, gx, gy,
-                                                                   a->flags, cap, ws.keys_in, ws.vals_in);
-      }
-      count_launch();
-      if ((rc = check_launch("emit_instances_kernel", stream, dbg))) return rc;
-      const int bit = (int)higher_msb(gx * gy);
-      {
-        StageTimer tm(kStSort, stream);
-        GSB_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.sort_temp, ws.sort_temp_bytes, ws.keys_in, ws.keys_out, ws.vals_in,
-                                                    ws.vals_out, R, 0, 32 + bit, stream));
-      }
-      if ((rc = check_launch("radix sort", stream, dbg))) return rc;
-    }
-    GSB_CUDA_OK(cudaMemsetAsync(ws.ranges, 0, ntiles * sizeof(uint2), stream));
-    if (R > 0) {
-      {
-        StageTimer tm(kStRanges, stream);
-        tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, ws.keys_out, ws.ranges);
-      }
-      count_launch();
-      if ((rc = check_launch("tile_ranges_kernel", stream, dbg))) return rc;
-    }
-    point_list = ws.vals_out;
-  } else {
-    // ---- default pipeline: depth-sort P, emit in that order, stable split by tile; nothing waits
-    uint32_t* rs = ws.radix_scratch;
-    uint64_t nl = 0;
-    const uint32_t* ids_sorted;
-    {
-      StageTimer tm(kStScan, stream);
-      // the last pass also delivers tiles-per-Gaussian in sorted order (ws.offsets is free on this path), so the
-      // scan and the emit pass read it contiguously instead of gathering tiles[ids_sorted[k]]
-      uint32_t* tiles_sorted = ws.offsets;
-      const int which = radix_sort_pairs(ws.depth_a, ws.ids_a, ws.depth_b, ws.ids_b, (uint32_t)P, nullptr, 0, (size_t)P, 32, rs,
-                                         nullptr, stream, &nl, /*histogram_ready=*/false, ws.tiles, tiles_sorted);
-      ids_sorted = which ? ws.ids_b : ws.ids_a;
-      const int sblocks = (P + kScanBlock - 1) / kScanBlock;
-      sorted_block_sums_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, tiles_sorted, ws.block_sums);
-      sorted_offsets_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, tiles_sorted, ws.block_sums, ws.sorted_offsets, ws.counters,
-                                                                 cap);
-      nl += 2;
-    }
-    if ((rc = check_launch("depth sort / offsets", stream, dbg))) return rc;
-    // tile-id sort buffers alias the 64-bit key arrays of the validation path
-    uint32_t* tk_a = reinterpret_cast<uint32_t*>(ws.keys_in);
-    uint32_t* tv_a = tk_a + cap;
-    uint32_t* tk_b = reinterpret_cast<uint32_t*>(ws.keys_out);
-    uint32_t* tv_b = tk_b + cap;
-    const int tile_bits = (int)higher_msb((uint32_t)ntiles);
-    {
-      StageTimer tm(kStEmit, stream);
-      radix_prepare(rs, (size_t)cap, tile_bits, stream);
-      emit_sorted_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ids_sorted, ws.sorted_offsets, ws.recA, ws.recB, ws.offsets,
-                                                              pp.radii, ws.masks, ws.rects, gx, gy, a->flags, ws.counters, tk_a, tv_a,
-                                                              radix_ghist(rs), (tile_bits + 7) / 8, radix_digit_bits(tile_bits));
-      init_ranges_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream>>>(ws.ranges, (uint32_t)ntiles);
-      nl += 2;
-    }
-    if ((rc = check_launch("emit_sorted_kernel", stream, dbg))) return rc;
-    {
-      StageTimer tm(kStSort, stream);
-      const int which = radix_sort_pairs(tk_a, tv_a, tk_b, tv_b, 0u, ws.counters, cap, (size_t)cap, tile_bits, rs, ws.ranges,
-                                         stream, &nl, /*histogram_ready=*/true);
-      point_list = which ? tv_b : tv_a;
-    }
-    count_launch(nl);
-    if ((rc = check_launch("tile sort", stream, dbg))) return rc;
-    if (a->num_rendered) {
-      write_counts_kernel<<<1, 1, 0, stream>>>(nullptr, P, ws.counters, a->num_rendered);
-      count_launch();
-    }
+// emit (+ scan) -> stable tile split -> blend, for one eye whose Gaussians are already in depth order
+static int bin_and_render(const Frame& f, const uint32_t* ids_sorted, cudaStream_t stream) {
+  const GsbRasterArgs* a = f.a;
+  const Workspace& ws = f.ws;
+  const int P = a->P;
+  const int64_t cap = f.cap;
+  const uint32_t gx = f.gx, gy = f.gy;
+  const size_t ntiles = f.ntiles;
+  uint32_t* rs = ws.radix_scratch;
+  uint64_t nl = 0;
+  int rc;
+  // tile-id sort buffers alias the 64-bit key arrays of the validation path
+  uint32_t* tk_a = reinterpret_cast<uint32_t*>(ws.keys_in);
+  uint32_t* tv_a = tk_a + cap;
+  uint32_t* tk_b = reinterpret_cast<uint32_t*>(ws.keys_out);
+  uint32_t* tv_b = tk_b + cap;
+  const int tile_bits = (int)higher_msb((uint32_t)ntiles);
+  const uint32_t* point_list;
+  {
+    StageTimer tm(kStEmit, stream);
+    radix_prepare(rs, (size_t)cap, tile_bits, stream);
+    const int eblocks = (P + kEmitThreads - 1) / kEmitThreads;
+    GSB_CUDA_OK(cudaMemsetAsync(ws.scan_status, 0, ((size_t)eblocks + 64) * sizeof(uint32_t), stream));
+    emit_scan_kernel<<<eblocks, kEmitThreads, 0, stream>>>(P, ids_sorted, ws.offsets, ws.recA, ws.recB, f.radii, ws.masks, ws.rects, gx,
+                                                           gy, a->flags, cap, ws.counters, ws.scan_status + 64, ws.scan_status, tk_a,
+                                                           tv_a, radix_ghist(rs), (tile_bits + 7) / 8, radix_digit_bits(tile_bits));
+    init_ranges_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream>>>(ws.ranges, (uint32_t)ntiles);
+    nl += 2;
   }
+  if ((rc = check_launch("emit_scan_kernel", stream, f.dbg))) return rc;
+  {
+    StageTimer tm(kStSort, stream);
+    const int which = radix_sort_pairs(tk_a, tv_a, tk_b, tv_b, 0u, ws.counters, cap, (size_t)cap, tile_bits, rs, ws.ranges, stream, &nl,
+                                       /*histogram_ready=*/true);
+    point_list = which ? tv_b : tv_a;
+  }
+  count_launch(nl);
+  if ((rc = check_launch("tile sort", stream, f.dbg))) return rc;
+  if (a->num_rendered) {
+    write_counts_kernel<<<1, 1, 0, stream>>>(nullptr, P, ws.counters, a->num_rendered);
+    count_launch();
+  }
+  return render_frame_impl(f, point_list, stream);
+}
+
+static int render_frame_impl(const Frame& f, const uint32_t* point_list, cudaStream_t stream) {
+  const GsbRasterArgs* a = f.a;
+  const Workspace& ws = f.ws;
+  const int W = a->width, H = a->height;
+  const int64_t cap = f.cap;
+  const uint32_t gx = f.gx, gy = f.gy;
   {
     StageTimer tm(kStRender, stream);
     static const int render_impl = [] {
@@ -1688,6 +1940,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
       if (e && e[0] == 'b') return 0;
       if (e && e[0] == 'c') return 2;
       if (e && e[0] == 'd') return 3;  // "dual": compact, two pixels per lane
+      if (e && e[0] == 't') return 4;  // "table": dual + per-column / per-row exponent tables, packed f32x2, predicated blend
       if (e && e[0] == 'w') return 1;
       return kDefaultRenderImpl;
     }();
@@ -1697,7 +1950,9 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   __VA_ARGS__<<<dim3(gx, gy), THREADS, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, \
                                                     a->out_color, a->out_depth, a->out_final_T, cap)
 #define GSB_LAUNCH_RENDER(KERNEL) GSB_LAUNCH_RENDER_T(kTilePixels, KERNEL)
-    if (impl == 3) {
+    if (impl == 4 && fast) {
+      GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_table_kernel);
+    } else if (impl == 3 || impl == 4) {  // the table kernel only exists for the ex2 blend: full-precision expf -> dual
       if (fast)
         GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<true, 2>);
       else
@@ -1722,20 +1977,158 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
 #undef GSB_LAUNCH_RENDER_T
   }
   count_launch();
-  if ((rc = check_launch("render_kernel", stream, dbg))) return rc;
+  return check_launch("render_kernel", stream, f.dbg);
+}
 
-  if (!use_cub && !(a->flags & GSB_RASTER_ASYNC)) {
-    // synchronous contract: report an undersized workspace now (one wait at the END of the frame;
-    // GSB_RASTER_ASYNC callers read num_rendered[2] themselves after their own synchronisation)
-    unsigned long long host_counters[4] = {0, 0, 0, 0};
-    GSB_CUDA_OK(cudaMemcpyAsync(host_counters, ws.counters, sizeof(host_counters), cudaMemcpyDeviceToHost, stream));
-    GSB_CUDA_OK(cudaStreamSynchronize(stream));
-    g_required_instances = (int64_t)host_counters[1];
-    if (host_counters[2])
-      return fail(GSB_ERR_WORKSPACE, "frame needs %lld instances, workspace sized for %lld", (long long)host_counters[1],
-                  (long long)cap);
-  }
+// synchronous contract: report an undersized workspace now (one wait at the END of the frame;
+// GSB_RASTER_ASYNC callers read num_rendered[2] themselves after their own synchronisation)
+static int finish_sync(const Frame& f, cudaStream_t stream) {
+  if (f.use_cub || (f.a->flags & GSB_RASTER_ASYNC)) return GSB_OK;
+  unsigned long long host_counters[4] = {0, 0, 0, 0};
+  GSB_CUDA_OK(cudaMemcpyAsync(host_counters, f.ws.counters, sizeof(host_counters), cudaMemcpyDeviceToHost, stream));
+  GSB_CUDA_OK(cudaStreamSynchronize(stream));
+  g_required_instances = (int64_t)host_counters[1];
+  if (host_counters[2])
+    return fail(GSB_ERR_WORKSPACE, "frame needs %lld instances, workspace sized for %lld", (long long)host_counters[1],
+                (long long)f.cap);
   return GSB_OK;
+}
+
+// the reference's own pipeline shape (P-sized scan, emit in Gaussian order, global radix sort of (tile | depth) keys,
+// boundary detection), incl. its host round trip -- validation only
+static int cub_path(const Frame& f, cudaStream_t stream) {
+  const GsbRasterArgs* a = f.a;
+  const Workspace& ws = f.ws;
+  const int P = a->P;
+  const int64_t cap = f.cap;
+  int rc;
+  {
+    StageTimer tm(kStScan, stream);
+    size_t temp_bytes = ws.scan_temp_bytes;
+    GSB_CUDA_OK(cub::DeviceScan::InclusiveSum(ws.scan_temp, temp_bytes, ws.tiles, ws.offsets, P, stream));
+  }
+  if (a->num_rendered) {
+    write_counts_kernel<<<1, 1, 0, stream>>>(ws.offsets, P, ws.counters, a->num_rendered);
+    count_launch();
+  }
+  uint32_t R32 = 0;
+  GSB_CUDA_OK(cudaMemcpyAsync(&R32, ws.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  GSB_CUDA_OK(cudaStreamSynchronize(stream));
+  const int64_t R = (int64_t)R32;
+  g_required_instances = R;
+  if (R > cap)
+    return fail(GSB_ERR_WORKSPACE, "frame needs %lld instances, workspace sized for %lld", (long long)R, (long long)cap);
+  if (R > 0) {
+    {
+      StageTimer tm(kStEmit, stream);
+      emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, ws.recA, ws.recB, ws.tiles, ws.offsets, f.radii, f.gx, f.gy, a->flags,
+                                                                 cap, ws.keys_in, ws.vals_in);
+    }
+    count_launch();
+    if ((rc = check_launch("emit_instances_kernel", stream, f.dbg))) return rc;
+    const int bit = (int)higher_msb(f.gx * f.gy);
+    {
+      StageTimer tm(kStSort, stream);
+      size_t temp_bytes = ws.sort_temp_bytes;
+      GSB_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.sort_temp, temp_bytes, ws.keys_in, ws.keys_out, ws.vals_in, ws.vals_out, R, 0,
+                                                  32 + bit, stream));
+    }
+    if ((rc = check_launch("radix sort", stream, f.dbg))) return rc;
+  }
+  GSB_CUDA_OK(cudaMemsetAsync(ws.ranges, 0, f.ntiles * sizeof(uint2), stream));
+  if (R > 0) {
+    {
+      StageTimer tm(kStRanges, stream);
+      tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, ws.keys_out, ws.ranges);
+    }
+    count_launch();
+    if ((rc = check_launch("tile_ranges_kernel", stream, f.dbg))) return rc;
+  }
+  return render_frame_impl(f, ws.vals_out, stream);
+}
+
+int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  Frame f{};
+  int rc;
+  if ((rc = validate_frame(a, f))) return rc;
+  if (a->P == 0) return empty_frame(a, stream);
+  PreParams pp{};
+  fill_common(f, pp);
+  fill_eye(f, pp.eye[0]);
+  pp.eye[1] = pp.eye[0];
+  pp.binned = f.use_cub ? 0 : 1;
+  GSB_CUDA_OK(cudaMemsetAsync(f.ws.counters, 0, 8 * sizeof(unsigned long long), stream));
+  const int pre_blocks = (a->P + kPreThreads - 1) / kPreThreads;
+  {
+    StageTimer tm(kStPreprocess, stream);
+    preprocess_kernel<1><<<pre_blocks, kPreThreads, 0, stream>>>(pp);
+  }
+  count_launch();
+  if ((rc = check_launch("preprocess_kernel", stream, f.dbg))) return rc;
+  if (f.use_cub) return cub_path(f, stream);
+  // ---- default pipeline: depth-sort P, emit in that order, stable split by tile; nothing waits
+  const uint32_t* ids_sorted = nullptr;
+  if ((rc = depth_sort(f, nullptr, stream, &ids_sorted))) return rc;
+  if ((rc = bin_and_render(f, ids_sorted, stream))) return rc;
+  return finish_sync(f, stream);
+}
+
+int gsb_raster_forward_pair(const GsbRasterArgs* left, const GsbRasterArgs* right, void* stream_left_v, void* stream_right_v) {
+  cudaStream_t sl = static_cast<cudaStream_t>(stream_left_v);
+  cudaStream_t sr = stream_right_v ? static_cast<cudaStream_t>(stream_right_v) : sl;
+  Frame fl{}, fr{};
+  int rc;
+  if ((rc = validate_frame(left, fl))) return rc;
+  if ((rc = validate_frame(right, fr))) return rc;
+  if (left->P != right->P || left->means3D != right->means3D || left->shs != right->shs ||
+      left->colors_precomp != right->colors_precomp || left->opacities != right->opacities || left->scales != right->scales ||
+      left->rotations != right->rotations || left->cov3D_precomp != right->cov3D_precomp ||
+      left->scale_modifier != right->scale_modifier || left->sh_degree != right->sh_degree || left->sh_coeffs != right->sh_coeffs ||
+      left->width != right->width || left->height != right->height)
+    return fail(GSB_ERR_INVALID, "forward_pair: both eyes must share the Gaussian tensors, SH settings and the image size");
+  if (fl.use_cub || fr.use_cub) return fail(GSB_ERR_INVALID, "forward_pair: GSB_RASTER_CUB_SORT is a single-view validation path");
+  if (left->workspace == right->workspace) return fail(GSB_ERR_INVALID, "forward_pair: each eye needs its own workspace");
+  if (left->P == 0) {
+    if ((rc = empty_frame(left, sl))) return rc;
+    return empty_frame(right, sr);
+  }
+  PreParams pp{};
+  fill_common(fl, pp);
+  pp.flags = left->flags;
+  fill_eye(fl, pp.eye[0]);
+  fill_eye(fr, pp.eye[1]);
+  pp.binned = 1;
+  const bool shared = (left->flags & GSB_RASTER_PAIR_SHARED_DEPTH) != 0;
+  pp.shared_depth = shared ? 1 : 0;
+  GSB_CUDA_OK(cudaMemsetAsync(fl.ws.counters, 0, 8 * sizeof(unsigned long long), sl));
+  GSB_CUDA_OK(cudaMemsetAsync(fr.ws.counters, 0, 8 * sizeof(unsigned long long), sl));
+  const int pre_blocks = (left->P + kPreThreads - 1) / kPreThreads;
+  {
+    StageTimer tm(kStPreprocess, sl);
+    preprocess_kernel<2><<<pre_blocks, kPreThreads, 0, sl>>>(pp);
+  }
+  count_launch();
+  if ((rc = check_launch("preprocess_kernel<2>", sl, fl.dbg))) return rc;
+  const uint32_t* ids_l = nullptr;
+  const uint32_t* ids_r = nullptr;
+  if (shared) {  // one depth order for both eyes
+    if ((rc = depth_sort(fl, &fr, sl, &ids_l))) return rc;
+    ids_r = ids_l;
+  }
+  if (sr != sl) {  // the right eye continues on its own stream once the shared part (preprocess [+ depth sort]) is enqueued
+    cudaEvent_t ev = pair_event();
+    GSB_CUDA_OK(cudaEventRecord(ev, sl));
+    GSB_CUDA_OK(cudaStreamWaitEvent(sr, ev, 0));
+  }
+  if (!shared) {
+    if ((rc = depth_sort(fl, nullptr, sl, &ids_l))) return rc;
+    if ((rc = depth_sort(fr, nullptr, sr, &ids_r))) return rc;
+  }
+  if ((rc = bin_and_render(fl, ids_l, sl))) return rc;
+  if ((rc = bin_and_render(fr, ids_r, sr))) return rc;
+  if ((rc = finish_sync(fl, sl))) return rc;
+  return finish_sync(fr, sr);
 }
 
 int gsb_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -1,15 +1,18 @@
-// TSDF integration for sm_100a: a bounded, brick-addressed window of Open3D's
-// ScalableTSDFVolume lattice (what gs2mesh_utils/tsdf_utils.py:53-56,107 drives).
+// TSDF integration for sm_100a: Open3D's ScalableTSDFVolume (what gs2mesh_utils/tsdf_utils.py:53-56,107 drives) as an
+// UNBOUNDED brick store -- a pool of 16^3-voxel bricks addressed through a device hash table keyed by the integer lattice
+// index of the brick, allocated on first touch exactly like Open3D's unordered_map<Vector3i, VolumeUnit>.
 //
 // The reference integrates through Open3D 0.17.0 (CPU): per frame it back-projects every
 // 4th pixel, opens all 16^3 "volume units" within +-sdf_trunc of those points and runs
 // UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier on each unit once
-// (SURVEY.md rows T1/T2).  Here the same two steps are two kernels over a dense brick store:
+// (SURVEY.md rows T1/T2).  Here the same two steps are two kernels:
 //
 //   mark_bricks   one thread per sampled pixel; fp64 back-projection (Open3D builds the point
-//                 cloud in double), brick box of the point +- trunc, de-duplication with a
-//                 per-brick frame stamp (atomicExch) and an append-only work list.
-//   integrate     persistent CTAs pull bricks from the list.  A brick is 32 KB of contiguous
+//                 cloud in double), brick box of the point +- trunc, find-or-insert of every brick of the box in the
+//                 hash (a new key takes the next pool slot), de-duplication with a per-entry frame stamp (atomicExch)
+//                 and an append-only work list of hash entries.  Nothing waits: an entry's pool slot is only read by the
+//                 next kernel.
+//   integrate     persistent CTAs pull entries from the list.  A brick is 32 KB of contiguous
 //                 (tsdf, weight) pairs: thread t owns voxel pairs (2 consecutive z) and moves
 //                 them with 16-byte loads/stores, 8 independent loads in flight per thread.
 //                 Projection, truncated distance and the running weighted mean are fused; the
@@ -23,17 +26,59 @@
 namespace gsb {
 namespace {
 
+// counters (uint32[8]): [0] entries queued this frame  [1] bricks dropped this frame (pool full / index out of range)
+//                       [4] pool slots in use (persistent)  [5] bricks dropped since creation (persistent)
+constexpr int kCntQueued = 0, kCntDropped = 1, kCntPool = 4, kCntDroppedTotal = 5;
+
+struct HashView {
+  unsigned long long* keys;
+  uint32_t* vals;
+  uint32_t* stamp;
+  int32_t* index;  // [pool][4]
+  uint32_t mask, pool;
+};
+
+// position of brick (bx,by,bz) in the table, inserting it (and giving it the next pool slot) if absent; kSlotNone if the
+// brick cannot be stored.  The pool slot of a fresh key is written by the inserting thread with a plain store: readers of
+// hash_vals are always a later kernel.
+__device__ __forceinline__ uint32_t brick_find_or_insert(const HashView& hv, uint32_t* __restrict__ counters, int bx, int by,
+                                                         int bz) {
+  if (!brick_key_ok(bx, by, bz)) return kSlotNone;
+  const unsigned long long key = brick_key(bx, by, bz);
+  uint32_t h = brick_hash(key, hv.mask);
+  for (uint32_t probe = 0; probe <= hv.mask; ++probe, h = (h + 1) & hv.mask) {
+    unsigned long long k = hv.keys[h];
+    if (k == kHashEmpty) {
+      // pool exhausted: do not grow the table any further (racy by a few entries at most, bounded by the probe limit)
+      if (*(volatile uint32_t*)&counters[kCntPool] >= hv.pool) return kSlotNone;
+      k = atomicCAS(&hv.keys[h], kHashEmpty, key);
+      if (k == kHashEmpty) {  // inserted: OpenVolumeUnit
+        const uint32_t slot = atomicAdd(&counters[kCntPool], 1u);
+        if (slot < hv.pool) {
+          hv.vals[h] = slot;
+          reinterpret_cast<int4*>(hv.index)[slot] = make_int4(bx, by, bz, 0);
+        } else {
+          hv.vals[h] = kSlotNone;
+          atomicSub(&counters[kCntPool], 1u);
+        }
+        return h;
+      }
+    }
+    if (k == key) return h;
+  }
+  return kSlotNone;
+}
+
 struct MarkParams {
   int W, H, nsx, nsy;
   double fx, fy, cx, cy;
   double pose[12];  // rows 0..2 of extrinsic^-1 (camera -> world)
   double trunc, unit_length;
-  int b0[3], nb[3];
 };
 
-__global__ void __launch_bounds__(256) mark_bricks_kernel(const MarkParams m, const float* __restrict__ depth,
-                                                          uint32_t* __restrict__ stamp, uint32_t* __restrict__ list,
-                                                          uint32_t* __restrict__ counters, uint32_t frame) {
+__global__ void __launch_bounds__(256) mark_bricks_kernel(const MarkParams m, const HashView hv, const float* __restrict__ depth,
+                                                          uint32_t* __restrict__ list, uint32_t* __restrict__ counters,
+                                                          uint32_t frame) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= m.nsx * m.nsy) return;
   const int i = (s / m.nsx) * 4, j = (s % m.nsx) * 4;  // depth_sampling_stride = 4
@@ -55,14 +100,13 @@ __global__ void __launch_bounds__(256) mark_bricks_kernel(const MarkParams m, co
   for (int bx = lo[0]; bx <= hi[0]; ++bx)
     for (int by = lo[1]; by <= hi[1]; ++by)
       for (int bz = lo[2]; bz <= hi[2]; ++bz) {
-        const int rx = bx - m.b0[0], ry = by - m.b0[1], rz = bz - m.b0[2];
-        if (rx < 0 || ry < 0 || rz < 0 || rx >= m.nb[0] || ry >= m.nb[1] || rz >= m.nb[2]) {
-          atomicAdd(&counters[1], 1u);  // point needs a brick outside the window (diagnostic)
+        const uint32_t h = brick_find_or_insert(hv, counters, bx, by, bz);
+        if (h == kSlotNone) {
+          atomicAdd(&counters[kCntDropped], 1u);  // reported by gsb_tsdf_last_stats; the stage class raises on it
           continue;
         }
-        const uint32_t b = ((uint32_t)rx * m.nb[1] + ry) * m.nb[2] + rz;
-        if (stamp[b] == frame) continue;
-        if (atomicExch(&stamp[b], frame) != frame) list[atomicAdd(&counters[0], 1u)] = b;
+        if (hv.stamp[h] == frame) continue;
+        if (atomicExch(&hv.stamp[h], frame) != frame) list[atomicAdd(&counters[kCntQueued], 1u)] = h;
       }
 }
 
@@ -73,7 +117,6 @@ struct FrameParams {
   float sx, sy, sz;  // E(:,2) * voxel_length
   float safe_w, safe_h;
   int W, H;
-  int b0[3], nb[3];
   double unit_length;
 };
 
@@ -143,19 +186,27 @@ __global__ void __launch_bounds__(kIntThreads, kMinBlocks) integrate_kernel(cons
                                                                   const uint8_t* __restrict__ rgb, float4* __restrict__ tw,
                                                                   float4* __restrict__ color,
                                                                   const uint32_t* __restrict__ list,
-                                                                  const uint32_t* __restrict__ counters) {
-  const uint32_t n = counters[0];
+                                                                  uint32_t* __restrict__ counters,
+                                                                  const unsigned long long* __restrict__ hash_keys,
+                                                                  const uint32_t* __restrict__ hash_vals, uint32_t pool) {
+  // a frame cannot queue more entries than the list holds (one per pool slot + the few a full pool refused)
+  const uint32_t n = counters[kCntQueued];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && counters[kCntDropped] != 0)
+    counters[kCntDroppedTotal] += counters[kCntDropped];  // the frame's drop count is final: mark_bricks ran before
   const int t = threadIdx.x;
   // thread -> voxel pair: pair q = pass*256 + t, first voxel 2q = (x, y, z) with
   //   x = 2*pass + (t >> 7), y = (t >> 3) & 15, z = 2 * (t & 7)
   const int y = (t >> 3) & 15, z0 = 2 * (t & 7), xo = t >> 7;
   const bool with_color = color != nullptr && rgb != nullptr;
   for (uint32_t it = blockIdx.x; it < n; it += gridDim.x) {
-    const uint32_t brick = list[it];
-    const int bz = brick % f.nb[2], by = (brick / f.nb[2]) % f.nb[1], bx = brick / (f.nb[2] * f.nb[1]);
-    const double ox = (double)(f.b0[0] + bx) * f.unit_length;  // origin = index * unit_length (OpenVolumeUnit)
-    const double oy = (double)(f.b0[1] + by) * f.unit_length;
-    const double oz = (double)(f.b0[2] + bz) * f.unit_length;
+    const uint32_t entry = list[it];
+    const uint32_t brick = hash_vals[entry];  // pool slot
+    if (brick >= pool) continue;              // the pool was full when this brick was opened (counted as dropped)
+    int bx, by, bz;
+    brick_unkey(hash_keys[entry], bx, by, bz);
+    const double ox = (double)bx * f.unit_length;  // origin = index * unit_length (OpenVolumeUnit)
+    const double oy = (double)by * f.unit_length;
+    const double oz = (double)bz * f.unit_length;
     float4* base = tw + (size_t)brick * (GSB_BRICK_VOXELS / 2) + t;
     float4* cbase = color + ((size_t)brick * GSB_BRICK_VOXELS + 2 * (size_t)t);
     const float py = (float)((double)__fadd_rn(f.half, __fmul_rn(f.vl, (float)y)) + oy);
@@ -298,13 +349,16 @@ __global__ void __launch_bounds__(256) morph_kernel(const uint8_t* __restrict__ 
   }
 }
 
-// (mean, weight) <-> (sum, weight); mode 0: to sums, 1: from sums.  `bricks` == NULL: the whole store,
-// else only the listed bricks (one CTA-row of 2048 voxel pairs per brick).
+// (mean, weight) <-> (sum, weight); mode 0: to sums, 1: from sums.  `bricks` == NULL: every pool slot in use,
+// else only the listed slots (one CTA-row of 2048 voxel pairs per brick).
 __global__ void __launch_bounds__(256) sums_kernel(float4* __restrict__ tw, float4* __restrict__ color, size_t n_pairs, int mode,
-                                                   const uint32_t* __restrict__ bricks) {
+                                                   const uint32_t* __restrict__ bricks, const uint32_t* __restrict__ counters) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pairs) return;
-  if (bricks != nullptr) i = (size_t)bricks[i / (GSB_BRICK_VOXELS / 2)] * (GSB_BRICK_VOXELS / 2) + i % (GSB_BRICK_VOXELS / 2);
+  if (bricks != nullptr)
+    i = (size_t)bricks[i / (GSB_BRICK_VOXELS / 2)] * (GSB_BRICK_VOXELS / 2) + i % (GSB_BRICK_VOXELS / 2);
+  else if (i / (GSB_BRICK_VOXELS / 2) >= counters[kCntPool])
+    return;
   float4 v = tw[i];
   if (v.y == 0.f && v.w == 0.f) return;
   const float w0 = v.y, w1 = v.w;
@@ -336,26 +390,64 @@ __global__ void __launch_bounds__(256) sums_kernel(float4* __restrict__ tw, floa
   }
 }
 
-__global__ void __launch_bounds__(256) export_dense_kernel(const float2* __restrict__ tw, int nbx, int nby, int nbz,
-                                                           float* __restrict__ tsdf, float* __restrict__ weight) {
+// Window of the lattice -> dense x*NY*NZ + y*NZ + z grids (Open3D UniformTSDFVolume indexing); unallocated bricks read as 0.
+__global__ void __launch_bounds__(256) export_dense_kernel(const float2* __restrict__ tw, const unsigned long long* __restrict__ keys,
+                                                           const uint32_t* __restrict__ vals, uint32_t mask, uint32_t pool, int b0x,
+                                                           int b0y, int b0z, int nbx, int nby, int nbz, float* __restrict__ tsdf,
+                                                           float* __restrict__ weight) {
   const size_t n = (size_t)nbx * nby * nbz * GSB_BRICK_VOXELS;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // brick-layout index
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (window brick, voxel) index
   if (i >= n) return;
-  const size_t brick = i / GSB_BRICK_VOXELS;
+  const size_t wb = i / GSB_BRICK_VOXELS;
   const int vi = (int)(i % GSB_BRICK_VOXELS);
-  const int bz = (int)(brick % nbz), by = (int)((brick / nbz) % nby), bx = (int)(brick / ((size_t)nbz * nby));
+  const int bz = (int)(wb % nbz), by = (int)((wb / nbz) % nby), bx = (int)(wb / ((size_t)nbz * nby));
   const int x = bx * 16 + (vi >> 8), y = by * 16 + ((vi >> 4) & 15), z = bz * 16 + (vi & 15);
   const size_t o = ((size_t)x * (nby * 16) + y) * (nbz * 16) + z;
-  const float2 v = tw[i];
+  float2 v = make_float2(0.f, 0.f);
+  if (brick_key_ok(b0x + bx, b0y + by, b0z + bz)) {
+    const uint32_t h = brick_find(keys, mask, brick_key(b0x + bx, b0y + by, b0z + bz));
+    const uint32_t slot = h == kSlotNone ? kSlotNone : vals[h];
+    if (slot < pool) v = tw[(size_t)slot * GSB_BRICK_VOXELS + vi];
+  }
   if (tsdf) tsdf[o] = v.x;
   if (weight) weight[o] = v.y;
 }
 
-__global__ void copy_stats_kernel(const uint32_t* counters, uint32_t frame, uint32_t* out) {
-  out[0] = counters[0];
-  out[1] = counters[1];
+// lattice indices -> pool slots (kSlotNone if absent); insert != 0 opens missing bricks (zero-filled, like OpenVolumeUnit)
+__global__ void __launch_bounds__(256) find_bricks_kernel(const HashView hv, uint32_t* __restrict__ counters,
+                                                          const int32_t* __restrict__ indices, uint32_t n,
+                                                          const uint32_t* __restrict__ n_dev, int insert,
+                                                          uint32_t* __restrict__ slots, uint32_t* __restrict__ entries) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (n_dev != nullptr && i >= *n_dev)) return;
+  const int bx = indices[4 * (size_t)i], by = indices[4 * (size_t)i + 1], bz = indices[4 * (size_t)i + 2];
+  uint32_t h = kSlotNone;
+  if (insert) {
+    h = brick_find_or_insert(hv, counters, bx, by, bz);
+    if (h == kSlotNone) atomicAdd(&counters[kCntDropped], 1u);
+  } else if (brick_key_ok(bx, by, bz)) {
+    h = brick_find(hv.keys, hv.mask, brick_key(bx, by, bz));
+  }
+  if (entries) entries[i] = h;
+  if (slots) slots[i] = kSlotNone;  // resolved by resolve_slots_kernel once every insertion of this launch has landed
+}
+__global__ void __launch_bounds__(256) resolve_slots_kernel(const uint32_t* __restrict__ vals, const uint32_t* __restrict__ entries,
+                                                            uint32_t n, const uint32_t* __restrict__ n_dev, uint32_t pool,
+                                                            uint32_t* __restrict__ slots) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (n_dev != nullptr && i >= *n_dev)) return;
+  const uint32_t h = entries[i];
+  const uint32_t s = h == kSlotNone ? kSlotNone : vals[h];
+  slots[i] = s < pool ? s : kSlotNone;
+}
+
+__global__ void copy_stats_kernel(uint32_t* counters, uint32_t frame, uint32_t* out) {
+  out[0] = counters[kCntQueued];
+  out[1] = counters[kCntDropped];
   out[2] = frame;
-  out[3] = 0;
+  out[3] = counters[kCntPool];
+  out[4] = counters[kCntDroppedTotal];
+  out[5] = out[6] = out[7] = 0;
 }
 
 // general 4x4 inverse in double (Gauss-Jordan with partial pivoting)
@@ -407,28 +499,37 @@ using namespace gsb;
 
 extern "C" {
 
+static HashView hash_view(const GsbVolumeDesc& d) {
+  HashView hv;
+  hv.keys = reinterpret_cast<unsigned long long*>(d.hash_keys);
+  hv.vals = d.hash_vals;
+  hv.stamp = d.hash_stamp;
+  hv.index = d.brick_index;
+  hv.mask = d.hash_slots - 1u;
+  hv.pool = d.pool_bricks;
+  return hv;
+}
+
 GsbVolume* gsb_tsdf_create(const GsbVolumeDesc* desc) {
-  if (!desc || !desc->tsdf_weight || !desc->brick_stamp || !desc->brick_list || !desc->counters) {
-    fail(GSB_ERR_INVALID, "tsdf_create: tsdf_weight, brick_stamp, brick_list and counters are required");
+  if (!desc || !desc->tsdf_weight || !desc->brick_index || !desc->hash_keys || !desc->hash_vals || !desc->hash_stamp ||
+      !desc->brick_list || !desc->counters) {
+    fail(GSB_ERR_INVALID, "tsdf_create: tsdf_weight, brick_index, hash_keys, hash_vals, hash_stamp, brick_list and counters are required");
     return nullptr;
   }
-  for (int k = 0; k < 3; ++k)
-    if (desc->brick_count[k] <= 0) {
-      fail(GSB_ERR_INVALID, "tsdf_create: brick_count must be positive");
-      return nullptr;
-    }
+  if (desc->pool_bricks == 0 || desc->pool_bricks > 0x7fffffffu) {
+    fail(GSB_ERR_INVALID, "tsdf_create: pool_bricks must be in 1 .. 2^31-1");
+    return nullptr;
+  }
+  if (desc->hash_slots < 2 * (uint64_t)desc->pool_bricks || (desc->hash_slots & (desc->hash_slots - 1u)) != 0) {
+    fail(GSB_ERR_INVALID, "tsdf_create: hash_slots must be a power of two >= 2 * pool_bricks");
+    return nullptr;
+  }
   if (!(desc->voxel_length > 0) || !(desc->sdf_trunc > 0)) {
     fail(GSB_ERR_INVALID, "tsdf_create: voxel_length and sdf_trunc must be positive");
     return nullptr;
   }
-  const size_t nb = (size_t)desc->brick_count[0] * desc->brick_count[1] * desc->brick_count[2];
-  if (nb > 0x7fffffffull) {
-    fail(GSB_ERR_INVALID, "tsdf_create: too many bricks");
-    return nullptr;
-  }
   GsbVolume* v = new GsbVolume();
   v->d = *desc;
-  v->n_bricks = nb;
   return v;
 }
 
@@ -463,19 +564,18 @@ int gsb_mask_morphology(const uint8_t* mask_in, int32_t width, int32_t height, i
   return check_launch("morph_kernel", stream, false);
 }
 
-int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, int32_t width, int32_t height, double fx,
-                       double fy, double cx, double cy, const double* extrinsic, void* stream_v) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!vol || !depth || !extrinsic || width <= 0 || height <= 0) return fail(GSB_ERR_INVALID, "tsdf_integrate: bad arguments");
+// block discovery of one frame (T1): opens every brick within +-sdf_trunc of the sampled depth points and queues it
+static int run_mark(GsbVolume* vol, const float* depth, int32_t width, int32_t height, double fx, double fy, double cx, double cy,
+                    const double* extrinsic, cudaStream_t stream, double* unit_length_out) {
   const GsbVolumeDesc& d = vol->d;
   double pose[16];
   if (!invert4(extrinsic, pose)) return fail(GSB_ERR_INVALID, "tsdf_integrate: extrinsic is singular");
   vol->frame += 1;
   if (vol->frame == 0) {  // stamp wrap-around: start over
-    GSB_CUDA_OK(cudaMemsetAsync(d.brick_stamp, 0, vol->n_bricks * sizeof(uint32_t), stream));
+    GSB_CUDA_OK(cudaMemsetAsync(d.hash_stamp, 0, (size_t)d.hash_slots * sizeof(uint32_t), stream));
     vol->frame = 1;
   }
-  GSB_CUDA_OK(cudaMemsetAsync(d.counters, 0, 8 * sizeof(uint32_t), stream));
+  GSB_CUDA_OK(cudaMemsetAsync(d.counters, 0, 4 * sizeof(uint32_t), stream));  // the per-frame words; [4..] persist
 
   MarkParams m{};
   m.W = width;
@@ -489,18 +589,40 @@ int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, i
   for (int k = 0; k < 12; ++k) m.pose[k] = pose[k];
   m.trunc = d.sdf_trunc;
   m.unit_length = d.voxel_length * GSB_BRICK;
-  for (int k = 0; k < 3; ++k) {
-    m.b0[k] = d.brick_origin[k];
-    m.nb[k] = d.brick_count[k];
-  }
+  *unit_length_out = m.unit_length;
   const int ns = m.nsx * m.nsy;
   {
     StageTimer tm(kStMarkBricks, stream);
-    mark_bricks_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(m, depth, d.brick_stamp, d.brick_list, d.counters, vol->frame);
+    mark_bricks_kernel<<<(ns + 255) / 256, 256, 0, stream>>>(m, hash_view(d), depth, d.brick_list, d.counters, vol->frame);
   }
   count_launch();
+  return check_launch("mark_bricks_kernel", stream, false);
+}
+
+__global__ void fold_drops_kernel(uint32_t* counters) {
+  if (counters[kCntDropped] != 0) counters[kCntDroppedTotal] += counters[kCntDropped];
+}
+
+int gsb_tsdf_touch(GsbVolume* vol, const float* depth, int32_t width, int32_t height, double fx, double fy, double cx, double cy,
+                   const double* extrinsic, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!vol || !depth || !extrinsic || width <= 0 || height <= 0) return fail(GSB_ERR_INVALID, "tsdf_touch: bad arguments");
+  double unit_length = 0;
   int rc;
-  if ((rc = check_launch("mark_bricks_kernel", stream, false))) return rc;
+  if ((rc = run_mark(vol, depth, width, height, fx, fy, cx, cy, extrinsic, stream, &unit_length))) return rc;
+  fold_drops_kernel<<<1, 1, 0, stream>>>(vol->d.counters);
+  count_launch();
+  return check_launch("fold_drops_kernel", stream, false);
+}
+
+int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, int32_t width, int32_t height, double fx,
+                       double fy, double cx, double cy, const double* extrinsic, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!vol || !depth || !extrinsic || width <= 0 || height <= 0) return fail(GSB_ERR_INVALID, "tsdf_integrate: bad arguments");
+  const GsbVolumeDesc& d = vol->d;
+  double unit_length = 0;
+  int rc;
+  if ((rc = run_mark(vol, depth, width, height, fx, fy, cx, cy, extrinsic, stream, &unit_length))) return rc;
 
   FrameParams f{};
   for (int k = 0; k < 12; ++k) f.E[k] = (float)extrinsic[k];
@@ -521,12 +643,9 @@ int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, i
   f.safe_h = height - 0.0001f;
   f.W = width;
   f.H = height;
-  f.unit_length = m.unit_length;
-  for (int k = 0; k < 3; ++k) {
-    f.b0[k] = d.brick_origin[k];
-    f.nb[k] = d.brick_count[k];
-  }
-  const int grid = (int)((size_t)num_sms() * 8 < vol->n_bricks ? (size_t)num_sms() * 8 : vol->n_bricks);
+  f.unit_length = unit_length;
+  const int grid = (int)((size_t)num_sms() * 8 < (size_t)d.pool_bricks ? (size_t)num_sms() * 8 : (size_t)d.pool_bricks);
+  const unsigned long long* hkeys = reinterpret_cast<const unsigned long long*>(d.hash_keys);
   {
     StageTimer tm(kStIntegrate, stream);
     static const int occ = [] {  // A/B switch for profiling: GSB_INTEGRATE_OCC=3 -> 85 registers, no spills
@@ -535,10 +654,12 @@ int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, i
     }();
     if (occ == 3)
       integrate_kernel<3><<<grid, kIntThreads, 0, stream>>>(f, depth, rgb, reinterpret_cast<float4*>(d.tsdf_weight),
-                                                            reinterpret_cast<float4*>(d.color), d.brick_list, d.counters);
+                                                            reinterpret_cast<float4*>(d.color), d.brick_list, d.counters, hkeys,
+                                                            d.hash_vals, d.pool_bricks);
     else
       integrate_kernel<4><<<grid, kIntThreads, 0, stream>>>(f, depth, rgb, reinterpret_cast<float4*>(d.tsdf_weight),
-                                                            reinterpret_cast<float4*>(d.color), d.brick_list, d.counters);
+                                                            reinterpret_cast<float4*>(d.color), d.brick_list, d.counters, hkeys,
+                                                            d.hash_vals, d.pool_bricks);
   }
   count_launch();
   return check_launch("integrate_kernel", stream, false);
@@ -546,10 +667,11 @@ int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, i
 
 static int run_sums(GsbVolume* vol, int mode, const uint32_t* bricks, uint32_t n_bricks, cudaStream_t stream) {
   if (!vol) return fail(GSB_ERR_INVALID, "tsdf: volume is NULL");
-  const size_t n_pairs = (bricks ? (size_t)n_bricks : vol->n_bricks) * (GSB_BRICK_VOXELS / 2);
+  const size_t n_pairs = (bricks ? (size_t)n_bricks : (size_t)vol->d.pool_bricks) * (GSB_BRICK_VOXELS / 2);
   if (n_pairs == 0) return GSB_OK;
   sums_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, stream>>>(reinterpret_cast<float4*>(vol->d.tsdf_weight),
-                                                                     reinterpret_cast<float4*>(vol->d.color), n_pairs, mode, bricks);
+                                                                     reinterpret_cast<float4*>(vol->d.color), n_pairs, mode, bricks,
+                                                                     vol->d.counters);
   count_launch();
   return check_launch("sums_kernel", stream, false);
 }
@@ -561,15 +683,33 @@ int gsb_tsdf_sums_bricks(GsbVolume* vol, int to_sums, const uint32_t* bricks, ui
   return run_sums(vol, to_sums ? 0 : 1, bricks, n_bricks, static_cast<cudaStream_t>(stream));
 }
 
-int gsb_tsdf_export_dense(const GsbVolume* vol, float* tsdf, float* weight, void* stream_v) {
+int gsb_tsdf_export_dense(const GsbVolume* vol, const int32_t* brick_origin, const int32_t* brick_count, float* tsdf, float* weight,
+                          void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!vol || (!tsdf && !weight)) return fail(GSB_ERR_INVALID, "tsdf_export_dense: bad arguments");
-  const size_t n = vol->n_bricks * GSB_BRICK_VOXELS;
-  export_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float2*>(vol->d.tsdf_weight),
-                                                                       vol->d.brick_count[0], vol->d.brick_count[1],
-                                                                       vol->d.brick_count[2], tsdf, weight);
+  if (!vol || !brick_origin || !brick_count || (!tsdf && !weight)) return fail(GSB_ERR_INVALID, "tsdf_export_dense: bad arguments");
+  for (int k = 0; k < 3; ++k)
+    if (brick_count[k] <= 0) return fail(GSB_ERR_INVALID, "tsdf_export_dense: brick_count must be positive");
+  const size_t n = (size_t)brick_count[0] * brick_count[1] * brick_count[2] * GSB_BRICK_VOXELS;
+  if (n > 0xffffffffull * 256) return fail(GSB_ERR_INVALID, "tsdf_export_dense: window too large");
+  const GsbVolumeDesc& d = vol->d;
+  export_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float2*>(d.tsdf_weight), reinterpret_cast<const unsigned long long*>(d.hash_keys), d.hash_vals,
+      d.hash_slots - 1u, d.pool_bricks, brick_origin[0], brick_origin[1], brick_origin[2], brick_count[0], brick_count[1],
+      brick_count[2], tsdf, weight);
   count_launch();
   return check_launch("export_dense_kernel", stream, false);
+}
+
+int gsb_tsdf_find_bricks(GsbVolume* vol, const int32_t* indices, uint32_t n, int insert, uint32_t* slots, uint32_t* scratch,
+                         void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!vol || (n && (!indices || !slots || !scratch))) return fail(GSB_ERR_INVALID, "tsdf_find_bricks: bad arguments");
+  if (n == 0) return GSB_OK;
+  const GsbVolumeDesc& d = vol->d;
+  find_bricks_kernel<<<(n + 255) / 256, 256, 0, stream>>>(hash_view(d), d.counters, indices, n, nullptr, insert, slots, scratch);
+  resolve_slots_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d.hash_vals, scratch, n, nullptr, d.pool_bricks, slots);
+  count_launch(2);
+  return check_launch("find_bricks_kernel", stream, false);
 }
 
 int gsb_tsdf_last_stats(const GsbVolume* vol, uint32_t* out, void* stream_v) {

@@ -122,24 +122,30 @@ def extract_triangle_mesh(volume, with_colors: Optional[bool] = None) -> Triangl
     with_colors = (volume.color is not None) if with_colors is None else with_colors
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        bricks = torch.nonzero(volume._stamp != 0).reshape(-1).to(torch.int32).contiguous()  # every brick ever touched
-        nb = int(bricks.numel())
+        nb = volume.num_bricks()  # every brick ever opened = pool slots [0, nb)
         if nb == 0:
             return TriangleMesh(np.zeros((0, 3)), np.zeros((0, 3), np.int64), np.zeros((0, 3)) if with_colors else None)
+        bricks = torch.arange(nb, dtype=torch.int32, device=dev)
+        # edge keys are voxel indices inside the bounding box of the open bricks (+1: a cube reaches into its +1 neighbours)
+        idx = volume._index[:nb, :3]
+        lo = idx.min(dim=0).values.cpu().numpy().astype(np.int64)
+        hi = idx.max(dim=0).values.cpu().numpy().astype(np.int64)
+        window = (C.c_int32 * 6)(*[int(v) for v in lo], *[int(v) for v in (hi - lo + 2)])
         counts = torch.zeros(nb, dtype=torch.int32, device=dev)
-        _lib.check(L.gsb_mesh_count(volume._h, ptr(bricks), nb, ptr(counts), stream))
+        _lib.check(L.gsb_mesh_count(volume._h, window, ptr(bricks), nb, ptr(counts), stream))
         offsets = torch.cumsum(counts.to(torch.int64), 0) - counts.to(torch.int64)
         n_tri = int(counts.sum().item())
         if n_tri == 0:
             return TriangleMesh(np.zeros((0, 3)), np.zeros((0, 3), np.int64), np.zeros((0, 3)) if with_colors else None)
         keys = torch.empty(n_tri * 3, dtype=torch.int64, device=dev)
-        _lib.check(L.gsb_mesh_emit(volume._h, ptr(bricks), nb, ptr(offsets.contiguous()), ptr(keys), stream))
+        _lib.check(L.gsb_mesh_emit(volume._h, window, ptr(bricks), nb, ptr(offsets.contiguous()), ptr(keys), stream))
         uniq, inverse = torch.unique(keys, return_inverse=True)  # vertex ids = rank of the edge key
         nv = int(uniq.numel())
         xyz = torch.empty(nv, 3, dtype=torch.float64, device=dev)
         rgb = torch.empty(nv, 3, dtype=torch.float32, device=dev) if with_colors else None
-        _lib.check(L.gsb_mesh_vertices(volume._h, ptr(uniq.contiguous()), nv, ptr(xyz), ptr(rgb), stream))
+        _lib.check(L.gsb_mesh_vertices(volume._h, window, ptr(uniq.contiguous()), nv, ptr(xyz), ptr(rgb), stream))
         tris = inverse.reshape(-1, 3)
         mesh = TriangleMesh(xyz.cpu().numpy(), tris.cpu().numpy(), None if rgb is None else rgb.double().cpu().numpy())
-        mesh.edge_keys = uniq.cpu().numpy()  # (window voxel index * 3 + axis) per vertex, for tests
+        mesh.edge_keys = uniq.cpu().numpy()  # (voxel index inside `key_window` * 3 + axis) per vertex, for tests
+        mesh.key_window = (tuple(int(v) for v in lo), tuple(int(v) for v in (hi - lo + 2)))  # (brick origin, brick count)
     return mesh

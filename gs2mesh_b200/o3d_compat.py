@@ -13,8 +13,8 @@ gs2mesh_utils/tsdf_utils.py touches, so its body (lines 51-142) reads the same w
     clusters, n_tri, area = mesh.cluster_connected_triangles(); mesh.remove_triangles_by_mask(mask);
     mesh.remove_unreferenced_vertices()                                                                          # :132-140
 
-Differences from Open3D, by construction: the volume is a bounded window of the same voxel lattice (default
-512^3 around the origin, `window_resolution=` to change it) living in GPU memory; images are uploaded on
+Differences from Open3D, by construction: the volume lives in GPU memory (an unbounded, hashed set of 16^3 bricks on
+the same voxel lattice, like Open3D's; `window_resolution=` only sets the window dense read-backs look at); images are uploaded on
 integrate().  Everything else (argument names, the RuntimeError on mismatching image sizes, float32 depth
 conversion rule `d / scale; d >= trunc -> 0`) follows Open3D 0.17.
 """
@@ -110,7 +110,7 @@ class TriangleMesh(_Mesh):
 
 class ScalableTSDFVolume:
     def __init__(self, voxel_length, sdf_trunc, color_type=TSDFVolumeColorType.RGB8, volume_unit_resolution=16,
-                 depth_sampling_stride=4, *, window_resolution=512, device="cuda"):
+                 depth_sampling_stride=4, *, window_resolution=512, device="cuda", pool_bricks=None):
         if volume_unit_resolution != 16 or depth_sampling_stride != 4:
             raise NotImplementedError("only Open3D's defaults (volume_unit_resolution=16, depth_sampling_stride=4) are built; "
                                       "gs2mesh does not override them (tsdf_utils.py:53-56)")
@@ -121,7 +121,7 @@ class ScalableTSDFVolume:
         origin, count = default_window(window_resolution)
         self.voxel_length, self.sdf_trunc, self.color_type = float(voxel_length), float(sdf_trunc), color_type
         self._vol = TSDFVolume(self.voxel_length, self.sdf_trunc, origin, count, with_color=color_type == TSDFVolumeColorType.RGB8,
-                               device=device)
+                               device=device, pool_bricks=pool_bricks)
 
     def integrate(self, image, intrinsic, extrinsic):
         d = np.asarray(image.depth)
@@ -131,8 +131,9 @@ class ScalableTSDFVolume:
             raise RuntimeError("[ScalableTSDFVolume::Integrate] Unsupported image format.")
         prepared = self._vol.prepare_depth(d.astype(np.float32), intrinsic.width, intrinsic.height, depth_scale=image._depth_scale,
                                            depth_trunc=image._depth_trunc)
-        self._vol.integrate(prepared, c if self._vol.color is not None else None, intrinsic.width, intrinsic.height, intrinsic.fx,
-                            intrinsic.fy, intrinsic.cx, intrinsic.cy, np.asarray(extrinsic, dtype=np.float64))
+        # unbounded like Open3D's hash map: bricks are opened (and the pool grown if need be) before any voxel is updated
+        self._vol.integrate_exact(prepared, c if self._vol.color is not None else None, intrinsic.width, intrinsic.height,
+                                  intrinsic.fx, intrinsic.fy, intrinsic.cx, intrinsic.cy, np.asarray(extrinsic, dtype=np.float64))
 
     def extract_triangle_mesh(self):
         m = _extract(self._vol)

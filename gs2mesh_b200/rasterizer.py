@@ -17,6 +17,9 @@ from . import _lib
 from ._lib import GsbRasterArgs, ptr
 
 DEFAULT_FLAGS = _lib.RASTER_EXACT_TILE_CULL
+# first guess of the binning capacity of a scratch block: instances per Gaussian / floor (tests shrink these to provoke overflow)
+GUESS_PER_GAUSSIAN = 4
+MIN_GUESS = 1 << 20
 
 
 class _Scratch:
@@ -44,11 +47,11 @@ class _Scratch:
 _scratch = {}
 
 
-def _scratch_for(device) -> _Scratch:
+def _scratch_for(device, stream=None) -> _Scratch:
     """One scratch block per (device, stream): frames enqueued on different streams may overlap."""
     dev = torch.device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    key = (idx, (stream if stream is not None else torch.cuda.current_stream(idx)).cuda_stream)
     if key not in _scratch:
         _scratch[key] = _Scratch(torch.device("cuda", idx))
     return _scratch[key]
@@ -119,7 +122,7 @@ def rasterize_forward(*, means3D, opacities, viewmatrix, projmatrix, campos, bg,
         radii = torch.empty(P, dtype=torch.int32, device=device) if want_radii else None
         counts = counts_out if counts_out is not None else (torch.zeros(4, dtype=torch.int64, device=device) if want_counts else None)
         scratch = _scratch_for(device)
-        guess = max(scratch.max_instances if scratch.key == (P, W, H) else 0, 4 * P, 1 << 20, int(min_instances))
+        guess = max(scratch.max_instances if scratch.key == (P, W, H) else 0, GUESS_PER_GAUSSIAN * P, MIN_GUESS, int(min_instances))
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         L = _lib.lib()
         if async_mode:
@@ -142,6 +145,41 @@ def rasterize_forward(*, means3D, opacities, viewmatrix, projmatrix, campos, bg,
             _lib.check(rc)
             break
     return dict(color=color, depth=depth, final_T=final_T, radii=radii, counts=counts)
+
+
+def rasterize_forward_pair(*, means3D, opacities, shs, scales, rotations, sh_degree, bg, width, height, eyes, streams,
+                           flags=DEFAULT_FLAGS, shared_depth=False, scale_modifier=1.0, min_instances=0):
+    """Both eyes of a stereo pair through `gsb_raster_forward_pair` (one fused preprocess pass over the Gaussian
+    parameters; with `shared_depth` also one depth sort).  Always asynchronous.
+
+    eyes: two dicts with viewmatrix[16], projmatrix[16], campos[3] (device), tan_fovx, tan_fovy, out_color[3,H,W],
+          out_depth / out_final_T ([H,W] or None), counts_out (int64[4], device or pinned host, or None).
+    streams: (left, right) torch streams; the shared part runs on the left one, each eye has its own scratch block.
+    The caller checks counts_out[2] (scratch overflow) and counts_out[3] (shared_depth claimed but depths differ) after
+    its own synchronisation."""
+    device = means3D.device
+    P = means3D.shape[0]
+    W, H = int(width), int(height)
+    M = int(shs.shape[1])
+    L = _lib.lib()
+    with torch.cuda.device(device):
+        blocks = []
+        for eye, st in zip(eyes, streams):
+            scratch = _scratch_for(device, st)
+            guess = max(scratch.max_instances if scratch.key == (P, W, H) else 0, GUESS_PER_GAUSSIAN * P, MIN_GUESS, int(min_instances))
+            ws = scratch.ensure(P, W, H, guess)
+            fl = int(flags) | _lib.RASTER_ASYNC | (_lib.RASTER_PAIR_SHARED_DEPTH if shared_depth else 0)
+            blocks.append(GsbRasterArgs(
+                P=P, sh_degree=int(sh_degree), sh_coeffs=M, width=W, height=H, background=ptr(bg), means3D=ptr(means3D),
+                shs=ptr(shs), colors_precomp=None, opacities=ptr(opacities), scales=ptr(scales), rotations=ptr(rotations),
+                cov3D_precomp=None, scale_modifier=float(scale_modifier), viewmatrix=ptr(eye["viewmatrix"]),
+                projmatrix=ptr(eye["projmatrix"]), cam_pos=ptr(eye["campos"]), tan_fovx=float(eye["tan_fovx"]),
+                tan_fovy=float(eye["tan_fovy"]), prefiltered=0, flags=fl, out_color=ptr(eye["out_color"]),
+                out_depth=ptr(eye.get("out_depth")), out_final_T=ptr(eye.get("out_final_T")), radii=None,
+                num_rendered=ptr(eye.get("counts_out")), workspace=ptr(ws), workspace_bytes=ws.numel(),
+                max_instances=scratch.max_instances))
+        _lib.check(L.gsb_raster_forward_pair(C.byref(blocks[0]), C.byref(blocks[1]), C.c_void_p(streams[0].cuda_stream),
+                                             C.c_void_p(streams[1].cuda_stream)))
 
 
 def mark_visible(positions, viewmatrix, projmatrix):

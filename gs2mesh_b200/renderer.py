@@ -35,14 +35,20 @@ DEFAULT_PAIRS_IN_FLIGHT = 2
 
 
 class _PairReady:
-    """Completion handle of an asynchronously rendered pair (render_image_pair(..., wait=False))."""
+    """Completion handle of an asynchronously rendered pair (render_image_pair(..., wait=False)).  synchronize() waits for
+    both eyes and -- like the synchronous call -- transparently re-renders the pair if its binning scratch turned out too
+    small (the reference resizes inside every frame, rasterizer_impl.cu:281-285)."""
 
-    def __init__(self, events):
+    def __init__(self, events, redo=None):
         self._events = events
+        self._redo = redo
 
     def synchronize(self):
         for e in self._events:
             e.synchronize()
+        if self._redo is not None:
+            redo, self._redo = self._redo, None
+            redo()
 
 
 class Renderer:
@@ -69,7 +75,7 @@ class Renderer:
         self.left_cameras = [c["left"] for c in self.cameras]
         print(f"num views: {len(self.cameras)}")
         print(f"baseline: {self.baseline}")
-        if output_dir_root is not None and getattr(args, "renderer_save_json", False):
+        if output_dir_root is not None and getattr(args, "renderer_save_json", True):  # argument_utils.py:63 default
             self.save_camera_data()
         self.write_images = output_dir_root is not None
         # blend with ex2.approx instead of full-precision expf (GSB_RASTER_FAST_EXP): ~2e-7 relative on
@@ -137,6 +143,12 @@ class Renderer:
                 vts.append(vt)
             self._views.append(vts)
         self._camera_table = torch.as_tensor(recs).to(dev)
+        # One depth sort can serve both eyes of a rig when every Gaussian has the same view depth in both, i.e. when the z
+        # rows of the two view matrices are bitwise equal (same rotation, translation along the camera x axis).  The right
+        # camera's rotation goes through a float32 Euler round trip (renderer_utils.py:186-196), which moves an entry by
+        # one ulp in about one rig of five: those pairs keep one depth sort per eye.
+        zrow = recs[:, :, [2, 6, 10, 14]].view(np.uint32)
+        self._shared_depth = [bool(np.array_equal(zrow[i, 0], zrow[i, 1])) for i in range(len(self.cameras))]
         self._bufs = {}
         # per-(view, side) rasterizer status words, written by the GPU straight into pinned host memory
         self._status = torch.zeros(len(self.cameras), 2, 4, dtype=torch.int64).pin_memory()
@@ -144,27 +156,44 @@ class Renderer:
         self._ready = True
         self.calibrate_capacity()
 
-    def calibrate_capacity(self, sample_views=3, slack=1.5):
-        """Size the binning scratch once from a few synchronous renders so that the hot loop can run
-        without ever waiting for the GPU (the reference re-sizes -- and blocks -- inside every frame,
-        rasterizer_impl.cu:281-285)."""
+    def calibrate_capacity(self, sample_views=None, slack=1.1):
+        """Size the binning scratch once so that the hot loop can run without ever waiting for the GPU (the reference
+        re-sizes -- and blocks -- inside every frame, rasterizer_impl.cu:281-285).  By default EVERY view of the rig is
+        rendered once (instance counts are deterministic per camera), so a frame of this camera set cannot outgrow the
+        scratch; `sample_views=k` looks at k evenly spaced views only (then an overflowing frame is caught by its status
+        word and re-rendered, see render_image_pair)."""
         n = len(self.cameras)
-        worst = 0
-        for i in sorted(set(int(round(k * (n - 1) / max(sample_views - 1, 1))) for k in range(sample_views))):
-            for s in range(2):
-                out = self.render_view(i, s, want_counts=True)
-                worst = max(worst, int(out["counts"][0].item()))
+        if sample_views is None or sample_views >= n:
+            views = range(n)
+        else:
+            views = sorted(set(int(round(k * (n - 1) / max(sample_views - 1, 1))) for k in range(sample_views)))
+        counts = [self.render_view(i, s, want_counts=True)["counts"] for i in views for s in range(2)]  # grow-and-redo renders
+        worst = int(torch.stack(counts)[:, 0].max().item()) if counts else 0
         self._min_instances = int(worst * slack) + 4096
 
     def check_status(self, views=None):
-        """After a synchronisation: raise if any asynchronously rendered frame overflowed the scratch."""
+        """After a synchronisation: raise if any asynchronously rendered frame is invalid (binning scratch too small, or a
+        shared depth order claimed for eyes whose depths differ).  render_image_pair repairs such frames itself on every
+        path that synchronises; this check is for callers of the pure device path (to_host=False, wait=False)."""
         st = self._status if views is None else self._status[list(views)]
-        bad = (st[..., 2] != 0).nonzero()
+        bad = ((st[..., 2] != 0) | (st[..., 3] != 0)).nonzero()
         if len(bad):
             need = int(st[..., 0].max().item())
-            self._min_instances = max(self._min_instances, int(need * 1.5))
-            raise RuntimeError(f"{len(bad)} frame(s) needed more binning scratch than calibrated ({need} instances); "
+            self._min_instances = max(self._min_instances, int(need * 1.25))
+            raise RuntimeError(f"{len(bad)} frame(s) are invalid (needed up to {need} instances of binning scratch); "
                                "capacity has been raised, render them again")
+
+    def _frame_ok(self, camera_number):
+        """Status words of one pair after a synchronisation; repairs the renderer's settings if the pair must be redone."""
+        st = self._status[camera_number]
+        ok = True
+        if bool((st[:, 2] != 0).any()):
+            self._min_instances = max(self._min_instances, int(int(st[:, 0].max().item()) * 1.25) + 4096)
+            ok = False
+        if bool((st[:, 3] != 0).any()):
+            self._shared_depth[camera_number] = False
+            ok = False
+        return ok
 
     def _buffers(self, w, h, parity=0):
         key = (w, h, parity)
@@ -197,22 +226,62 @@ class Renderer:
             out_color=out_color, out_depth=out_depth, out_final_T=out_final_T, async_mode=async_mode,
             counts_out=self._status[camera_number, side] if async_mode else None, min_instances=self._min_instances)
 
+    def _enqueue_pair(self, camera_number, b, streams):
+        """Both eyes of one view into buffer set `b`: rasterize (+ u8 conversion) on `streams` (left, right)."""
+        mode = os.environ.get("GSB_PAIR_MODE", "fused")  # A/B switch: fused | noshare (fused preprocess, two depth sorts) | separate
+        flags = rast.DEFAULT_FLAGS | (rast._lib.RASTER_FAST_EXP if self.fast_exp else 0)
+        self._status[camera_number].zero_()
+        if mode == "separate":
+            for s in range(2):
+                with torch.cuda.stream(streams[s]):
+                    self.render_view(camera_number, s, want_depth=(s == 0), out_color=b["color"][s],
+                                     out_depth=b["depth"] if s == 0 else None, out_final_T=b["final_T"] if s == 0 else None,
+                                     async_mode=True)
+        else:
+            eyes = []
+            for s in range(2):
+                vt = self._views[camera_number][s]
+                rec = self._camera_table[camera_number, s]
+                eyes.append(dict(viewmatrix=rec[0:16], projmatrix=rec[16:32], campos=rec[32:35], tan_fovx=vt.tan_fovx,
+                                 tan_fovy=vt.tan_fovy, out_color=b["color"][s], out_depth=b["depth"] if s == 0 else None,
+                                 out_final_T=b["final_T"] if s == 0 else None, counts_out=self._status[camera_number, s]))
+            vt = self._views[camera_number][0]
+            rast.rasterize_forward_pair(means3D=self.means3D, opacities=self.opacity, shs=self.shs, scales=self.scales,
+                                        rotations=self.rotations, sh_degree=self.sh_degree, bg=self.background, width=vt.width,
+                                        height=vt.height, eyes=eyes, streams=streams, flags=flags,
+                                        shared_depth=self._shared_depth[camera_number] and mode != "noshare",
+                                        min_instances=self._min_instances)
+        for s in range(2):
+            with torch.cuda.stream(streams[s]):
+                rast.image_to_u8(b["color"][s], out=b["u8"][s])
+
     def render_image_pair(self, camera_number, visualize=False, *, to_host: Optional[bool] = None, wait: bool = True):
         """Render the stereo-aligned left/right pair of view `camera_number`
         (reference: renderer_utils.py:363-395).  Returns a dict of DEVICE tensors
         (left/right float CHW, left_u8/right_u8 HWC, depth = left sum(z*alpha*T), final_T) and, when
         `to_host` (default: whenever PNGs are written), pinned host copies `host_left_u8`,
-        `host_right_u8`.  With `wait=False` the call only enqueues: `result["ready"]` is a CUDA event to
-        synchronise on before touching the host copies (lets the caller overlap the next pair's rendering
-        with the host-side consumption of this one)."""
+        `host_right_u8`.  With `wait=False` the call only enqueues: `result["ready"].synchronize()` waits for the pair
+        (lets the caller overlap the next pair's rendering with the host-side consumption of this one).
+
+        Both eyes go through ONE `gsb_raster_forward_pair` call: the Gaussian parameters are read once, and -- for rigs whose
+        eyes see every Gaussian at the same view depth -- depth-sorted once.
+
+        A frame whose binning scratch turns out too small is re-rendered transparently wherever the call (or the handle's
+        synchronize()) waits for the GPU anyway; prepare_renderer() sizes the scratch from every view of the rig, so the
+        pure device path (to_host=False) cannot overflow for this camera set.
+
+        Buffer rotation: the returned tensors belong to one of pairs_in_flight + 2 buffer sets.  The tensors of call n
+        stay valid for work enqueued on the CALLER'S CURRENT STREAM until call n + pairs_in_flight + 1 is entered (the
+        renders that overwrite them wait for an event recorded on that stream at that moment); consumers on other
+        streams must order themselves (e.g. wait on an event recorded after the call)."""
         with torch.no_grad():
             vt = self._views[camera_number][0]
             dev = self._camera_table.device
             main = torch.cuda.current_stream(dev)
+            to_host = self.write_images if to_host is None else to_host
+            if self.write_images:
+                to_host = True  # PNGs are written from the pinned host copies
             if self.overlap_eyes:
-                # outputs rotate over pairs_in_flight + 2 buffer sets: the tensors returned by call n stay valid until
-                # call n + pairs_in_flight + 1 returns, which covers a caller that consumes pair n only after
-                # enqueuing the next pairs_in_flight pairs (wait=False)
                 self._call_index = getattr(self, "_call_index", -1) + 1
                 depth = max(1, int(self.pairs_in_flight))
                 nslots = depth + 2
@@ -246,33 +315,45 @@ class Renderer:
             else:
                 b = self._buffers(vt.width, vt.height)
                 streams = [main, main]
-            for s in range(2):
-                with torch.cuda.stream(streams[s]):
-                    self.render_view(camera_number, s, want_depth=(s == 0), out_color=b["color"][s],
-                                     out_depth=b["depth"] if s == 0 else None, out_final_T=b["final_T"] if s == 0 else None,
-                                     async_mode=True)
-                    rast.image_to_u8(b["color"][s], out=b["u8"][s])
+
+            def enqueue():
+                self._enqueue_pair(camera_number, b, streams)
+                if to_host:
+                    for s in range(2):
+                        with torch.cuda.stream(streams[s]):
+                            b["host_u8"][s].copy_(b["u8"][s], non_blocking=True)
+
+            def redo_if_invalid():
+                """Called after the pair's streams have been waited for: grow the scratch / drop the shared depth order and
+                render the pair again, synchronously, until its status words are clean."""
+                for _ in range(4):
+                    if self._frame_ok(camera_number):
+                        return
+                    enqueue()
+                    for st in streams:
+                        st.synchronize()
+                self.check_status([camera_number])
+
+            enqueue()
             result = dict(left=b["color"][0], right=b["color"][1], left_u8=b["u8"][0], right_u8=b["u8"][1],
                           depth=b["depth"], final_T=b["final_T"])
-            to_host = self.write_images if to_host is None else to_host
-            if to_host:
-                for s in range(2):
-                    with torch.cuda.stream(streams[s]):
-                        b["host_u8"][s].copy_(b["u8"][s], non_blocking=True)
             if self.overlap_eyes:
                 self._slot_done[slot] = [st.record_event() for st in streams]
-            asynchronous = to_host and not wait and not self.write_images and self.overlap_eyes
+            asynchronous = to_host and not wait and not self.write_images and not self.keep_frames and self.overlap_eyes
             if self.overlap_eyes and not asynchronous:
                 for st in streams:
                     main.wait_stream(st)  # device-side dependency only: later work on the caller's stream sees both eyes
             if to_host:
                 result["host_left_u8"], result["host_right_u8"] = b["host_u8"]
                 if asynchronous:
-                    result["ready"] = _PairReady([st.record_event() for st in streams])
+                    result["ready"] = _PairReady([st.record_event() for st in streams], redo_if_invalid)
                 else:
                     main.synchronize()
-                    self.check_status([camera_number])
+                    redo_if_invalid()
                     result["ready"] = _PairReady([])
+            elif self.keep_frames:
+                main.synchronize()
+                redo_if_invalid()
             if self.write_images:
                 import cv2
 
@@ -280,8 +361,9 @@ class Renderer:
                 os.makedirs(out_dir, exist_ok=True)
                 for s, name in enumerate(("left", "right")):
                     cv2.imwrite(os.path.join(out_dir, f"{name}.png"), cv2.cvtColor(b["host_u8"][s].numpy(), cv2.COLOR_RGB2BGR))
-            if self.keep_frames:
-                self._frames[camera_number] = dict(left_u8=b["u8"][0].clone(), depth=self.expected_depth(b["depth"], b["final_T"]))
+            if self.keep_frames:  # in-memory hand-off to the TSDF stage (the caller's stream already waits for both eyes)
+                self._frames[camera_number] = dict(left_u8=b["u8"][0].clone(), right_u8=b["u8"][1].clone(),
+                                                   depth=self.expected_depth(b["depth"], b["final_T"]))
             return result
 
     # north_star alias
@@ -296,3 +378,31 @@ class Renderer:
 
     def get_frame(self, camera_number):
         return self._frames.get(camera_number)
+
+    # ---- in-memory hand-off to / from the stereo stage ---------------------------------------------
+    def stereo_inputs(self, camera_number, device=None):
+        """What `Stereo.run` builds by re-reading left.png / right.png right after render_image_pair
+        (stereo_utils.py:68-80,100-103): two float tensors [1,3,H,W] holding the uint8-quantised RGB frames -- bit for bit
+        the values `load_image` returns, without the PNG encode / file / decode round trip.  Renders the pair if it is not
+        in the frame cache (`keep_frames`)."""
+        f = self._frames.get(camera_number)
+        if f is None:
+            keep, self.keep_frames = self.keep_frames, True
+            try:
+                self.render_image_pair(camera_number)
+            finally:
+                self.keep_frames = keep
+            f = self._frames[camera_number]
+            if not keep:
+                self._frames.pop(camera_number, None)
+        to = lambda u8: u8.permute(2, 0, 1).float()[None].to(device or u8.device)
+        return to(f["left_u8"]), to(f["right_u8"])
+
+    def put_stereo_outputs(self, camera_number, depth, occlusion_mask=None):
+        """The other direction: the stereo stage's depth (= fx * baseline / disparity_LR, stereo_utils.py:133) and
+        left-right occlusion mask (:132) for one view, as tensors / arrays, instead of depth.npy / occlusion_mask.npy on disk
+        (stereo_utils.py:135-137 -> tsdf_utils.py:67,79-80).  TSDF.run() picks them up from the frame cache."""
+        f = self._frames.setdefault(camera_number, {})
+        f["depth"] = depth
+        if occlusion_mask is not None:
+            f["occlusion_mask"] = occlusion_mask

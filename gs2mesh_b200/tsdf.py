@@ -28,17 +28,23 @@ from ._lib import BRICK, BRICK_VOXELS, GsbVolumeDesc, ptr
 
 def default_window(resolution: int = 512):
     """Brick window of the dense `resolution`^3 lattice centred on the origin: the dense equivalent
-    of `voxel_length = TSDF_voxel / 512` (tsdf_utils.py:51)."""
+    of `voxel_length = TSDF_voxel / 512` (tsdf_utils.py:51).  Only a VIEW for dense read-backs
+    (`TSDFVolume.bricks()` / `.dense()`): the volume itself is unbounded."""
     nb = resolution // BRICK
     return (-(nb // 2),) * 3, (nb,) * 3
 
 
-class TSDFVolume:
-    """A bounded window of Open3D's ScalableTSDFVolume lattice, resident in HBM (brick layout,
-    see GsbVolumeDesc in include/gs2mesh_b200.h)."""
+DEFAULT_POOL_BRICKS = 1 << 15  # 32768 bricks = 1 GiB of (tsdf, weight) + 2 GiB of colour; grown on demand
 
-    def __init__(self, voxel_length: float, sdf_trunc: float, brick_origin: Sequence[int] = (-16, -16, -16),
-                 brick_count: Sequence[int] = (32, 32, 32), with_color: bool = True, device="cuda"):
+
+class TSDFVolume:
+    """Open3D's ScalableTSDFVolume in HBM: an unbounded set of 16^3-voxel bricks, opened on first touch, addressed by their
+    integer lattice index through a device hash table and stored in a brick pool (GsbVolumeDesc in include/gs2mesh_b200.h).
+    `brick_origin` / `brick_count` only define the window the dense read-backs `bricks()` / `dense()` look at."""
+
+    def __init__(self, voxel_length: float, sdf_trunc: float, brick_origin: Optional[Sequence[int]] = None,
+                 brick_count: Optional[Sequence[int]] = None, with_color: bool = True, device="cuda",
+                 pool_bricks: Optional[int] = None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("TSDFVolume needs a CUDA device (gs2mesh_b200 has no CPU path)")
@@ -46,38 +52,69 @@ class TSDFVolume:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.voxel_length = float(voxel_length)
         self.sdf_trunc = float(sdf_trunc)
+        if brick_origin is None or brick_count is None:
+            brick_origin, brick_count = default_window(512)
         self.brick_origin = tuple(int(v) for v in brick_origin)
         self.brick_count = tuple(int(v) for v in brick_count)
-        self.n_bricks = int(np.prod(self.brick_count))
-        n_vox = self.n_bricks * BRICK_VOXELS
+        self.with_color = bool(with_color)
+        self._L = _lib.lib()
+        self._h = None
+        self._comms = {}
+        self._reduce_scratch = None
+        self._allocate(int(pool_bricks or DEFAULT_POOL_BRICKS))
+        self.frames_integrated = 0
+
+    # ------------------------------------------------------------------ storage
+    def _allocate(self, pool_bricks: int):
         dev = self.device
+        self.pool_bricks = int(pool_bricks)
+        self.hash_slots = 1 << max(4, int(2 * self.pool_bricks - 1).bit_length())
+        n_vox = self.pool_bricks * BRICK_VOXELS
         self.tsdf_weight = torch.zeros(n_vox * 2, dtype=torch.float32, device=dev)
-        self.color = torch.zeros(n_vox * 4, dtype=torch.float32, device=dev) if with_color else None
-        self._stamp = torch.zeros(self.n_bricks, dtype=torch.int32, device=dev)
-        self._list = torch.zeros(self.n_bricks, dtype=torch.int32, device=dev)
+        self.color = torch.zeros(n_vox * 4, dtype=torch.float32, device=dev) if self.with_color else None
+        self._index = torch.zeros(self.pool_bricks, 4, dtype=torch.int32, device=dev)
+        self._hash_keys = torch.full((self.hash_slots,), -1, dtype=torch.int64, device=dev)  # all-ones = empty
+        self._hash_vals = torch.zeros(self.hash_slots, dtype=torch.int32, device=dev)
+        self._hash_stamp = torch.zeros(self.hash_slots, dtype=torch.int32, device=dev)
+        self._list = torch.zeros(self.hash_slots, dtype=torch.int32, device=dev)
         self._counters = torch.zeros(8, dtype=torch.int32, device=dev)
-        self._depth_buf = None
         desc = GsbVolumeDesc()
-        desc.brick_origin = (C.c_int32 * 3)(*self.brick_origin)
-        desc.brick_count = (C.c_int32 * 3)(*self.brick_count)
         desc.voxel_length = self.voxel_length
         desc.sdf_trunc = self.sdf_trunc
+        desc.pool_bricks = self.pool_bricks
+        desc.hash_slots = self.hash_slots
         desc.tsdf_weight = ptr(self.tsdf_weight)
         desc.color = ptr(self.color)
-        desc.brick_stamp = ptr(self._stamp)
+        desc.brick_index = ptr(self._index)
+        desc.hash_keys = ptr(self._hash_keys)
+        desc.hash_vals = ptr(self._hash_vals)
+        desc.hash_stamp = ptr(self._hash_stamp)
         desc.brick_list = ptr(self._list)
         desc.counters = ptr(self._counters)
-        self._L = _lib.lib()
+        if self._h:
+            self._L.gsb_tsdf_destroy(self._h)
         self._h = self._L.gsb_tsdf_create(C.byref(desc))
         if not self._h:
             raise _lib.GsbError(_lib.GSB_ERR_INVALID, self._L.gsb_last_error().decode())
-        self.frames_integrated = 0
 
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
             self._L.gsb_tsdf_destroy(h)
             self._h = None
+        for comm in getattr(self, "_comms", {}).values():
+            self._L.gsb_comm_destroy(comm)
+
+    def grow(self, pool_bricks: Optional[int] = None):
+        """Re-house the volume in a larger pool (synchronises): every open brick keeps its content and its pool slot."""
+        n = self.num_bricks()
+        old_tw, old_color, old_index = self.tsdf_weight, self.color, self._index
+        self._allocate(int(pool_bricks or 2 * self.pool_bricks))
+        if n:
+            perm = self.find_bricks(old_index[:n], insert=True).long()  # where the parallel insert put each brick
+            self.tsdf_weight.view(self.pool_bricks, -1)[perm] = old_tw.view(-1, BRICK_VOXELS * 2)[:n]
+            if self.color is not None:
+                self.color.view(self.pool_bricks, -1)[perm] = old_color.view(-1, BRICK_VOXELS * 4)[:n]
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -86,7 +123,7 @@ class TSDFVolume:
 
     @property
     def origin(self):
-        """World position of the window's minimum corner."""
+        """World position of the view window's minimum corner."""
         return tuple(o * BRICK * self.voxel_length for o in self.brick_origin)
 
     def _stream(self):
@@ -143,13 +180,134 @@ class TSDFVolume:
                                                   e.ctypes.data_as(C.POINTER(C.c_double)), self._stream()))
         self.frames_integrated += 1
 
-    def last_stats(self):
-        """(bricks touched, points needing bricks outside the window, frame id) of the last integrate (syncs)."""
-        out = torch.zeros(4, dtype=torch.int32, device=self.device)
+    def integrate_exact(self, depth, rgb, width, height, fx, fy, cx, cy, extrinsic_w2c):
+        """integrate() that can never lose a brick: the frame's bricks are opened first (`gsb_tsdf_touch`), the pool is grown
+        if they did not fit, and only then are the voxels updated.  Two host synchronisations per frame -- for callers that
+        want Open3D's unbounded behaviour frame by frame (the o3d_compat facade); the stage class checks once per run."""
+        with torch.cuda.device(self.device):
+            depth = self._f32(depth, "depth")
+            e = np.ascontiguousarray(np.asarray(extrinsic_w2c, dtype=np.float64).reshape(16))
+            for _ in range(16):
+                _lib.check(self._L.gsb_tsdf_touch(self._h, ptr(depth), int(width), int(height), float(fx), float(fy), float(cx),
+                                                  float(cy), e.ctypes.data_as(C.POINTER(C.c_double)), self._stream()))
+                if self.ensure_capacity():
+                    break
+        self.integrate(depth, rgb, width, height, fx, fy, cx, cy, extrinsic_w2c)
+
+    def pool_stats(self):
+        """dict(touched, dropped, frame, bricks, dropped_total) -- synchronises.  `dropped` counts bricks the last integrate
+        could not open (pool exhausted); `dropped_total` since creation / reset."""
+        out = torch.zeros(8, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._L.gsb_tsdf_last_stats(self._h, ptr(out), self._stream()))
         v = out.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-        return int(v[0]), int(v[1]), int(v[2])
+        return dict(touched=int(v[0]), dropped=int(v[1]), frame=int(v[2]), bricks=int(v[3]), dropped_total=int(v[4]))
+
+    def last_stats(self):
+        """(bricks touched, bricks dropped, frame id) of the last integrate (syncs)."""
+        s = self.pool_stats()
+        return s["touched"], s["dropped"], s["frame"]
+
+    def num_bricks(self) -> int:
+        """Bricks opened so far (synchronises)."""
+        return int(self._counters[4].item())
+
+    def ensure_capacity(self):
+        """After a batch of integrations: True if every brick found room.  Otherwise the pool is doubled (content kept, the
+        dropped-bricks counter cleared) and False is returned -- the views since the last check must be integrated again."""
+        s = self.pool_stats()
+        if s["dropped_total"] == 0:
+            return True
+        self.grow()
+        self._counters[5] = 0
+        return False
+
+    # ------------------------------------------------------------------ brick access
+    def find_bricks(self, indices, insert: bool = False):
+        """Lattice indices [n,3|4] -> pool slots int32[n] (-1 = not in the volume)."""
+        idx = torch.as_tensor(indices).to(self.device, dtype=torch.int32)
+        if idx.ndim != 2 or idx.shape[1] not in (3, 4):
+            raise ValueError("indices must be [n,3]")
+        n = int(idx.shape[0])
+        idx4 = torch.zeros(n, 4, dtype=torch.int32, device=self.device)
+        idx4[:, :3] = idx[:, :3]
+        slots = torch.empty(n, dtype=torch.int32, device=self.device)
+        scratch = torch.empty(n, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.gsb_tsdf_find_bricks(self._h, ptr(idx4), n, 1 if insert else 0, ptr(slots), ptr(scratch), self._stream()))
+        return slots
+
+    def brick_indices(self):
+        """int32 [n,3] lattice indices of the open bricks, in pool order (synchronises)."""
+        return self._index[: self.num_bricks(), :3]
+
+    def pool(self):
+        """View [pool_bricks, 4096, 2] of the brick pool (no copy); slots >= num_bricks() are unused (zero)."""
+        return self.tsdf_weight.view(self.pool_bricks, BRICK_VOXELS, 2)
+
+    def brick_at(self, index):
+        """[4096, 2] (tsdf, weight) view of the brick with integer lattice index (bx, by, bz) (Open3D's volume-unit index)."""
+        slot = int(self.find_bricks(np.asarray(index, dtype=np.int32).reshape(1, -1)[:, :3])[0].item())
+        if slot < 0:
+            raise KeyError(f"brick {tuple(int(v) for v in index)} was never opened")
+        return self.pool()[slot]
+
+    def export_units(self):
+        """{(bx,by,bz): (tsdf_weight float32 [4096,2], colour float32 [4096,4] | None)} of every open brick, on the host
+        (Open3D: the contents of volume_units_)."""
+        n = self.num_bricks()
+        idx = self._index[:n, :3].cpu().numpy()
+        tw = self.pool()[:n].cpu().numpy()
+        col = self.color.view(self.pool_bricks, BRICK_VOXELS, 4)[:n].cpu().numpy() if self.color is not None else None
+        return {tuple(int(v) for v in idx[i]): (tw[i], None if col is None else col[i]) for i in range(n)}
+
+    def bricks(self, brick_origin=None, brick_count=None):
+        """Dense read-back [n_window_bricks, 4096, 2] of a window of the lattice (default: the view window), bricks row-major
+        over (bx,by,bz), never-opened bricks zero: the layout oracle.OracleTSDFVolume.export_bricks produces.  A COPY."""
+        b0 = self.brick_origin if brick_origin is None else tuple(int(v) for v in brick_origin)
+        nb = self.brick_count if brick_count is None else tuple(int(v) for v in brick_count)
+        g = torch.stack(torch.meshgrid(*[torch.arange(b0[k], b0[k] + nb[k], dtype=torch.int32) for k in range(3)], indexing="ij"),
+                        -1).reshape(-1, 3)
+        slots = self.find_bricks(g).long()
+        out = torch.zeros(len(g), BRICK_VOXELS, 2, dtype=torch.float32, device=self.device)
+        have = slots >= 0
+        out[have] = self.pool()[slots[have]]
+        return out
+
+    def colors(self, brick_origin=None, brick_count=None):
+        """Colour companion of bricks(): [n_window_bricks, 4096, 4] running-mean (r, g, b, unused), zeros where never opened."""
+        b0 = self.brick_origin if brick_origin is None else tuple(int(v) for v in brick_origin)
+        nb = self.brick_count if brick_count is None else tuple(int(v) for v in brick_count)
+        g = torch.stack(torch.meshgrid(*[torch.arange(b0[k], b0[k] + nb[k], dtype=torch.int32) for k in range(3)], indexing="ij"),
+                        -1).reshape(-1, 3)
+        slots = self.find_bricks(g).long()
+        out = torch.zeros(len(g), BRICK_VOXELS, 4, dtype=torch.float32, device=self.device)
+        have = slots >= 0
+        out[have] = self.color.view(self.pool_bricks, BRICK_VOXELS, 4)[slots[have]]
+        return out
+
+    def dense(self, brick_origin=None, brick_count=None):
+        """(tsdf, weight) of a window of the lattice as dense [X,Y,Z] grids in Open3D UniformTSDFVolume index order."""
+        b0 = self.brick_origin if brick_origin is None else tuple(int(v) for v in brick_origin)
+        nb = self.brick_count if brick_count is None else tuple(int(v) for v in brick_count)
+        rx, ry, rz = (n * BRICK for n in nb)
+        tsdf = torch.empty(rx, ry, rz, dtype=torch.float32, device=self.device)
+        weight = torch.empty_like(tsdf)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.gsb_tsdf_export_dense(self._h, (C.c_int32 * 3)(*b0), (C.c_int32 * 3)(*nb), ptr(tsdf), ptr(weight),
+                                                     self._stream()))
+        return tsdf, weight
+
+    def reset(self):
+        self.tsdf_weight.zero_()
+        if self.color is not None:
+            self.color.zero_()
+        self._index.zero_()
+        self._hash_keys.fill_(-1)
+        self._hash_vals.zero_()
+        self._hash_stamp.zero_()
+        self._counters.zero_()
+        self.frames_integrated = 0
 
     # ------------------------------------------------------------------ multi-GPU merge
     def to_sums(self):
@@ -160,70 +318,51 @@ class TSDFVolume:
         with torch.cuda.device(self.device):
             _lib.check(self._L.gsb_tsdf_from_sums(self._h, self._stream()))
 
-    def reduce_across_ranks(self, group=None, dst: Optional[int] = None, chunk_bytes: int = 256 << 20, sparse: bool = True):
-        """Merge view-sharded volumes: (mean, w) -> (sum, w), ONE NCCL SUM reduce, -> (mean, w).  With dst=None every
-        rank ends with the merged volume, else only rank `dst`.
+    def _comm(self, group):
+        """ncclComm_t of this volume's merge, created once per process group: rank 0 makes the id, torch.distributed carries
+        its 128 bytes to the others (plumbing), every rank joins with gsb_comm_create."""
+        import torch.distributed as dist
 
-        sparse=True (default) exchanges only the bricks at least one rank has touched: a small MAX all-reduce of the
-        brick stamps gives every rank the same brick list, the listed bricks are packed into a contiguous buffer,
-        reduced and unpacked.  A fused volume touches a few percent of its bricks, so the payload shrinks from
-        24 bytes x N^3 to 96 KB x touched bricks (C4, 1024^3: 25.8 GB -> ~2 GB per rank)."""
+        key = id(group) if group is not None else 0
+        if key not in self._comms:
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            buf = (C.c_uint8 * 128)()
+            if rank == 0:
+                _lib.check(self._L.gsb_comm_unique_id(buf))
+            t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=self.device)
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+            with torch.cuda.device(self.device):
+                comm = self._L.gsb_comm_create(ident, world, rank)
+            if not comm:
+                raise _lib.GsbError(_lib.GSB_ERR_CUDA, self._L.gsb_last_error().decode())
+            self._comms[key] = comm
+        return self._comms[key]
+
+    def reduce_across_ranks(self, group=None, dst: Optional[int] = None):
+        """Merge view-sharded volumes with ONE `gsb_tsdf_reduce` call per rank (include/gs2mesh_b200.h): the ranks exchange
+        their brick lattice indices, agree on the union, and sum-reduce (sum tsdf*w, w, sum rgb*w) of exactly those bricks in
+        one NCCL reduce (dst = rank) or all-reduce (dst=None); everything runs on the current stream, the only host
+        synchronisation is the read of the union's size.  The root exchanges its pool in place."""
         import torch.distributed as dist
 
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return
-        if not sparse:
-            self.to_sums()
-            reduce_sum_chunked([self.tsdf_weight, self.color], group=group, dst=dst, chunk_bytes=chunk_bytes)
-            self.from_sums()
-            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        comm = self._comm(group)
         with torch.cuda.device(self.device):
-            touched = (self._stamp != 0).to(torch.int32)
-            dist.all_reduce(touched, op=dist.ReduceOp.MAX, group=group)
-            ids = torch.nonzero(touched).reshape(-1)
-            n = int(ids.numel())
-            if n == 0:
-                return
-            ids32 = ids.to(torch.int32).contiguous()
-            _lib.check(self._L.gsb_tsdf_sums_bricks(self._h, 1, ptr(ids32), n, self._stream()))
-            packed = [self.bricks()[ids]]  # [n, 4096, 2] contiguous copies of the listed bricks
-            if self.color is not None:
-                packed.append(self.color.view(self.n_bricks, BRICK_VOXELS, 4)[ids])
-            reduce_sum_chunked(packed, group=group, dst=dst, chunk_bytes=chunk_bytes)
-            self.bricks()[ids] = packed[0]
-            if self.color is not None:
-                self.color.view(self.n_bricks, BRICK_VOXELS, 4)[ids] = packed[1]
-            self._stamp[ids] = torch.clamp_min(self._stamp[ids], 1)  # merged bricks count as touched everywhere
-            _lib.check(self._L.gsb_tsdf_sums_bricks(self._h, 0, ptr(ids32), n, self._stream()))
-
-    # ------------------------------------------------------------------ read-back
-    def bricks(self):
-        """View [n_bricks, 4096, 2] of the brick store (no copy)."""
-        return self.tsdf_weight.view(self.n_bricks, BRICK_VOXELS, 2)
-
-    def brick_at(self, index):
-        """[4096, 2] (tsdf, weight) view of the brick with integer lattice index (bx, by, bz) (Open3D's volume-unit index)."""
-        b = [int(index[k]) - self.brick_origin[k] for k in range(3)]
-        if any(b[k] < 0 or b[k] >= self.brick_count[k] for k in range(3)):
-            raise KeyError(f"brick {tuple(int(v) for v in index)} is outside the window")
-        return self.bricks()[(b[0] * self.brick_count[1] + b[1]) * self.brick_count[2] + b[2]]
-
-    def dense(self):
-        """(tsdf, weight) as dense [X,Y,Z] grids in Open3D UniformTSDFVolume index order."""
-        rx, ry, rz = self.resolution
-        tsdf = torch.empty(rx, ry, rz, dtype=torch.float32, device=self.device)
-        weight = torch.empty_like(tsdf)
-        with torch.cuda.device(self.device):
-            _lib.check(self._L.gsb_tsdf_export_dense(self._h, ptr(tsdf), ptr(weight), self._stream()))
-        return tsdf, weight
-
-    def reset(self):
-        self.tsdf_weight.zero_()
-        if self.color is not None:
-            self.color.zero_()
-        self._stamp.zero_()
-        self.frames_integrated = 0
-
+            need = int(self._L.gsb_tsdf_reduce_scratch_bytes(self._h, world, max(1024, self.pool_bricks // 16)))
+            for _ in range(3):
+                if self._reduce_scratch is None or self._reduce_scratch.numel() < need:
+                    self._reduce_scratch = None
+                    self._reduce_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+                rc = self._L.gsb_tsdf_reduce(self._h, comm, world, rank, -1 if dst is None else int(dst), ptr(self._reduce_scratch),
+                                             self._reduce_scratch.numel(), self._stream())
+                if rc != _lib.GSB_ERR_WORKSPACE:
+                    break
+                # the required size is the same on every rank (it depends on the union only): all ranks retry together
+                need = int(self._L.gsb_tsdf_reduce_required_bytes()) * 5 // 4
+            _lib.check(rc)
 
 def filter_object_mask(mask, closing_kernel_size: int = 10, erosion_kernel_size: int = 10, invert: bool = False, device="cuda"):
     """tsdf_utils.py:69-77 on the GPU: optional inversion, cv2.morphologyEx(MORPH_CLOSE, ones(ck,ck)) (dilate, then
@@ -246,23 +385,69 @@ def filter_object_mask(mask, closing_kernel_size: int = 10, erosion_kernel_size:
     return a
 
 
-def reduce_sum_chunked(buffers, group=None, dst: Optional[int] = None, chunk_bytes: int = 256 << 20):
-    """The one collective of the multi-GPU path: an in-place SUM reduce (all-reduce when dst is None)
-    of each flat fp32 buffer, issued in `chunk_bytes` pieces so a 1024^3 volume (8.6 GB) does not
-    need one giant NCCL launch and the tail of integration can overlap the first chunks."""
+def merge_units_protocol(units, group=None, dst: Optional[int] = None, pool_bricks: int = 4096):
+    """Host-side statement of `gsb_tsdf_reduce`'s protocol (csrc/gsb_reduce.cu), step for step, on numpy units
+    {(bx,by,bz): tsdf_weight float32 [4096,2]} with torch.distributed collectives of ANY backend -- what the CPU (gloo,
+    world_size 2) tests run, since the device path needs GPUs:
+      1. all-gather of every rank's (count, fixed-size padded list of brick lattice indices);
+      2. the receiving ranks open the bricks they lack (zero-filled);
+      3. broadcast of the canonical rank's brick order;
+      4. pack in canonical order, (mean,w) -> (sum,w), bricks a rank never saw travel as zeros;
+      5. ONE sum reduce (dst) / all-reduce (dst=None) of the packed payload;
+      6. (sum,w) -> (mean,w) where the result lives.
+    Returns this rank's units after the merge."""
     import torch.distributed as dist
 
-    for buf in buffers:
-        if buf is None:
-            continue
-        flat = buf.view(-1)
-        step = max(1, chunk_bytes // flat.element_size())
-        for s in range(0, flat.numel(), step):
-            piece = flat[s:s + step]
-            if dst is None:
-                dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=group)
-            else:
-                dist.reduce(piece, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    canon_rank = 0 if dst is None else int(dst)
+    receives = dst is None or rank == canon_rank
+    units = {k: np.array(v, dtype=np.float32, copy=True) for k, v in units.items()}
+    order = list(units)  # pool order of this rank
+    # 1.
+    mine = torch.zeros(1 + pool_bricks, 4, dtype=torch.int32)
+    mine[0, 0] = len(order)
+    if order:
+        mine[1:1 + len(order), :3] = torch.tensor(order, dtype=torch.int32)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    # 2.
+    if receives:
+        for r in range(world):
+            if r == rank:
+                continue
+            for k in gathered[r][1:1 + int(gathered[r][0, 0])].tolist():
+                key = tuple(k[:3])
+                if key not in units:
+                    units[key] = np.zeros((BRICK_VOXELS, 2), np.float32)
+                    order.append(key)
+    # 3.
+    canon = torch.zeros(1 + pool_bricks, 4, dtype=torch.int32)
+    if rank == canon_rank:
+        canon[0, 0] = len(order)
+        canon[1:1 + len(order), :3] = torch.tensor(order, dtype=torch.int32)
+    dist.broadcast(canon, src=canon_rank if group is None else dist.get_global_rank(group, canon_rank), group=group)
+    n = int(canon[0, 0])
+    canon_keys = [tuple(k[:3]) for k in canon[1:1 + n].tolist()]
+    # 4.
+    packed = torch.zeros(n, BRICK_VOXELS, 2, dtype=torch.float32)
+    for i, key in enumerate(canon_keys):
+        if key in units:
+            tw = units[key]
+            packed[i, :, 0] = torch.from_numpy(tw[:, 0] * tw[:, 1])
+            packed[i, :, 1] = torch.from_numpy(tw[:, 1])
+    # 5.
+    if dst is None:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(packed, dst=canon_rank if group is None else dist.get_global_rank(group, canon_rank), op=dist.ReduceOp.SUM,
+                    group=group)
+    # 6.
+    if receives:
+        p = packed.numpy()
+        for i, key in enumerate(canon_keys):
+            w = p[i, :, 1]
+            units[key] = np.stack([np.where(w > 0, p[i, :, 0] / np.maximum(w, 1e-30), 0).astype(np.float32), w], -1)
+    return units
 
 
 def merge_bricks_reference(volumes_tw):
@@ -282,12 +467,14 @@ def shard_views(num_views: int, rank: int, world_size: int):
 class TSDF:
     """Stage class with the reference's surface (gs2mesh_utils/tsdf_utils.py:23-142)."""
 
-    def __init__(self, renderer, stereo, args, out_name, *, window_resolution: int = 512, device=None):
+    def __init__(self, renderer, stereo, args, out_name, *, window_resolution: int = 512, device=None,
+                 pool_bricks: Optional[int] = None):
         self.model_name = getattr(stereo, "model_name", "rendered")  # tsdf_utils.py:34
         self.renderer = renderer
         self.out_name = out_name
         self.args = args
-        self.window_resolution = window_resolution
+        self.window_resolution = window_resolution  # only the window dense read-backs look at; the volume is unbounded
+        self.pool_bricks = pool_bricks
         self.device = device or getattr(renderer, "device", "cuda")
         self.volume: Optional[TSDFVolume] = None
         self.mesh = None
@@ -300,7 +487,7 @@ class TSDF:
         voxel_length = float(self._arg("TSDF_voxel", 2)) / 512  # tsdf_utils.py:51
         origin, count = default_window(self.window_resolution)
         return TSDFVolume(voxel_length, float(self._arg("TSDF_sdf_trunc", 0.04)), origin, count, with_color=True,
-                          device=self.device)
+                          device=self.device, pool_bricks=self.pool_bricks)
 
     @staticmethod
     def _view_list(value):
@@ -336,8 +523,10 @@ class TSDF:
             frame = getter(camera_number)
         out_dir = self.renderer.render_folder_name(camera_number)
         obj_mask = occ_mask = None
-        if frame is not None:
+        have_mem = frame is not None and "left_u8" in frame and "depth" in frame
+        if have_mem:
             rgb, depth = frame["left_u8"], frame["depth"]
+            occ_mask = frame.get("occlusion_mask")  # handed over by the stereo stage (Renderer.put_stereo_outputs)
         else:
             from PIL import Image
 
@@ -351,7 +540,7 @@ class TSDF:
                                               int(self._arg("TSDF_erosion_kernel_size", 10)), invert, device=self.device)
             else:
                 obj_mask = ~m if invert else m
-        if self._arg("TSDF_use_occlusion_mask", True) and frame is None:
+        if self._arg("TSDF_use_occlusion_mask", True) and not have_mem:
             occ_path = os.path.join(out_dir, f"out_{self.model_name}", "occlusion_mask.npy")
             if os.path.exists(occ_path):
                 occ_mask = np.load(occ_path).astype(bool)
@@ -376,8 +565,24 @@ class TSDF:
                               left_camera["cy"], np.linalg.inv(extrinsic))  # :106-107
 
     def run(self, visualize=False, views: Optional[Sequence[int]] = None):
-        """tsdf_utils.py:39-110.  `views` restricts the loop (used for view sharding across ranks)."""
+        """tsdf_utils.py:39-110.  `views` restricts the loop (used for view sharding across ranks).  The volume is unbounded
+        like Open3D's; if the brick pool turns out too small it is doubled and the loop repeated."""
+        check = getattr(self.renderer, "check_status", None)
+        if check is not None and getattr(self.renderer, "_ready", False):
+            torch.cuda.synchronize()
+            check()  # no frame of the renderer's cache came out of an overflowed binning scratch
         self.volume = self._make_volume()
+        for _attempt in range(8):
+            self._fuse_views(views)
+            if self.volume.ensure_capacity():
+                break
+            self.volume.reset()
+        else:
+            raise RuntimeError("TSDF.run: the brick pool kept overflowing")
+        self.mesh = None
+        return self.volume
+
+    def _fuse_views(self, views):
         for camera_number, left_camera in enumerate(self.renderer.left_cameras):
             if views is not None and camera_number not in views:
                 continue
@@ -391,8 +596,6 @@ class TSDF:
                 m = self.volume._u8(m if isinstance(m, torch.Tensor) else np.asarray(m).astype(np.uint8))
                 mask = m if mask is None else mask * m
             self.integrate(depth, rgb, left_camera, mask=mask)
-        self.mesh = None
-        return self.volume
 
     def extract_mesh(self):
         """`volume.extract_triangle_mesh()` + scale + vertex normals (tsdf_utils.py:108-110)."""

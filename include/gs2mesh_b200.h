@@ -82,12 +82,19 @@ int gsb_profile_collect(double* total_ms, uint64_t* samples, int n_stages);
 /* A/B overrides of the library defaults, for tests and profiling (0 in a field = library default, which the
  * environment variables GSB_RENDER_IMPL / GSB_PRE_SH may also change):
  *   bits 8..10  blend kernel: 1 block (one barrier per 256-record batch), 2 warp (per-warp bit scan), 3 compact
- *               (per-warp compacted hit list, 8x4 pixels per warp), 4 dual (compact, 8x8 pixels per warp; default)
+ *               (per-warp compacted hit list, 8x4 pixels per warp), 4 dual (compact, 8x8 pixels per warp), 5 table (dual
+ *               with per-column / per-row exponent tables, packed f32x2 and predicated accumulation; default, needs
+ *               GSB_RASTER_FAST_EXP -- without it the dual kernel runs)
  *   bits 12..13 SH staging of full-degree blocks: 1 scalar reads, 2 16-byte reads (default), 3 per-lane bulk copies
  *               into padded slots + 16-byte reads
- * All variants produce the same transmittance bit for bit; colours differ by accumulation rounding only. */
+ * Variants 1-4 produce the same transmittance bit for bit (colours differ by accumulation rounding only); 5 rounds the
+ * exponent differently (~1e-6 relative on alpha). */
 #define GSB_RASTER_RENDER_IMPL(n) (((uint32_t)(n) & 7u) << 8)
 #define GSB_RASTER_SH_MODE(n) (((uint32_t)(n) & 3u) << 12)
+#define GSB_RASTER_PAIR_SHARED_DEPTH 64u /* gsb_raster_forward_pair only (left->flags): the caller asserts that both eyes see
+                                         every Gaussian at the same view depth, i.e. viewmatrix[2], [6], [10], [14] are
+                                         bitwise equal in the two argument blocks; ONE depth sort then serves both eyes.
+                                         Verified on the device: a mismatch sets num_rendered[3].                 */
 #define GSB_RASTER_ASYNC 16u          /* never wait for the stream: an undersized workspace is then
                                          reported through num_rendered[2] instead of the return
                                          value                                                 */
@@ -123,7 +130,8 @@ typedef struct GsbRasterArgs {
   /* num_rendered: int64[4] written asynchronously on `stream` (device or pinned host memory);
      [0] = instances actually binned, [1] = reference-equivalent count (sum of tile rectangles,
      what rasterize_points.cu:114 returns), [2] = 1 if the frame needed more than max_instances
-     (outputs invalid), [3] = reserved (0).  May be NULL.                                  */
+     (outputs invalid), [3] = 1 if gsb_raster_forward_pair found view depths that differ between the
+     eyes (outputs invalid; always 0 for gsb_raster_forward).  May be NULL.                 */
   int64_t* num_rendered;
   /* caller-owned scratch */
   void* workspace;             /* device, >= gsb_raster_workspace_bytes(...)        */
@@ -144,6 +152,21 @@ size_t gsb_raster_workspace_bytes(int32_t P, int32_t width, int32_t height, int6
 int gsb_raster_forward(const GsbRasterArgs* args, void* stream);
 int64_t gsb_raster_required_instances(void);
 
+/* Both eyes of a stereo pair in one call -- what Renderer.render_image_pair (renderer_utils.py:378-389) does with two
+ * back-to-back forward calls on the same Gaussian cloud.  The Gaussian parameters are read ONCE (one fused preprocess
+ * pass projects, bins and shades every Gaussian for both cameras).  With GSB_RASTER_PAIR_SHARED_DEPTH in left->flags the
+ * Gaussians are also depth-sorted ONCE: the eyes of a rig share the camera rotation and differ by a translation along the
+ * camera x axis (transformation_utils.py:219-223), so a Gaussian's view depth is the same float in both eyes whenever
+ * viewmatrix[2], [6], [10], [14] are bitwise equal (about 4 of 5 rigs built like renderer_utils.py:178-206; the right
+ * camera's rotation goes through a float32 Euler round trip, which moves an entry by one ulp in the others).  The kernel
+ * verifies the claim: if some Gaussian's depth differs, num_rendered[3] of both eyes is set to 1 and the frames must be
+ * rendered again without the flag.
+ * Requirements: same P / tensors / SH settings / image size in both argument blocks, separate outputs and workspaces.
+ * stream_right may be NULL (= stream_left); otherwise the right eye's binning and blending are enqueued on it, ordered
+ * after the shared part by an event, so the two eyes overlap like two independent calls would.
+ * Results are bit-identical to two gsb_raster_forward calls. */
+int gsb_raster_forward_pair(const GsbRasterArgs* left, const GsbRasterArgs* right, void* stream_left, void* stream_right);
+
 /* Frustum test only (rasterizer.h:23-28 markVisible): present[i] = z_view > 0.2. */
 int gsb_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                             uint8_t* present, void* stream);
@@ -159,23 +182,31 @@ int gsb_image_to_u8(const float* chw, int32_t width, int32_t height, uint8_t* hw
 #define GSB_BRICK 16               /* Open3D volume_unit_resolution default               */
 #define GSB_BRICK_VOXELS 4096
 
-/* A bounded window of Open3D's ScalableTSDFVolume lattice: bricks (= Open3D "volume units",
- * 16^3 voxels, unit_length = 16*voxel_length) with integer indices brick_origin + [0, brick_count)
- * per axis.  Voxel (bx,by,bz | x,y,z) has its centre at
+/* Open3D's ScalableTSDFVolume on the GPU: an UNBOUNDED set of bricks (= Open3D "volume units", 16^3 voxels,
+ * unit_length = 16*voxel_length) addressed by their integer lattice index (bx,by,bz) through a device hash table and
+ * stored in a brick pool, opened on first touch like Open3D's unordered_map<Vector3i, VolumeUnit>
+ * (tsdf_utils.py:53-56: no origin, no extent).  Voxel (bx,by,bz | x,y,z) has its centre at
  *     (brick_index * 16 + xyz + 0.5) * voxel_length
- * i.e. exactly on Open3D's lattice.  Storage ("brick layout"): bricks row-major over
- * (bx,by,bz); inside a brick voxels at x*256 + y*16 + z (UniformTSDFVolume::IndexOf).
- * All arrays are caller-allocated device memory, zero-initialised by the caller. */
+ * i.e. exactly on Open3D's lattice; inside a brick voxels sit at x*256 + y*16 + z (UniformTSDFVolume::IndexOf).
+ * All arrays are caller-allocated device memory (the library never allocates):
+ *   tsdf_weight / color / brick_index / hash_vals / hash_stamp / brick_list / counters zero-initialised,
+ *   hash_keys initialised to all-ones bytes (0xFF).
+ * Lattice indices must lie in [-2^20, 2^20) per axis.  When the pool is exhausted further bricks are dropped and counted
+ * (gsb_tsdf_last_stats); the caller grows the pool and integrates again. */
 typedef struct GsbVolumeDesc {
-  int32_t brick_origin[3];
-  int32_t brick_count[3];
   double voxel_length;
   double sdf_trunc;
-  float* tsdf_weight;     /* device [n_bricks*4096*2]  (tsdf, weight) interleaved            */
-  float* color;           /* device [n_bricks*4096*4]  (r,g,b,unused) running mean, or NULL  */
-  uint32_t* brick_stamp;  /* device [n_bricks]   last frame id that touched the brick        */
-  uint32_t* brick_list;   /* device [n_bricks]   scratch: bricks touched by the current frame */
-  uint32_t* counters;     /* device [8]          scratch counters                            */
+  uint32_t pool_bricks;    /* capacity of the brick pool                                              */
+  uint32_t hash_slots;     /* power of two >= 2 * pool_bricks                                         */
+  float* tsdf_weight;      /* device [pool_bricks*4096*2]  (tsdf, weight) interleaved, per pool slot   */
+  float* color;            /* device [pool_bricks*4096*4]  (r,g,b,unused) running mean, or NULL        */
+  int32_t* brick_index;    /* device [pool_bricks*4]   lattice index (bx,by,bz,0) of every pool slot   */
+  uint64_t* hash_keys;     /* device [hash_slots]      packed lattice index, all-ones = empty          */
+  uint32_t* hash_vals;     /* device [hash_slots]      pool slot of the entry                          */
+  uint32_t* hash_stamp;    /* device [hash_slots]      last frame id that queued the entry             */
+  uint32_t* brick_list;    /* device [hash_slots]      scratch: entries touched by the current frame   */
+  uint32_t* counters;      /* device [8]  [0] entries queued this frame, [1] bricks dropped this frame,
+                                          [4] pool slots in use, [5] bricks dropped since creation     */
 } GsbVolumeDesc;
 
 typedef struct GsbVolume GsbVolume; /* opaque; owns no device memory */
@@ -206,39 +237,84 @@ int gsb_mask_morphology(const uint8_t* mask_in, int32_t width, int32_t height, i
 int gsb_tsdf_integrate(GsbVolume* vol, const float* depth, const uint8_t* rgb, int32_t width, int32_t height, double fx,
                        double fy, double cx, double cy, const double* extrinsic_w2c, void* stream);
 
-/* Cross-rank merge support (view-sharded multi-GPU): convert (mean, weight) -> (sum, weight)
- * before an NCCL SUM reduce of tsdf_weight (and color), and back afterwards. */
+/* Block discovery only (T1): opens the bricks the frame would touch without updating any voxel.  Lets a caller that must
+ * never lose a brick (the Open3D-shaped facade) check gsb_tsdf_last_stats and grow the pool BEFORE integrating. */
+int gsb_tsdf_touch(GsbVolume* vol, const float* depth, int32_t width, int32_t height, double fx, double fy, double cx, double cy,
+                   const double* extrinsic_w2c, void* stream);
+
+/* (mean, weight) <-> (sum, weight) of every pool slot in use / of the listed pool slots (device uint32[n_bricks]);
+ * to_sums != 0: (mean,w) -> (sum,w).  Building blocks of the cross-rank merge below. */
 int gsb_tsdf_to_sums(GsbVolume* vol, void* stream);
 int gsb_tsdf_from_sums(GsbVolume* vol, void* stream);
-/* Same conversion restricted to the listed bricks (device uint32[n_bricks]); to_sums != 0: (mean,w) -> (sum,w).
- * Used by the sparse merge, which only exchanges the bricks some rank has touched. */
 int gsb_tsdf_sums_bricks(GsbVolume* vol, int to_sums, const uint32_t* bricks, uint32_t n_bricks, void* stream);
 
-/* Brick layout -> dense x*N^2... linear grids (dims = brick_count*16), for consumers that want
- * Open3D UniformTSDFVolume indexing.  tsdf / weight: device float [nx*ny*nz]. */
-int gsb_tsdf_export_dense(const GsbVolume* vol, float* tsdf, float* weight, void* stream);
+/* Lattice indices (device int32[n*4]: bx,by,bz,unused) -> pool slots (device uint32[n]; 0xFFFFFFFF = not in the volume).
+ * insert != 0 opens missing bricks (zero-filled) like a touch by integrate would.  `scratch` = device uint32[n]. */
+int gsb_tsdf_find_bricks(GsbVolume* vol, const int32_t* indices, uint32_t n, int insert, uint32_t* slots, uint32_t* scratch,
+                         void* stream);
 
-/* Statistics of the last integrate call, read back asynchronously into `out` (device or pinned
- * host, uint32[4]): [0] bricks touched, [1] bricks outside the window, [2] frame id. */
+/* A window of the lattice (bricks brick_origin + [0, brick_count) per axis, host int32[3] each) as dense x*NY*NZ + y*NZ + z
+ * grids with dims = brick_count*16, for consumers that want Open3D UniformTSDFVolume indexing; bricks that were never
+ * opened read as (0, 0).  tsdf / weight: device float [nx*ny*nz], either may be NULL. */
+int gsb_tsdf_export_dense(const GsbVolume* vol, const int32_t* brick_origin, const int32_t* brick_count, float* tsdf,
+                          float* weight, void* stream);
+
+/* Statistics, read back asynchronously into `out` (device or pinned host, uint32[8]): [0] bricks touched by the last
+ * integrate, [1] bricks it had to drop (pool exhausted / index out of range), [2] frame id, [3] pool slots in use,
+ * [4] bricks dropped since creation. */
 int gsb_tsdf_last_stats(const GsbVolume* vol, uint32_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU merge of view-sharded volumes (SURVEY.md 8(b) seam 2, 8(e)): ONE call per rank,
+ *     gsb_tsdf_reduce(vol, comm, root, scratch, scratch_bytes, stream)
+ * enqueues, on `stream`,
+ *   1. an ncclAllGather of every rank's brick lattice indices (fixed-size message, no host round trip),
+ *   2. the insertion of the other ranks' bricks into this rank's hash (the receiving ranks open them zero-filled),
+ *   3. an ncclBroadcast of the root's brick order (the canonical order of the exchange),
+ *   4. one fused pack kernel: (mean,w) -> (sum,w) of every brick, gathered in canonical order into `scratch`,
+ *   5. ONE ncclReduce (root >= 0) / ncclAllReduce (root < 0) of the packed buffer,
+ *   6. one fused unpack kernel on the receiving rank(s): (sum,w) -> (mean,w) back into the pool.
+ * The only host synchronisation is the read of one 32-bit word (the size of the union, which NCCL needs as a count).
+ * `comm` is an ncclComm_t (from gsb_comm_create or any other owner); NCCL is resolved from the process at run time
+ * (the libnccl.so.2 torch already loaded), the library does not link against it.
+ * scratch: device, >= gsb_tsdf_reduce_scratch_bytes(vol, nranks, bricks in the union) bytes. */
+size_t gsb_tsdf_reduce_scratch_bytes(const GsbVolume* vol, int nranks, uint32_t union_bricks);
+/* Returns GSB_ERR_WORKSPACE when `scratch` cannot hold the packed union (known only after the index exchange);
+ * gsb_tsdf_reduce_required_bytes() then tells the size to retry with.  The required size is the same on every rank, so
+ * ranks that pass equally sized scratch blocks take the same decision (a collective must not be entered by some ranks
+ * only); a retry repeats the cheap index exchange.  root >= 0: ncclReduce to `root` (only its volume is changed);
+ * root < 0: ncclAllReduce (every rank ends with the merged volume). */
+int gsb_tsdf_reduce(GsbVolume* vol, void* nccl_comm, int nranks, int rank, int root, void* scratch, size_t scratch_bytes,
+                    void* stream);
+size_t gsb_tsdf_reduce_required_bytes(void);
+/* Communicator helpers (thin wrappers of ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy): rank 0 creates the
+ * 128-byte id, distributes it by any means (torch.distributed broadcast in gs2mesh_b200/tsdf.py), every rank calls
+ * gsb_comm_create with it; returns the ncclComm_t as an opaque pointer (NULL on failure, see gsb_last_error). */
+int gsb_comm_unique_id(void* id128);
+void* gsb_comm_create(const void* id128, int nranks, int rank);
+void gsb_comm_destroy(void* nccl_comm);
 
 /* ------------------------------------------------------------------------------------------
  * Mesh extraction: volume.extract_triangle_mesh() + compute_vertex_normals()
  * (gs2mesh_utils/tsdf_utils.py:108-110; Open3D ScalableTSDFVolume::ExtractTriangleMesh)
  * ------------------------------------------------------------------------------------------
- * Marching cubes over the bricks listed in `bricks` (device uint32[n_bricks], normally every brick with
- * a non-zero stamp).  A cube is skipped when any of its 8 corners has weight 0; corners are inside when
- * tsdf < 0.  Vertices are identified by an edge key = ((gx*NY + gy)*NZ + gz)*3 + axis over the window's
- * voxel grid; the caller sorts/uniques the keys (that is the de-duplication Open3D does with a hash map)
- * and asks for the attributes of the unique edges.
+ * Marching cubes over the pool slots listed in `bricks` (device uint32[n_bricks], normally every slot in use).
+ * A cube is skipped when any of its 8 corners has weight 0 (corners in bricks that were never opened count as
+ * weight 0, like Open3D's hash-map miss); corners are inside when tsdf < 0.  Vertices are identified by an edge
+ * key = ((gx*NY + gy)*NZ + gz)*3 + axis over the voxel grid of `window` (host int32[6]: brick origin, brick count of a
+ * box containing every listed brick and its +1 neighbours, e.g. the bounding box of the pool + 1); the caller
+ * sorts/uniques the keys (that is the de-duplication Open3D does with a hash map) and asks for the attributes of the
+ * unique edges.
  *   gsb_mesh_count    tri_counts[b]  = triangles produced by brick b
  *   gsb_mesh_emit     edge_keys[3*t..3*t+2] for every triangle, brick b writing from tri_offsets[b]
  *   gsb_mesh_vertices xyz (fp64, Open3D's interpolation) and rgb in [0,1] (or NULL) of n unique keys
  *   gsb_mesh_vertex_normals area-weighted vertex normals (fp64 [n_vertices,3]) of an indexed mesh */
-int gsb_mesh_count(const GsbVolume* vol, const uint32_t* bricks, uint32_t n_bricks, uint32_t* tri_counts, void* stream);
-int gsb_mesh_emit(const GsbVolume* vol, const uint32_t* bricks, uint32_t n_bricks, const int64_t* tri_offsets, int64_t* edge_keys,
-                  void* stream);
-int gsb_mesh_vertices(const GsbVolume* vol, const int64_t* keys, int64_t n, double* xyz, float* rgb, void* stream);
+int gsb_mesh_count(const GsbVolume* vol, const int32_t* window, const uint32_t* bricks, uint32_t n_bricks, uint32_t* tri_counts,
+                   void* stream);
+int gsb_mesh_emit(const GsbVolume* vol, const int32_t* window, const uint32_t* bricks, uint32_t n_bricks, const int64_t* tri_offsets,
+                  int64_t* edge_keys, void* stream);
+int gsb_mesh_vertices(const GsbVolume* vol, const int32_t* window, const int64_t* keys, int64_t n, double* xyz, float* rgb,
+                      void* stream);
 int gsb_mesh_vertex_normals(const double* xyz, int64_t n_vertices, const int64_t* triangles, int64_t n_triangles, double* normals,
                             void* stream);
 

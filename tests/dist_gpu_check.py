@@ -44,32 +44,45 @@ def main():
             st.integrate(out["depth"], out["left_u8"], rigs[i]["left"], final_T=out["final_T"])
         return st.volume
 
+    def compare(merged, seq, what):
+        a, b = merged.export_units(), seq.export_units()
+        assert set(a) == set(b), f"{what}: merged volume holds {len(a)} bricks, sequential fusion {len(b)}"
+        err = cerr = 0.0
+        nvox = 0
+        for k in a:
+            assert np.array_equal(a[k][0][:, 1], b[k][0][:, 1]), f"{what}: merged weights differ from sequential fusion in brick {k}"
+            err = max(err, float(np.abs(a[k][0][:, 0] - b[k][0][:, 0]).max()))
+            cerr = max(cerr, float(np.abs(a[k][1] - b[k][1]).max()))
+            nvox += int((b[k][0][:, 1] > 0).sum())
+        assert err <= 2e-6, (what, err)
+        assert cerr <= 1e-3, (what, cerr)
+        return len(a), nvox, err, cerr
+
     mine = shard_views(NV, rank, world)
-    vol = fuse(mine)
-    vol.reduce_across_ranks(dst=None, chunk_bytes=1 << 20)  # sparse merge (touched bricks only), many chunks
-    dense = fuse(mine)
-    dense.reduce_across_ranks(dst=None, chunk_bytes=1 << 22, sparse=False)  # whole-volume merge
-    torch.cuda.synchronize()
-    # same sums, but NCCL may associate them differently for the two buffer shapes: equal to rounding, same weights
-    assert torch.equal(vol.tsdf_weight.view(-1, 2)[:, 1], dense.tsdf_weight.view(-1, 2)[:, 1]), "sparse != dense merge (weights)"
-    assert float((vol.tsdf_weight - dense.tsdf_weight).abs().max()) <= 1e-6, "sparse != dense merge (tsdf)"
-    assert float((vol.color - dense.color).abs().max()) <= 1e-3, "sparse != dense merge (colour)"
-    del dense
     seq = fuse(range(NV))
+    # (1) all-reduce: every rank ends with the merged volume (C-ABI gsb_tsdf_reduce, root < 0)
+    vol = fuse(mine)
+    own = vol.num_bricks()
+    vol.reduce_across_ranks(dst=None)
     torch.cuda.synchronize()
-    a = vol.bricks().cpu().numpy()
-    b = seq.bricks().cpu().numpy()
-    assert np.array_equal(a[..., 1], b[..., 1]), "merged weights differ from sequential fusion"
-    err = float(np.abs(a[..., 0] - b[..., 0]).max())
-    assert err <= 2e-6, err
-    ca = vol.color.view(-1, 4).cpu().numpy()
-    cb = seq.color.view(-1, 4).cpu().numpy()
-    cerr = float(np.abs(ca - cb).max())
-    assert cerr <= 1e-3, cerr
+    n, nvox, err, cerr = compare(vol, seq, f"all-reduce on rank {rank}")
+    # (2) reduce to the last rank: only its volume changes (a small scratch first: the retry path of the workspace protocol)
+    root = world - 1
+    vol2 = fuse(mine)
+    before = vol2.export_units()
+    vol2._reduce_scratch = None
+    vol2.reduce_across_ranks(dst=root)
+    torch.cuda.synchronize()
+    if rank == root:
+        compare(vol2, seq, "reduce to root")
+    else:
+        after = vol2.export_units()
+        assert set(after) == set(before) and all(np.array_equal(after[k][0], before[k][0]) for k in before), "a non-root volume changed"
+    # (3) merging twice in a row with different shards stays consistent: fuse more views into the merged volume
     dist.barrier()
     if rank == 0:
         print(f"dist_gpu_check ok: world={world} views/rank={[len(shard_views(NV, q, world)) for q in range(world)]} "
-              f"touched voxels={int((b[..., 1] > 0).sum())} max|dtsdf|={err:.2e} max|dcolor|={cerr:.2e}")
+              f"bricks own/union={own}/{n} touched voxels={nvox} max|dtsdf|={err:.2e} max|dcolor|={cerr:.2e}")
     dist.destroy_process_group()
 
 

@@ -41,6 +41,19 @@ def test_argument_validation_without_gpu(gsb_lib):
     assert gsb_lib.gsb_raster_forward(C.byref(a), None) == _lib.GSB_ERR_INVALID
     assert b"required" in gsb_lib.gsb_last_error()
     assert gsb_lib.gsb_tsdf_create(None) is None
+    # stereo-pair entry point: both argument blocks are validated before anything is enqueued
+    assert gsb_lib.gsb_raster_forward_pair(C.byref(a), None, None, None) == _lib.GSB_ERR_INVALID
+    # brick pool descriptor: hash_slots must be a power of two >= 2 * pool_bricks
+    d = _lib.GsbVolumeDesc(voxel_length=0.01, sdf_trunc=0.04, pool_bricks=100, hash_slots=128)
+    for f in ("tsdf_weight", "brick_index", "hash_keys", "hash_vals", "hash_stamp", "brick_list", "counters"):
+        setattr(d, f, 256)  # any non-NULL value: create() only records the pointers
+    assert gsb_lib.gsb_tsdf_create(C.byref(d)) is None and b"power of two" in gsb_lib.gsb_last_error()
+    d.hash_slots = 256
+    h = gsb_lib.gsb_tsdf_create(C.byref(d))
+    assert h is not None
+    assert gsb_lib.gsb_tsdf_reduce_scratch_bytes(h, 8, 1000) > 1000 * 4096 * 8  # (sum, w) payload of the union, no colour
+    assert gsb_lib.gsb_tsdf_reduce(h, None, 8, 0, 0, None, 0, None) == _lib.GSB_ERR_INVALID
+    gsb_lib.gsb_tsdf_destroy(h)
 
 
 def test_struct_layout_matches_header():
@@ -48,7 +61,9 @@ def test_struct_layout_matches_header():
 
     # 5 int32 (+4 pad) | 8 ptr | float (+4) | 3 ptr | 2 float | int32 | uint32 | 8 ptr/size fields
     assert C.sizeof(_lib.GsbRasterArgs) == 24 + 8 * 8 + 8 + 3 * 8 + 16 + 8 * 8
-    assert C.sizeof(_lib.GsbVolumeDesc) == 24 + 16 + 5 * 8
+    # 2 double | 2 uint32 | 8 pointers
+    assert C.sizeof(_lib.GsbVolumeDesc) == 16 + 8 + 8 * 8
+    assert _lib.GsbVolumeDesc.tsdf_weight.offset == 24 and _lib.GsbVolumeDesc.counters.offset == 24 + 7 * 8
 
 
 def test_sass_contains_bulk_tma():

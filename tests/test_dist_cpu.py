@@ -30,13 +30,16 @@ def _views():
 
 
 def _fuse(orc, idxs):
+    """{(bx,by,bz): (tsdf, weight)[4096,2]} of the units the CPU oracle opens for these views."""
     views = _views()
     vol = orc.OracleTSDFVolume(VL, TRUNC, with_color=False)
     for i in idxs:
         vol.integrate(views[i][0], None, W, H, FX, FY, CX, CY, views[i][1])
-    tw, _, outside = vol.export_bricks(B0, NB)
-    assert outside == 0
-    return tw
+    out = {}
+    for i, k in enumerate(vol.unit_indices()):
+        t, w, _ = vol.unit_data(i)
+        out[tuple(int(v) for v in k)] = np.stack([t, w], -1)
+    return out
 
 
 def _worker(rank, world, port, q):
@@ -45,16 +48,14 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from gs2mesh_b200.tsdf import reduce_sum_chunked, shard_views
+        from gs2mesh_b200.tsdf import merge_units_protocol, shard_views
         from oracle import oracle as orc
 
         mine = shard_views(N_VIEWS, rank, world)
-        tw = _fuse(orc, mine)
-        sums = torch.from_numpy(np.stack([tw[..., 0] * tw[..., 1], tw[..., 1]], -1).copy())  # (mean,w) -> (sum,w)
-        reduce_sum_chunked([sums, None], chunk_bytes=1 << 16)  # many small chunks on purpose
-        s = sums.numpy()
-        mean = np.where(s[..., 1] > 0, s[..., 0] / np.maximum(s[..., 1], 1e-30), 0).astype(np.float32)
-        q.put((rank, mine, mean, s[..., 1].copy()))
+        units = _fuse(orc, mine)
+        merged_all = merge_units_protocol(units, dst=None)   # all-reduce: every rank ends with the union
+        merged_root = merge_units_protocol(units, dst=1)     # reduce to rank 1: rank 0's volume is untouched
+        q.put((rank, mine, sorted(units), merged_all, merged_root))
     finally:
         dist.destroy_process_group()
 
@@ -88,8 +89,21 @@ def test_two_rank_gloo_merge_equals_sequential(oracle):
         p.join(timeout=60)
         assert p.exitcode == 0
     seq = _fuse(oracle, range(N_VIEWS))
-    shards = {r: m for r, m, _, _ in results}
-    assert sorted(shards[0] + shards[1]) == list(range(N_VIEWS))
-    for _, _, mean, weight in results:  # all-reduce: every rank holds the merged volume
-        np.testing.assert_array_equal(weight, seq[..., 1])
-        np.testing.assert_allclose(mean, seq[..., 0], atol=1e-6)
+    by_rank = {r: rest for r, *rest in results}
+    assert sorted(by_rank[0][0] + by_rank[1][0]) == list(range(N_VIEWS))
+    own0, own1 = set(by_rank[0][1]), set(by_rank[1][1])
+    assert own0 != own1 and own0 | own1 == set(seq), "the two shards open different unit sets whose union is the sequential one"
+
+    def same(merged):
+        assert set(merged) == set(seq)
+        for k in seq:
+            np.testing.assert_array_equal(merged[k][:, 1], seq[k][:, 1])
+            np.testing.assert_allclose(merged[k][:, 0], seq[k][:, 0], atol=1e-6)
+
+    for r in (0, 1):  # all-reduce: every rank holds the merged volume
+        same(by_rank[r][2])
+    same(by_rank[1][3])  # reduce to rank 1
+    assert set(by_rank[0][3]) == own0  # ... leaves rank 0 with what it had
+    own_units = _fuse(oracle, by_rank[0][0])
+    for k in own0:
+        np.testing.assert_array_equal(by_rank[0][3][k], own_units[k])

@@ -10,6 +10,21 @@ from tests.test_gpu_tsdf import B0, CX, CY, FX, FY, H, NB, TRUNC, VL, W, _gpu_vo
 pytestmark = pytest.mark.gpu
 
 
+def _rekey(mesh, b0, nb):
+    """mesh.edge_keys index voxels inside mesh.key_window (the bounding box of the open bricks); re-express them inside the
+    window (b0, nb) the oracle mesh was extracted from."""
+    (k0, kn) = mesh.key_window
+    key = mesh.edge_keys.astype(np.int64)
+    axis = key % 3
+    lin = key // 3
+    ny, nz = kn[1] * 16, kn[2] * 16
+    gz = lin % nz
+    gy = (lin // nz) % ny
+    gx = lin // (nz * ny)
+    gx, gy, gz = gx + (k0[0] - b0[0]) * 16, gy + (k0[1] - b0[1]) * 16, gz + (k0[2] - b0[2]) * 16
+    return ((gx * (nb[1] * 16) + gy) * (nb[2] * 16) + gz) * 3 + axis
+
+
 def _canon(tris):
     """triangles as a set of rotation-canonical key triples"""
     out = set()
@@ -31,14 +46,16 @@ def test_mesh_matches_open3d_restatement(oracle, gsb_lib, cuda_device):
     torch.cuda.synchronize()
     mesh = extract_triangle_mesh(gvol)
     tw = gvol.bricks().cpu().numpy()
-    col = gvol.color.view(-1, 4096, 4).cpu().numpy()
+    col = gvol.colors().cpu().numpy()
     ref = oracle.extract_mesh_from_bricks(tw, B0, NB, VL, color=col)
     assert len(ref["triangles"]) > 2000
 
     nx, ny, nz = (n * 16 for n in NB)
     ref_key = ((ref["keys"][:, 0] * ny + ref["keys"][:, 1]) * nz + ref["keys"][:, 2]) * 3 + ref["keys"][:, 3]
     order = np.argsort(ref_key)
-    np.testing.assert_array_equal(mesh.edge_keys, ref_key[order])  # same vertex set (sorted edge keys)
+    mine = _rekey(mesh, B0, NB)
+    assert (np.diff(mine) > 0).all()  # both windows are row-major over (x, y, z): the vertex order is the same
+    np.testing.assert_array_equal(mine, ref_key[order])  # same vertex set (sorted edge keys)
     np.testing.assert_allclose(mesh.vertices, ref["vertices"][order], rtol=0, atol=1e-12)
     np.testing.assert_allclose(mesh.vertex_colors, ref["colors"][order], atol=2e-6)
     rank = np.empty(len(order), np.int64)

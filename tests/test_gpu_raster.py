@@ -244,7 +244,7 @@ def test_fast_exp_stays_inside_parity_budget(oracle, gsb_lib, cuda_device):
 
 @pytest.mark.parametrize("fast", [False, True])
 def test_blend_kernel_variants_agree(gsb_lib, cuda_device, fast):
-    """block / warp / compact / dual blend kernels decide the three thresholds of forward.cu:336-353 on the same
+    """block / warp / compact / dual (and, up to the rounding of alpha, table) blend kernels decide the three thresholds of forward.cu:336-353 on the same
     alpha and T values: the transmittance image is bit-identical; colour and depth differ only by the rounding of
     fma(c, alpha*T, C) vs fma(c*alpha, T, C)."""
     from gs2mesh_b200 import _lib
@@ -256,10 +256,20 @@ def test_blend_kernel_variants_agree(gsb_lib, cuda_device, fast):
         outs = {name: _ours(cuda_device, inp, flags=base | _lib.RASTER_RENDER_IMPL(name)) for name in _lib.RENDER_IMPLS}
         ref = outs["warp"]
         for name, out in outs.items():
+            if name == "table" and fast:
+                # the table kernel (default) evaluates the exponent in the log2 domain from per-column / per-row terms:
+                # same thresholds, different rounding of alpha (~1e-6 relative) -> compared like against the reference
+                for k in ("color", "final_T", "depth"):
+                    cmp = compare_images(out[k], ref[k])
+                    assert cmp["frac_bad"] <= BUDGET and cmp["median"] <= 2e-6, (name, k, cmp)
+                np.testing.assert_array_equal(out["counts"], ref["counts"], err_msg=f"counts {name}")
+                continue
             np.testing.assert_array_equal(out["final_T"], ref["final_T"], err_msg=f"final_T {name}")
             np.testing.assert_array_equal(out["counts"], ref["counts"], err_msg=f"counts {name}")
             np.testing.assert_allclose(out["color"], ref["color"], rtol=0, atol=5e-6, err_msg=f"color {name}")
             np.testing.assert_allclose(out["depth"], ref["depth"], rtol=5e-6, atol=1e-6, err_msg=f"depth {name}")
+        if not fast:  # without GSB_RASTER_FAST_EXP the table variant is the dual kernel
+            np.testing.assert_array_equal(outs["table"]["color"], outs["dual"]["color"])
         np.testing.assert_array_equal(outs["compact"]["color"], outs["dual"]["color"])  # same arithmetic per pixel
         np.testing.assert_array_equal(outs["block"]["color"], outs["warp"]["color"])
 

@@ -89,14 +89,10 @@ def test_brick_volume_bit_exact_vs_oracle(oracle, gsb_lib, cuda_device):
     np.testing.assert_array_equal(got[..., 0], tw[..., 0])  # tsdf, bit-exact
     assert (got[alloc == 0] == 0).all()  # bricks Open3D would not allocate stay untouched
     assert (tw[..., 1] > 0).sum() > 10000
-    # colour: fp32 running mean vs Open3D's fp64
-    col = gvol.color.view(-1, 4096, 4).cpu().numpy()
-    units = ovol.unit_indices()
-    for i in range(0, ovol.num_units, 7):
-        _, w, c = ovol.unit_data(i)
-        b = units[i] - np.array(B0)
-        brick = (b[0] * NB[1] + b[1]) * NB[2] + b[2]
-        np.testing.assert_allclose(col[brick, :, :3][w > 0], c[w > 0], rtol=1e-5, atol=1e-3)
+    # unit by unit, keyed by lattice index; colour: fp32 running mean vs Open3D's fp64
+    from tests.volume_compare import assert_units_equal
+
+    assert assert_units_equal(gvol, ovol) == ovol.num_units == gvol.num_bricks()
 
 
 def test_prepare_depth_matches_reference_filters(oracle, gsb_lib, cuda_device):
@@ -146,14 +142,17 @@ def test_view_order_independence_and_sum_form_roundtrip(gsb_lib, cuda_device):
     np.testing.assert_array_equal(ta[..., 1], tb[..., 1])
     np.testing.assert_allclose(ta[..., 0], tb[..., 0], atol=2e-6)
     # sharded merge: (mean,w) -> (sum,w), add, -> (mean,w) equals the sequential volume
+    # (the two shards open different bricks in different pool slots: add them brick by brick through the view window)
     s0, s1 = fuse([0, 2, 4]), fuse([1, 3, 5])
     s0.to_sums()
     s1.to_sums()
-    s0.tsdf_weight += s1.tsdf_weight
-    s0.from_sums()
-    tm = s0.bricks().cpu().numpy()
-    np.testing.assert_array_equal(tm[..., 1], ta[..., 1])
-    np.testing.assert_allclose(tm[..., 0], ta[..., 0], atol=2e-6)
+    sums = s0.bricks().cpu().numpy() + s1.bricks().cpu().numpy()
+    wsum = sums[..., 1]
+    tm = np.where(wsum > 0, sums[..., 0] / np.maximum(wsum, 1), 0).astype(np.float32)
+    np.testing.assert_array_equal(wsum, ta[..., 1])
+    np.testing.assert_allclose(tm, ta[..., 0], atol=2e-6)
+    s0.from_sums()  # and back: (sum, w) -> (mean, w) restores the shard
+    np.testing.assert_allclose(s0.bricks().cpu().numpy(), fuse([0, 2, 4]).bricks().cpu().numpy(), atol=1e-6)
 
 
 def test_dense_export_layout(gsb_lib, cuda_device):
@@ -167,14 +166,72 @@ def test_dense_export_layout(gsb_lib, cuda_device):
     np.testing.assert_array_equal(weight.cpu().numpy(), dense[..., 1])
 
 
-def test_points_outside_window_are_counted_not_written(gsb_lib, cuda_device):
+def test_pool_exhaustion_is_counted_and_grown(gsb_lib, cuda_device):
+    """The volume is unbounded (a hash of bricks, like Open3D's); what is finite is the brick pool.  Bricks that do not fit
+    are counted, never written out of bounds; ensure_capacity() doubles the pool and reports that the batch must be fused
+    again.  The regrown volume equals one that had room from the start, and grow() keeps what was already fused."""
     from gs2mesh_b200.tsdf import TSDFVolume
 
-    depth, rgb, w2c = _views(1)[0]
-    tiny = TSDFVolume(VL, TRUNC, (0, 0, 0), (2, 2, 2), with_color=False, device=cuda_device)
-    tiny.integrate(tiny.prepare_depth(depth, W, H), None, W, H, FX, FY, CX, CY, w2c)
-    touched, outside, frame = tiny.last_stats()
-    assert outside > 0 and touched <= 8 and frame == 1
+    views = _views(3, seed=5)
+    big = _gpu_volume(cuda_device)
+    for depth, rgb, w2c in views:
+        big.integrate(big.prepare_depth(depth, W, H), rgb, W, H, FX, FY, CX, CY, w2c)
+    assert big.pool_stats()["dropped_total"] == 0
+    small = TSDFVolume(VL, TRUNC, B0, NB, with_color=True, device=cuda_device, pool_bricks=8)
+    attempts = 0
+    for attempts in range(1, 16):
+        for depth, rgb, w2c in views:
+            small.integrate(small.prepare_depth(depth, W, H), rgb, W, H, FX, FY, CX, CY, w2c)
+        if attempts == 1:
+            st = small.pool_stats()
+            assert st["dropped"] > 0 and st["dropped_total"] >= st["dropped"] and st["bricks"] <= 8
+        if small.ensure_capacity():
+            break
+        small.reset()
+    assert attempts > 1 and small.pool_bricks >= big.num_bricks() and small.num_bricks() == big.num_bricks()
+    np.testing.assert_array_equal(small.bricks().cpu().numpy(), big.bricks().cpu().numpy())
+    a, b = small.export_units(), big.export_units()
+    assert set(a) == set(b)
+    for k in a:
+        np.testing.assert_array_equal(a[k][1], b[k][1])
+    # grow() re-houses the open bricks
+    before = small.export_units()
+    small.grow()
+    after = small.export_units()
+    assert set(before) == set(after)
+    for k in before:
+        np.testing.assert_array_equal(before[k][0], after[k][0])
+        np.testing.assert_array_equal(before[k][1], after[k][1])
+    depth, rgb, w2c = views[0]
+    small.integrate(small.prepare_depth(depth, W, H), rgb, W, H, FX, FY, CX, CY, w2c)  # and stays usable
+    big.integrate(big.prepare_depth(depth, W, H), rgb, W, H, FX, FY, CX, CY, w2c)
+    np.testing.assert_array_equal(small.bricks().cpu().numpy(), big.bricks().cpu().numpy())
+
+
+def test_unbounded_volume_far_from_the_origin(oracle, gsb_lib, cuda_device):
+    """Reference semantics of tsdf_utils.py:51-56,85-93: ScalableTSDFVolume has no origin and no extent.  A scene centred at
+    (5, -3, 2) fused with TSDF_scale = 0.1 (translations / 0.1, depth_scale 0.1: lattice indices around (50, -30, 20) * 16)
+    opens exactly the oracle's units -- none dropped, none clipped -- with bit-identical voxels; likewise an off-centre
+    principal point.  Frames = the seeded ones of tests/golden/make_tsdf_golden.py."""
+    from gs2mesh_b200.tsdf import TSDFVolume
+    from tests.golden import make_tsdf_golden as g
+    from tests.volume_compare import assert_units_equal
+
+    for case in ("scaled_shifted", "offcentre"):
+        c = g.CASES[case]
+        frames = g.make_frames(case)
+        ovol = g.oracle_volume(case, frames)
+        vol = TSDFVolume(c["voxel"] / 512, c["trunc"], with_color=True, device=cuda_device, pool_bricks=4096)
+        for f in frames:
+            d, e, trunc = g.reference_filters(f["depth"], f["extrinsic"], c["scale"])
+            prepared = vol.prepare_depth(d, c["W"], c["H"], depth_scale=c["scale"], depth_trunc=trunc)
+            vol.integrate(prepared, f["rgb"], c["W"], c["H"], c["fx"], c["fy"], c["cx"], c["cy"], np.linalg.inv(e))
+        st = vol.pool_stats()
+        assert st["dropped_total"] == 0
+        n = assert_units_equal(vol, ovol)
+        assert n == st["bricks"] > 50
+        if case == "scaled_shifted":
+            assert np.abs(vol.brick_indices().cpu().numpy()).max() > 40  # nowhere near a window around the origin
 
 
 def test_invalid_inputs(gsb_lib, cuda_device):
