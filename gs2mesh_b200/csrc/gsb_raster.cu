@@ -418,8 +418,8 @@ struct WarpStage {  // one warp's staged parameter block; every member offset is
 // so a Gaussian's view depth is THE SAME float in both eyes whenever the z rows of the two view matrices are bitwise
 // equal; then one depth key per Gaussian (and one depth sort) serves both eyes.  The kernel verifies that and raises
 // counters[3] otherwise (the caller then renders the eyes separately).
-template <int kEyes>
-__global__ void __launch_bounds__(kPreThreads, kEyes == 1 ? 6 : 4) preprocess_kernel(const PreParams p) {
+template <int kEyes, int kMinBlocks>
+__global__ void __launch_bounds__(kPreThreads, kMinBlocks) preprocess_kernel(const PreParams p) {
   __shared__ __align__(128) WarpStage stage[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpStage& st = stage[warp];
@@ -773,74 +773,70 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const float4
 //                                   [2] overflow flag (R > capacity)
 // ---------------------------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 8;
+constexpr int kScanBlock = kScanThreads * kScanItems;
 
-// thread k = k-th Gaussian in depth order.  ONE kernel turns the tiles-per-Gaussian counts (delivered in depth order by the
-// depth sort's last pass) into instance offsets AND writes the instances:
-//   * exclusive scan: per-block scan + chained look-back over per-block status words (blocks take tickets in arrival
-//     order, so every predecessor of a block is already running; a full warp inspects 32 predecessors per round);
-//   * the warp writes the (tile id, Gaussian id) instances of its 32 Gaussians.  Rectangles with a stored bitmask are
-//     replayed from it, flattened across the warp (every lane busy, stores run along the output); larger ones are
-//     re-tested cooperatively.
-// The last block publishes R (counters[1]) and the overflow flag (counters[2]); stores beyond `capacity` are dropped.
-// status words: [31:30] 0 = not ready, 1 = block aggregate, 2 = inclusive prefix | 30-bit value (capacity < 2^30).
-__global__ void __launch_bounds__(kEmitThreads) emit_scan_kernel(int P, const uint32_t* __restrict__ ids_sorted,
-                                                                  const uint32_t* __restrict__ tiles_sorted,
-                                                                  const float4* __restrict__ recA, const float4* __restrict__ recB,
-                                                                  const int* __restrict__ radii, const uint64_t* __restrict__ masks,
-                                                                  const uint32_t* __restrict__ rects, uint32_t gx, uint32_t gy,
-                                                                  uint32_t flags, int64_t capacity,
-                                                                  unsigned long long* __restrict__ counters,
-                                                                  uint32_t* __restrict__ scan_status, uint32_t* __restrict__ scan_ticket,
-                                                                  uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
-                                                                  uint32_t* __restrict__ ghist, int hist_passes, int digit_bits) {
-  // digit histograms of the tile ids this block emits (what the tile sort's passes need), so the
-  // sort does not have to read the instance stream once more just to count
-  __shared__ uint32_t shist[kRdxMaxPasses][kRdxBins];
-  __shared__ uint32_t warp_tot[kEmitThreads / 32];
+// Exclusive scan of the tiles-per-Gaussian counts in depth order (delivered contiguously by the depth sort's last pass) ->
+// instance offsets.  One pass: per-block scan + chained look-back over per-block status words (blocks take tickets in
+// arrival order, so every predecessor of a block is already running; a full warp inspects 32 predecessors per round).
+// With 8192 items per block the whole grid (123 blocks for 1M Gaussians) is co-resident and the chain is a few rounds deep.
+// (The scan used to be fused into the emit pass; there every one of ~4000 heavy blocks paid the look-back latency before
+// it could start writing: 104 us instead of 57 + this kernel's ~8.)  The last block publishes R (counters[1]) and the
+// overflow flag (counters[2]).  status words: [31:30] 0 = not ready, 1 = block aggregate, 2 = inclusive prefix | 30-bit
+// value (capacity < 2^30; values saturate, so an oversized frame still raises the flag).
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int P, const uint32_t* __restrict__ tiles_sorted,
+                                                                 uint32_t* __restrict__ offsets, int64_t capacity,
+                                                                 unsigned long long* __restrict__ counters,
+                                                                 uint32_t* __restrict__ scan_status, uint32_t* __restrict__ scan_ticket) {
+  __shared__ uint32_t warp_tot[kScanThreads / 32];
   __shared__ uint32_t s_bid, s_prefix;
-  for (int p = 0; p < hist_passes; ++p) shist[p][threadIdx.x] = 0;
   if (threadIdx.x == 0) s_bid = atomicAdd(scan_ticket, 1u);
   __syncthreads();
-  auto tally = [&](uint32_t tile) {
-    for (int p = 0; p < hist_passes; ++p) atomicAdd(&shist[p][(tile >> (digit_bits * p)) & ((1u << digit_bits) - 1u)], 1u);
-  };
   const uint32_t bid = s_bid;
-  const int k = (int)(bid * kEmitThreads + threadIdx.x);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t cnt = k < P ? tiles_sorted[k] : 0u;
-  // ---- block-level exclusive scan of the counts
-  uint32_t incl_cnt = cnt;
+  const int base = (int)(bid * kScanBlock + threadIdx.x * kScanItems);
+  uint32_t v[kScanItems];
+  uint32_t tsum = 0;
+  if (base + kScanItems <= P) {  // two 16-byte loads
+    const uint4 a = reinterpret_cast<const uint4*>(tiles_sorted + base)[0], b = reinterpret_cast<const uint4*>(tiles_sorted + base)[1];
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) v[k] = base + k < P ? tiles_sorted[base + k] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) tsum += v[k];
+  uint32_t incl = tsum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, incl_cnt, o);
-    if (lane >= o) incl_cnt += v;
+    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
   }
-  if (lane == 31) warp_tot[warp] = incl_cnt;
+  if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
   uint32_t wbase = 0, block_total = 0;
 #pragma unroll
-  for (int w = 0; w < kEmitThreads / 32; ++w) {
+  for (int w = 0; w < kScanThreads / 32; ++w) {
     const uint32_t t = warp_tot[w];
     if (w < warp) wbase += t;
     block_total += t;
   }
-  // ---- block prefix: chained look-back, one warp, 32 predecessors per round
   if (warp == 0) {
     uint32_t* my = scan_status + bid;
-    // values saturate at 2^30 - 1 (> any admissible capacity), so an oversized frame still raises the overflow flag
     if (lane == 0) st_status(my, (bid == 0 ? kStIncl : kStAgg) | min(block_total, kStVal));
     uint32_t prev = 0;
     if (bid > 0) {
       for (int64_t b = (int64_t)bid - 1;; b -= 32) {
         const int64_t src = b - lane;
-        uint32_t v = src >= 0 ? ld_status(scan_status + src) : kStIncl;  // before block 0: prefix 0
-        for (uint32_t spin = 0; (v >> 30) == 0; ++spin) {
+        uint32_t sv = src >= 0 ? ld_status(scan_status + src) : kStIncl;  // before block 0: prefix 0
+        for (uint32_t spin = 0; (sv >> 30) == 0; ++spin) {
           if (spin > (1u << 24)) __trap();  // a predecessor never published: fail loudly instead of hanging
-          v = ld_status(scan_status + src);
+          sv = ld_status(scan_status + src);
         }
-        const unsigned closed = __ballot_sync(0xffffffffu, (v >> 30) == 2);
+        const unsigned closed = __ballot_sync(0xffffffffu, (sv >> 30) == 2);
         const int first = closed ? __ffs(closed) - 1 : 31;  // nearest predecessor holding an inclusive prefix
-        unsigned long long part = lane <= first ? (unsigned long long)(v & kStVal) : 0ull;
+        unsigned long long part = lane <= first ? (unsigned long long)(sv & kStVal) : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         prev = (uint32_t)min(part + prev, (unsigned long long)kStVal);
@@ -858,16 +854,68 @@ __global__ void __launch_bounds__(kEmitThreads) emit_scan_kernel(int P, const ui
     }
   }
   __syncthreads();
-  const uint32_t off = s_prefix + wbase + incl_cnt - cnt;
+  uint32_t run = s_prefix + wbase + incl - tsum;
+  if (base + kScanItems <= P) {
+    uint4 a, b;
+    a.x = run, run += v[0];
+    a.y = run, run += v[1];
+    a.z = run, run += v[2];
+    a.w = run, run += v[3];
+    b.x = run, run += v[4];
+    b.y = run, run += v[5];
+    b.z = run, run += v[6];
+    b.w = run;
+    reinterpret_cast<uint4*>(offsets + base)[0] = a;
+    reinterpret_cast<uint4*>(offsets + base)[1] = b;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (base + k < P) offsets[base + k] = run;
+      run += v[k];
+    }
+  }
+}
+
+// thread k = k-th Gaussian in depth order; the warp writes the (tile id, Gaussian id) instances of its 32 Gaussians at the
+// offsets the scan produced.  Rectangles with a stored bitmask are replayed from it, flattened across the
+// warp (every lane busy, stores run along the output); larger ones are re-tested cooperatively.  Stores beyond `capacity`
+// are dropped (the frame is then flagged by the scan and re-rendered with a larger scratch).
+__global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int P, const uint32_t* __restrict__ ids_sorted,
+                                                                    const uint32_t* __restrict__ tiles_sorted,
+                                                                    const uint32_t* __restrict__ offsets,
+                                                                    const float4* __restrict__ recA, const float4* __restrict__ recB,
+                                                                    const int* __restrict__ radii, const uint64_t* __restrict__ masks,
+                                                                    const uint32_t* __restrict__ rects, uint32_t gx, uint32_t gy,
+                                                                    uint32_t flags, int64_t capacity,
+                                                                    uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ tile_vals,
+                                                                    uint32_t* __restrict__ ghist, int hist_passes, int digit_bits) {
+  // digit histograms of the tile ids this block emits (what the tile sort's passes need), so the
+  // sort does not have to read the instance stream once more just to count
+  __shared__ uint32_t shist[kRdxMaxPasses][kRdxBins];
+  for (int p = 0; p < hist_passes; ++p) shist[p][threadIdx.x] = 0;
+  __syncthreads();
+  auto tally = [&](uint32_t tile) {
+    for (int p = 0; p < hist_passes; ++p) atomicAdd(&shist[p][(tile >> (digit_bits * p)) & ((1u << digit_bits) - 1u)], 1u);
+  };
+  const int k = (int)(blockIdx.x * kEmitThreads + threadIdx.x);
+  const int lane = threadIdx.x & 31;
+  uint32_t cnt = 0, off = 0, gid = 0;
+  if (k < P) {  // three independent loads
+    cnt = tiles_sorted[k];
+    off = offsets[k];
+    gid = ids_sorted[k];
+  }
   const int64_t cap = capacity;
 
-  uint32_t gid = 0, rect = kRectLarge;
+  uint32_t rect = kRectLarge;
   const bool active = cnt != 0;
-  if (active) gid = ids_sorted[k];
   uint64_t mask = 0ull;
-  if (active) rect = rects[gid];
+  if (active) {  // both gathers in flight together (the mask is only meaningful for a packed rectangle)
+    rect = rects[gid];
+    mask = masks[gid];
+  }
   const bool small = active && rect != kRectLarge;
-  if (small) mask = masks[gid];
+  if (!small) mask = 0ull;
   // ---- flattened replay of the stored masks (bits up to the highest kept tile of each rectangle)
   const uint32_t cand = small ? 64u - (uint32_t)__clzll((long long)mask) : 0u;
   uint32_t incl = cand;
@@ -1481,6 +1529,11 @@ __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
   return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
 
+// One CTA per tile in the hardware's block order.  Measured dead end (profiles/r02d_*, r02e_*): persistent CTAs (or warps)
+// pulling tiles from a queue sorted by descending list length -- 0.298 vs 0.249 ms on C1, 0.889 vs 0.629 ms on C3.  The
+// hardware order mixes long and short lists on every SM, so the gather latency of the short ones hides behind the
+// arithmetic of the long ones; sorted, the kernel ends in a long phase of latency-bound tiles, and a persistent grid
+// also keeps the kernels of the other in-flight views off the SMs.
 __global__ void __launch_bounds__(kTilePixels / 2, 7)
     render_table_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
                         const float4* __restrict__ recA, const float4* __restrict__ recB, const float2* __restrict__ recC,
@@ -1491,101 +1544,105 @@ __global__ void __launch_bounds__(kTilePixels / 2, 7)
   const uint32_t tiles_x = (W + kTile - 1) / kTile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t a0 = smem_u32(&slots[warp][0]);
-  const uint32_t blk_x = blockIdx.x * kTile + (warp & 1) * 8, blk_y = blockIdx.y * kTile + (warp >> 1) * 8;
-  const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
-  const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 7);
   const uint32_t xoff = kTabX + (lane & 7) * 8, yoff = kTabY + (lane >> 3) * 16;
-  uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
-  if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);
-  const int total = range.y - range.x;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const bool inside0 = pix_x < (uint32_t)W && pix_y < (uint32_t)H, inside1 = pix_x < (uint32_t)W && pix_y + 4 < (uint32_t)H;
-  // the sign of T is the pixel's "done" flag
-  unsigned long long TT = pack_f32x2(inside0 ? 1.0f : -1.0f, inside1 ? 1.0f : -1.0f);
-  float C00 = 0.f, C10 = 0.f, C20 = 0.f, Dz0 = 0.f, C01 = 0.f, C11 = 0.f, C21 = 0.f, Dz1 = 0.f;
-
-  float4 cA = make_float4(0.f, 0.f, 0.f, 0.f), cB = cA, nA = cA, nB = cA;
-  float2 cC = make_float2(0.f, 0.f), nC = cC;
-  if (lane < total) {
-    const uint32_t g = point_list[range.x + lane];
-    cA = recA[g];
-    cB = recB[g];
-    cC = recC[g];
-  }
   // per-lane bases of the column / row entries; `off` (byte offset of the record's slot) is warp-uniform
   const uint32_t xbase = a0 + xoff, ybase = a0 + yoff;
-  auto blend = [&](uint32_t off) {
-    const float2 X = lds64(xbase + off);       // u', v of this lane's column
-    const float4 Y = lds128(ybase + off);      // dy, w of this lane's two rows
-    const float4 Q = lds128(a0 + kTabC + off);  // r, g, b, z
-    const float thr = lds32(a0 + kTabThr + off);
-    blend_record_tab(X.x, X.y, Y.x, Y.y, Y.z, Y.w, thr, Q.x, Q.y, Q.z, Q.w, TT, C00, C10, C20, Dz0, C01, C11, C21, Dz1);
-  };
-  for (int c0 = 0; c0 < total; c0 += 32) {
-    if (__all_sync(0xffffffffu, (TT & 0x8000000080000000ull) == 0x8000000080000000ull)) break;  // both pixels done
-    const int nxt = c0 + 32 + lane;
-    if (nxt < total) {  // next chunk's gathers fly while this one is tested and blended
-      const uint32_t g = point_list[range.x + nxt];
-      nA = recA[g];
-      nB = recB[g];
-      nC = recC[g];
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+  {
+    const uint32_t tile = blockIdx.y * tiles_x + blockIdx.x;
+    const uint32_t blk_x = blockIdx.x * kTile + (warp & 1) * 8, blk_y = blockIdx.y * kTile + (warp >> 1) * 8;
+    const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
+    const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 7);
+    uint2 range = ranges[tile];
+    if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);
+    const int total = range.y - range.x;
+    const bool inside0 = pix_x < (uint32_t)W && pix_y < (uint32_t)H, inside1 = pix_x < (uint32_t)W && pix_y + 4 < (uint32_t)H;
+    // the sign of T is the pixel's "done" flag
+    unsigned long long TT = pack_f32x2(inside0 ? 1.0f : -1.0f, inside1 ? 1.0f : -1.0f);
+    float C00 = 0.f, C10 = 0.f, C20 = 0.f, Dz0 = 0.f, C01 = 0.f, C11 = 0.f, C21 = 0.f, Dz1 = 0.f;
+
+    float4 cA = make_float4(0.f, 0.f, 0.f, 0.f), cB = cA, nA = cA, nB = cA;
+    float2 cC = make_float2(0.f, 0.f), nC = cC;
+    if (lane < total) {
+      const uint32_t g = point_list[range.x + lane];
+      cA = recA[g];
+      cB = recB[g];
+      cC = recC[g];
     }
-    bool hit = false;
-    if (c0 + lane < total) {
-      const Footprint fp = make_footprint(cB.x, cB.y, cB.z, 2.f * __logf(255.f * cA.w) + 1e-3f);
-      hit = rect_can_contribute(cA.x, cA.y, fp, bx0, by0, bx1, by1);
-    }
-    const unsigned votes = __ballot_sync(0xffffffffu, hit);
-    const int n = __popc(votes);
-    if (hit) {  // this lane's record goes to slot `rank`: per-column and per-row terms of the exponent, colour, depth
-      const uint32_t dst = a0 + __popc(votes & lt_mask) * kTabSlotBytes;
-      const float ap = -0.72134752044448170f * cB.x, bp = -1.4426950408889634f * cB.y, cp = -0.72134752044448170f * cB.z;
-      const float l2o = __log2f(cA.w);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float dx = cA.x - (bx0 + (float)i);
-        sts64(dst + kTabX + 8 * i, make_float2(fmaf(ap * dx, dx, l2o), bp * dx));
+    auto blend = [&](uint32_t off) {
+      const float2 X = lds64(xbase + off);       // u', v of this lane's column
+      const float4 Y = lds128(ybase + off);      // dy, w of this lane's two rows
+      const float4 Q = lds128(a0 + kTabC + off);  // r, g, b, z
+      const float thr = lds32(a0 + kTabThr + off);
+      blend_record_tab(X.x, X.y, Y.x, Y.y, Y.z, Y.w, thr, Q.x, Q.y, Q.z, Q.w, TT, C00, C10, C20, Dz0, C01, C11, C21, Dz1);
+    };
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      if (__all_sync(0xffffffffu, (TT & 0x8000000080000000ull) == 0x8000000080000000ull)) break;  // both pixels done
+      const int nxt = c0 + 32 + lane;
+      if (nxt < total) {  // next chunk's gathers fly while this one is tested and blended
+        const uint32_t g = point_list[range.x + nxt];
+        nA = recA[g];
+        nB = recB[g];
+        nC = recC[g];
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float dy0 = cA.y - (by0 + (float)j), dy1 = cA.y - (by0 + (float)(j + 4));
-        sts128(dst + kTabY + 16 * j, make_float4(dy0, dy1, cp * dy0 * dy0, cp * dy1 * dy1));
+      bool hit = false;
+      if (c0 + lane < total) {
+        const Footprint fp = make_footprint(cB.x, cB.y, cB.z, 2.f * __logf(255.f * cA.w) + 1e-3f);
+        hit = rect_can_contribute(cA.x, cA.y, fp, bx0, by0, bx1, by1);
       }
-      sts128(dst + kTabC, make_float4(cB.w, cC.x, cC.y, cA.z));
-      sts128(dst + kTabThr, make_float4(l2o, 0.f, 0.f, 0.f));
+      const unsigned votes = __ballot_sync(0xffffffffu, hit);
+      const int n = __popc(votes);
+      if (hit) {  // this lane's record goes to slot `rank`: per-column and per-row terms of the exponent, colour, depth
+        const uint32_t dst = a0 + __popc(votes & lt_mask) * kTabSlotBytes;
+        const float ap = -0.72134752044448170f * cB.x, bp = -1.4426950408889634f * cB.y, cp = -0.72134752044448170f * cB.z;
+        const float l2o = __log2f(cA.w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dx = cA.x - (bx0 + (float)i);
+          sts64(dst + kTabX + 8 * i, make_float2(fmaf(ap * dx, dx, l2o), bp * dx));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dy0 = cA.y - (by0 + (float)j), dy1 = cA.y - (by0 + (float)(j + 4));
+          sts128(dst + kTabY + 16 * j, make_float4(dy0, dy1, cp * dy0 * dy0, cp * dy1 * dy1));
+        }
+        sts128(dst + kTabC, make_float4(cB.w, cC.x, cC.y, cA.z));
+        sts128(dst + kTabThr, make_float4(l2o, 0.f, 0.f, 0.f));
+      }
+      if (lane < kTabSlotBytes / 16) {  // sentinel after the last hit: u' = -1e30 -> alpha 0 -> skipped
+        const float big = lane < 4 ? -1.0e30f : 0.f;  // quads 0..3 = the X table: (u', v, u', v)
+        sts128(a0 + n * kTabSlotBytes + 16 * lane, make_float4(big, 0.f, big, 0.f));
+      }
+      __syncwarp();  // the list is visible to every lane of the warp
+      const uint32_t end = (uint32_t)n * kTabSlotBytes;
+      for (uint32_t off = 0; off < end; off += 2 * kTabSlotBytes) {
+        blend(off);
+        blend(off + kTabSlotBytes);
+      }
+      __syncwarp();  // every lane is done reading before the next chunk overwrites the slots
+      cA = nA;
+      cB = nB;
+      cC = nC;
     }
-    if (lane < kTabSlotBytes / 16) {  // sentinel after the last hit: u' = -1e30 -> alpha 0 -> skipped
-      const float big = lane < 4 ? -1.0e30f : 0.f;  // quads 0..3 = the X table: (u', v, u', v)
-      sts128(a0 + n * kTabSlotBytes + 16 * lane, make_float4(big, 0.f, big, 0.f));
+    const size_t plane = (size_t)H * W;
+    const float Tf0 = fabsf(__uint_as_float((uint32_t)TT)), Tf1 = fabsf(__uint_as_float((uint32_t)(TT >> 32)));
+    if (inside0) {
+      const size_t pid = (size_t)pix_y * W + pix_x;
+      out_color[pid] = C00 + Tf0 * bg0;
+      out_color[plane + pid] = C10 + Tf0 * bg1;
+      out_color[2 * plane + pid] = C20 + Tf0 * bg2;
+      if (out_depth) out_depth[pid] = Dz0;
+      if (out_T) out_T[pid] = Tf0;
     }
-    __syncwarp();  // the list is visible to every lane of the warp
-    const uint32_t end = (uint32_t)n * kTabSlotBytes;
-    for (uint32_t off = 0; off < end; off += 2 * kTabSlotBytes) {
-      blend(off);
-      blend(off + kTabSlotBytes);
+    if (inside1) {
+      const size_t pid = (size_t)(pix_y + 4) * W + pix_x;
+      out_color[pid] = C01 + Tf1 * bg0;
+      out_color[plane + pid] = C11 + Tf1 * bg1;
+      out_color[2 * plane + pid] = C21 + Tf1 * bg2;
+      if (out_depth) out_depth[pid] = Dz1;
+      if (out_T) out_T[pid] = Tf1;
     }
-    __syncwarp();  // every lane is done reading before the next chunk overwrites the slots
-    cA = nA;
-    cB = nB;
-    cC = nC;
-  }
-  const size_t plane = (size_t)H * W;
-  const float Tf0 = fabsf(__uint_as_float((uint32_t)TT)), Tf1 = fabsf(__uint_as_float((uint32_t)(TT >> 32)));
-  if (inside0) {
-    const size_t pid = (size_t)pix_y * W + pix_x;
-    out_color[pid] = C00 + Tf0 * bg[0];
-    out_color[plane + pid] = C10 + Tf0 * bg[1];
-    out_color[2 * plane + pid] = C20 + Tf0 * bg[2];
-    if (out_depth) out_depth[pid] = Dz0;
-    if (out_T) out_T[pid] = Tf0;
-  }
-  if (inside1) {
-    const size_t pid = (size_t)(pix_y + 4) * W + pix_x;
-    out_color[pid] = C01 + Tf1 * bg[0];
-    out_color[plane + pid] = C11 + Tf1 * bg[1];
-    out_color[2 * plane + pid] = C21 + Tf1 * bg[2];
-    if (out_depth) out_depth[pid] = Dz1;
-    if (out_T) out_T[pid] = Tf1;
   }
 }
 
@@ -1651,7 +1708,7 @@ struct Workspace {
   uint32_t* sorted_offsets;
   uint64_t* masks;
   uint32_t* rects;
-  uint32_t* scan_status;  // emit_scan_kernel: [0] ticket, [64..] per-block status words
+  uint32_t* scan_status;  // scan_tiles_kernel: [0] ticket, [64..] per-block status words
   uint32_t* radix_scratch;
   uint64_t* keys_in;
   uint64_t* keys_out;
@@ -1684,7 +1741,7 @@ Workspace carve(void* base, int32_t P, int32_t W, int32_t H, int64_t R) {
   w.sorted_offsets = c.take<uint32_t>(Pn);
   w.masks = c.take<uint64_t>(Pn);
   w.rects = c.take<uint32_t>(Pn);
-  w.scan_status = c.take<uint32_t>((Pn + kEmitThreads - 1) / kEmitThreads + 64);
+  w.scan_status = c.take<uint32_t>((Pn + kScanBlock - 1) / kScanBlock + 64);
   w.radix_scratch = c.take<uint32_t>(radix_scratch_words(std::max(Pn, Rn)));
   w.keys_in = c.take<uint64_t>(Rn);
   w.keys_out = c.take<uint64_t>(Rn);
@@ -1901,15 +1958,17 @@ static int bin_and_render(const Frame& f, const uint32_t* ids_sorted, cudaStream
   {
     StageTimer tm(kStEmit, stream);
     radix_prepare(rs, (size_t)cap, tile_bits, stream);
-    const int eblocks = (P + kEmitThreads - 1) / kEmitThreads;
-    GSB_CUDA_OK(cudaMemsetAsync(ws.scan_status, 0, ((size_t)eblocks + 64) * sizeof(uint32_t), stream));
-    emit_scan_kernel<<<eblocks, kEmitThreads, 0, stream>>>(P, ids_sorted, ws.offsets, ws.recA, ws.recB, f.radii, ws.masks, ws.rects, gx,
-                                                           gy, a->flags, cap, ws.counters, ws.scan_status + 64, ws.scan_status, tk_a,
-                                                           tv_a, radix_ghist(rs), (tile_bits + 7) / 8, radix_digit_bits(tile_bits));
+    const int sblocks = (P + kScanBlock - 1) / kScanBlock;
+    GSB_CUDA_OK(cudaMemsetAsync(ws.scan_status, 0, ((size_t)sblocks + 64) * sizeof(uint32_t), stream));
+    scan_tiles_kernel<<<sblocks, kScanThreads, 0, stream>>>(P, ws.offsets, ws.sorted_offsets, cap, ws.counters, ws.scan_status + 64,
+                                                            ws.scan_status);
+    emit_sorted_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, stream>>>(
+        P, ids_sorted, ws.offsets, ws.sorted_offsets, ws.recA, ws.recB, f.radii, ws.masks, ws.rects, gx, gy, a->flags, cap, tk_a, tv_a,
+        radix_ghist(rs), (tile_bits + 7) / 8, radix_digit_bits(tile_bits));
     init_ranges_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream>>>(ws.ranges, (uint32_t)ntiles);
-    nl += 2;
+    nl += 3;
   }
-  if ((rc = check_launch("emit_scan_kernel", stream, f.dbg))) return rc;
+  if ((rc = check_launch("emit_sorted_kernel", stream, f.dbg))) return rc;
   {
     StageTimer tm(kStSort, stream);
     const int which = radix_sort_pairs(tk_a, tv_a, tk_b, tv_b, 0u, ws.counters, cap, (size_t)cap, tile_bits, rs, ws.ranges, stream, &nl,
@@ -2062,7 +2121,7 @@ int gsb_raster_forward(const GsbRasterArgs* a, void* stream_v) {
   const int pre_blocks = (a->P + kPreThreads - 1) / kPreThreads;
   {
     StageTimer tm(kStPreprocess, stream);
-    preprocess_kernel<1><<<pre_blocks, kPreThreads, 0, stream>>>(pp);
+    preprocess_kernel<1, 6><<<pre_blocks, kPreThreads, 0, stream>>>(pp);
   }
   count_launch();
   if ((rc = check_launch("preprocess_kernel", stream, f.dbg))) return rc;
@@ -2106,7 +2165,14 @@ int gsb_raster_forward_pair(const GsbRasterArgs* left, const GsbRasterArgs* righ
   const int pre_blocks = (left->P + kPreThreads - 1) / kPreThreads;
   {
     StageTimer tm(kStPreprocess, sl);
-    preprocess_kernel<2><<<pre_blocks, kPreThreads, 0, sl>>>(pp);
+    static const int occ = [] {  // A/B switch: GSB_PRE_OCC=5 -> 96 registers (spills) for 5 CTAs per SM instead of 4
+      const char* e = getenv("GSB_PRE_OCC");
+      return e ? atoi(e) : 4;
+    }();
+    if (occ == 5)
+      preprocess_kernel<2, 5><<<pre_blocks, kPreThreads, 0, sl>>>(pp);
+    else
+      preprocess_kernel<2, 4><<<pre_blocks, kPreThreads, 0, sl>>>(pp);
   }
   count_launch();
   if ((rc = check_launch("preprocess_kernel<2>", sl, fl.dbg))) return rc;

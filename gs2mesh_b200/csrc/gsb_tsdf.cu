@@ -97,16 +97,59 @@ __global__ void __launch_bounds__(256) mark_bricks_kernel(const MarkParams m, co
     lo[r] = (int)floor(__ddiv_rn(__dadd_rn(w, -m.trunc), m.unit_length));
     hi[r] = (int)floor(__ddiv_rn(__dadd_rn(w, m.trunc), m.unit_length));
   }
+  auto queue = [&](uint32_t h) {
+    if (hv.stamp[h] == frame) return;
+    if (atomicExch(&hv.stamp[h], frame) != frame) list[atomicAdd(&counters[kCntQueued], 1u)] = h;
+  };
+  const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+  const int total = nx * ny * nz;
+  if (total <= 8) {
+    // the usual box (sdf_trunc < unit_length: at most 2 bricks per axis): the first probes of all its bricks are issued
+    // together -- one memory round trip instead of up to eight dependent ones; only misses walk the table
+    unsigned long long key[8], seen[8];
+    uint32_t h[8], st[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      key[i] = kHashEmpty;
+      if (i < total) {
+        const int bz = lo[2] + i % nz, by = lo[1] + (i / nz) % ny, bx = lo[0] + i / (nz * ny);
+        if (brick_key_ok(bx, by, bz)) {
+          key[i] = brick_key(bx, by, bz);
+          h[i] = brick_hash(key[i], hv.mask);
+          seen[i] = hv.keys[h[i]];
+          st[i] = hv.stamp[h[i]];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i >= total) break;
+      if (key[i] == kHashEmpty) {
+        atomicAdd(&counters[kCntDropped], 1u);
+        continue;
+      }
+      if (seen[i] == key[i]) {  // found at its home slot
+        if (st[i] != frame && atomicExch(&hv.stamp[h[i]], frame) != frame) list[atomicAdd(&counters[kCntQueued], 1u)] = h[i];
+        continue;
+      }
+      const int bz = lo[2] + i % nz, by = lo[1] + (i / nz) % ny, bx = lo[0] + i / (nz * ny);
+      const uint32_t hh = brick_find_or_insert(hv, counters, bx, by, bz);
+      if (hh == kSlotNone)
+        atomicAdd(&counters[kCntDropped], 1u);  // reported by gsb_tsdf_last_stats; the stage class grows the pool
+      else
+        queue(hh);
+    }
+    return;
+  }
   for (int bx = lo[0]; bx <= hi[0]; ++bx)
     for (int by = lo[1]; by <= hi[1]; ++by)
       for (int bz = lo[2]; bz <= hi[2]; ++bz) {
         const uint32_t h = brick_find_or_insert(hv, counters, bx, by, bz);
         if (h == kSlotNone) {
-          atomicAdd(&counters[kCntDropped], 1u);  // reported by gsb_tsdf_last_stats; the stage class raises on it
+          atomicAdd(&counters[kCntDropped], 1u);
           continue;
         }
-        if (hv.stamp[h] == frame) continue;
-        if (atomicExch(&hv.stamp[h], frame) != frame) list[atomicAdd(&counters[kCntQueued], 1u)] = h;
+        queue(h);
       }
 }
 

@@ -47,11 +47,12 @@ class _Scratch:
 _scratch = {}
 
 
-def _scratch_for(device, stream=None) -> _Scratch:
-    """One scratch block per (device, stream): frames enqueued on different streams may overlap."""
+def _scratch_for(device, stream=None, eye=0) -> _Scratch:
+    """One scratch block per (device, stream, eye): frames enqueued on different streams may overlap, and the two eyes of a
+    stereo pair are in flight together even when they share a stream."""
     dev = torch.device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    key = (idx, (stream if stream is not None else torch.cuda.current_stream(idx)).cuda_stream)
+    key = (idx, (stream if stream is not None else torch.cuda.current_stream(idx)).cuda_stream, eye)
     if key not in _scratch:
         _scratch[key] = _Scratch(torch.device("cuda", idx))
     return _scratch[key]
@@ -164,8 +165,8 @@ def rasterize_forward_pair(*, means3D, opacities, shs, scales, rotations, sh_deg
     L = _lib.lib()
     with torch.cuda.device(device):
         blocks = []
-        for eye, st in zip(eyes, streams):
-            scratch = _scratch_for(device, st)
+        for s_, (eye, st) in enumerate(zip(eyes, streams)):
+            scratch = _scratch_for(device, st, s_)
             guess = max(scratch.max_instances if scratch.key == (P, W, H) else 0, GUESS_PER_GAUSSIAN * P, MIN_GUESS, int(min_instances))
             ws = scratch.ensure(P, W, H, guess)
             fl = int(flags) | _lib.RASTER_ASYNC | (_lib.RASTER_PAIR_SHARED_DEPTH if shared_depth else 0)

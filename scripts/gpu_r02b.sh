@@ -3,7 +3,7 @@
 # emit+scan, unbounded TSDF brick pool): GPU tests (all, not -x), smoke, bench A/Bs.
 mkdir -p gpurun_out
 T=gpurun_out/r02b
-timeout 900 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_pipeline.py::test_full_size_parity_vs_reference_binary_and_oracle > ${T}_tests.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q --deselect tests/test_gpu_pipeline.py::test_full_size_parity_vs_reference_binary_and_oracle > ${T}_tests.log 2>&1
 echo "tests exit $? : $(tail -1 ${T}_tests.log)"
 grep -E "^(FAILED|ERROR)" ${T}_tests.log | head -20
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > ${T}_smoke.log 2>&1; tail -2 ${T}_smoke.log

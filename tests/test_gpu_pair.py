@@ -11,7 +11,7 @@ from gs2mesh_b200 import scene
 
 pytestmark = pytest.mark.gpu
 
-W, H, NPTS, NPAIRS = 400, 304, 20000, 12
+W, H, NPTS, NPAIRS = 400, 304, 20000, 10  # a 10-camera ring: views 3, 4, 5, 8, 9 have eyes whose z rows differ by an ulp
 
 
 class Args:
