@@ -20,7 +20,7 @@ RASTER_CUB_SORT = 8
 RASTER_ASYNC = 16
 RASTER_FAST_EXP = 32
 RASTER_PAIR_SHARED_DEPTH = 64
-RENDER_IMPLS = {"block": 1, "warp": 2, "compact": 3, "dual": 4, "table": 5}
+RENDER_IMPLS = {"dual": 4, "table": 5}
 SH_MODES = {"scalar": 1, "vec": 2, "padded": 3}
 
 

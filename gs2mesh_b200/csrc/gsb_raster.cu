@@ -1057,264 +1057,25 @@ __device__ __forceinline__ void sts64(uint32_t addr, const float2& v) {
   asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
-// forward.cu:261-374, re-organised:
-//  * batches of 256 records (position/depth/opacity, conic/red, green/blue) are staged in a
-//    DOUBLE-buffered shared-memory ring: while batch i is blended, batch i+1 is already in the other
-//    buffer and batch i+2 is in flight in registers -> one block barrier per batch, no global
-//    access inside the blend loop;
-//  * each warp owns an 8x4 pixel block of the 16x16 tile and first asks, 32 Gaussians at a time
-//    (one per lane, exact footprint test), which ones can reach alpha >= 1/255 anywhere in its
-//    block; only those are evaluated per pixel.  Skipped Gaussians are exactly the ones every pixel
-//    of the block would `continue` past in the reference loop, so the result is bit-identical;
-//  * an expected-depth accumulator (sum z*alpha*T) runs next to the colour.
-// kFastExp: alpha = opacity * ex2.approx(power * log2 e) instead of the reference's full-precision
-// expf (forward.cu:340): ~2e-7 relative on alpha, far inside the 1e-4 parity budget.
-template <bool kFastExp>
-__global__ void __launch_bounds__(kTilePixels) render_kernel(const uint2* __restrict__ ranges,
-                                                            const uint32_t* __restrict__ point_list, int W, int H,
-                                                            const float4* __restrict__ recA,
-                                                            const float4* __restrict__ recB,
-                                                            const float2* __restrict__ recC,
-                                                            const float* __restrict__ bg, float* __restrict__ out_color,
-                                                            float* __restrict__ out_depth, float* __restrict__ out_T,
-                                                            int64_t capacity) {
-  __shared__ __align__(16) float4 sA[2][kTilePixels];
-  __shared__ __align__(16) float4 sB[2][kTilePixels];
-  __shared__ __align__(16) float2 sC[2][kTilePixels];
-  const uint32_t aA = smem_u32(&sA[0][0]), aB = smem_u32(&sB[0][0]), aC = smem_u32(&sC[0][0]);
-  constexpr uint32_t kStrideAB = kTilePixels * 16, kStrideC = kTilePixels * 8;
-  const uint32_t tiles_x = (W + kTile - 1) / kTile;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // warp -> 8x4 block inside the tile: 2 blocks across, 4 down
-  const uint32_t blk_x = blockIdx.x * kTile + (warp & 1) * 8, blk_y = blockIdx.y * kTile + (warp >> 1) * 4;
-  const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
-  const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
-  const float pfx = (float)pix_x, pfy = (float)pix_y;
-  const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 3);
-  uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
-  if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);  // empty tile / invalid frame
-  const int total = range.y - range.x;
-  const int rounds = (total + kTilePixels - 1) / kTilePixels;
-  bool done = !inside;
-  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
-
-  float4 nA = make_float4(0.f, 0.f, 0.f, 0.f), nB = nA;
-  float2 nC = make_float2(0.f, 0.f);
-  auto fetch = [&](int batch_index) {
-    const int slot = batch_index * kTilePixels + (int)threadIdx.x;
-    if (slot < total) {
-      const uint32_t g = point_list[range.x + slot];
-      nA = recA[g];
-      nB = recB[g];
-      nC = recC[g];
-    }
-  };
-  auto stage = [&](int buf) {
-    sts128(aA + buf * kStrideAB + threadIdx.x * 16, nA);
-    sts128(aB + buf * kStrideAB + threadIdx.x * 16, nB);
-    sts64(aC + buf * kStrideC + threadIdx.x * 8, nC);
-  };
-  if (rounds > 0) {
-    fetch(0);
-    stage(0);
-    fetch(1);
-  }
-  __syncthreads();
-  for (int i = 0; i < rounds; ++i) {
-    const int cur = i & 1;
-    if (i + 1 < rounds) {  // buffer cur^1 was released by the barrier that ended iteration i-1
-      stage(cur ^ 1);
-      fetch(i + 2);
-    }
-    const uint32_t bA = aA + cur * kStrideAB, bB = aB + cur * kStrideAB, bC = aC + cur * kStrideC;
-    const int batch = min(kTilePixels, total - i * kTilePixels);
-    bool warp_done = __all_sync(0xffffffffu, done);
-    for (int c0 = 0; c0 < batch && !warp_done; c0 += 32) {
-      const int jt = c0 + lane;
-      bool hit = false;
-      if (jt < batch) {
-        const float4 A = lds128(bA + jt * 16);
-        const float4 B = lds128(bB + jt * 16);
-        const Footprint fp = make_footprint(B.x, B.y, B.z, 2.f * __logf(255.f * A.w) + 1e-3f);
-        hit = rect_can_contribute(A.x, A.y, fp, bx0, by0, bx1, by1);
-      }
-      unsigned todo = __ballot_sync(0xffffffffu, hit);
-      while (todo) {
-        const int j = c0 + __ffs(todo) - 1;
-        todo &= todo - 1;
-        if (done) continue;
-        const float4 A = lds128(bA + j * 16);
-        const float4 B = lds128(bB + j * 16);
-        const float dx = A.x - pfx, dy = A.y - pfy;
-        const float power = -0.5f * (B.x * dx * dx + B.z * dy * dy) - B.y * dx * dy;
-        if (power > 0.0f) continue;
-        const float alpha = min(0.99f, A.w * (kFastExp ? __expf(power) : exp(power)));
-        if (alpha < 1.0f / 255.0f) continue;
-        const float test_T = T * (1 - alpha);
-        if (test_T < 0.0001f) {
-          done = true;
-          continue;
-        }
-        const float2 gb = lds64(bC + j * 8);
-        C0 += B.w * alpha * T;
-        C1 += gb.x * alpha * T;
-        C2 += gb.y * alpha * T;
-        Dz += A.z * alpha * T;
-        T = test_T;
-      }
-      warp_done = __all_sync(0xffffffffu, done);
-    }
-    // one barrier per batch: batch i+1 is now visible, buffer `cur` may be overwritten, and the
-    // tile stops as soon as every pixel is saturated
-    if (__syncthreads_count(done) == kTilePixels) break;
-  }
-  if (inside) {
-    const size_t pid = (size_t)pix_y * W + pix_x;
-    const size_t plane = (size_t)H * W;
-    out_color[pid] = C0 + T * bg[0];
-    out_color[plane + pid] = C1 + T * bg[1];
-    out_color[2 * plane + pid] = C2 + T * bg[2];
-    if (out_depth) out_depth[pid] = Dz;
-    if (out_T) out_T[pid] = T;
-  }
-}
-
-// Barrier-free variant: the 8 warps of a tile never wait for each other.  Every warp streams the
-// tile's sorted instance list on its own, 32 Gaussians at a time: each lane gathers ONE record
-// (the 8 warps of the CTA hit the same lines, so all but the first gather is an L1 hit), tests it
-// against the warp's 8x4 pixel block straight from registers, and publishes it in the warp's private
-// double-buffered shared-memory slot for the broadcast reads of the blend loop.  The next chunk's
-// gathers are in flight while the current one is blended; no __syncthreads anywhere, and a warp
-// leaves as soon as its own 32 pixels are saturated.
-template <bool kFastExp>
-__global__ void __launch_bounds__(kTilePixels, 5) render_warp_kernel(const uint2* __restrict__ ranges,
-                                                                 const uint32_t* __restrict__ point_list, int W, int H,
-                                                                 const float4* __restrict__ recA,
-                                                                 const float4* __restrict__ recB,
-                                                                 const float2* __restrict__ recC,
-                                                                 const float* __restrict__ bg, float* __restrict__ out_color,
-                                                                 float* __restrict__ out_depth, float* __restrict__ out_T,
-                                                                 int64_t capacity) {
-  __shared__ __align__(16) float4 sA[8][2][32];
-  __shared__ __align__(16) float4 sB[8][2][32];
-  __shared__ __align__(16) float2 sC[8][2][32];
-  const uint32_t tiles_x = (W + kTile - 1) / kTile;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t aA = smem_u32(&sA[warp][0][0]), aB = smem_u32(&sB[warp][0][0]), aC = smem_u32(&sC[warp][0][0]);
-  const uint32_t blk_x = blockIdx.x * kTile + (warp & 1) * 8, blk_y = blockIdx.y * kTile + (warp >> 1) * 4;
-  const uint32_t pix_x = blk_x + (lane & 7), pix_y = blk_y + (lane >> 3);
-  const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
-  const float pfx = (float)pix_x, pfy = (float)pix_y;
-  const float bx0 = (float)blk_x, by0 = (float)blk_y, bx1 = (float)(blk_x + 7), by1 = (float)(blk_y + 3);
-  uint2 range = ranges[blockIdx.y * tiles_x + blockIdx.x];
-  if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);
-  const int total = range.y - range.x;
-  bool done = !inside;
-  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
-
-  float4 cA = make_float4(0.f, 0.f, 0.f, 0.f), cB = cA, nA = cA, nB = cA;
-  float2 cC = make_float2(0.f, 0.f), nC = cC;
-  if (lane < total) {
-    const uint32_t g = point_list[range.x + lane];
-    cA = recA[g];
-    cB = recB[g];
-    cC = recC[g];
-  }
-  for (int c0 = 0; c0 < total; c0 += 32) {
-    if (__all_sync(0xffffffffu, done)) break;
-    const int buf = (c0 >> 5) & 1;
-    sts128(aA + (buf * 32 + lane) * 16, cA);
-    sts128(aB + (buf * 32 + lane) * 16, cB);
-    sts64(aC + (buf * 32 + lane) * 8, cC);
-    const int nxt = c0 + 32 + lane;
-    if (nxt < total) {  // next chunk's gathers fly while this one is blended
-      const uint32_t g = point_list[range.x + nxt];
-      nA = recA[g];
-      nB = recB[g];
-      nC = recC[g];
-    }
-    bool hit = false;
-    if (c0 + lane < total) {
-      const Footprint fp = make_footprint(cB.x, cB.y, cB.z, 2.f * __logf(255.f * cA.w) + 1e-3f);
-      hit = rect_can_contribute(cA.x, cA.y, fp, bx0, by0, bx1, by1);
-    }
-    __syncwarp();  // the chunk's records are visible to every lane of the warp
-    unsigned todo = __ballot_sync(0xffffffffu, hit);
-    const uint32_t bA = aA + buf * 512, bB = aB + buf * 512, bC = aC + buf * 256;
-    // two hits per trip: their loads, quadratic forms and exponentials are independent and overlap; only
-    // the transmittance update is applied in order
-    while (todo) {
-      const int j0 = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const bool two = todo != 0;
-      const int j1 = two ? __ffs(todo) - 1 : j0;
-      todo &= todo - 1;  // no-op when todo is already 0
-      if (done) continue;
-      const float4 A0 = lds128(bA + j0 * 16), B0 = lds128(bB + j0 * 16);
-      const float4 A1 = lds128(bA + j1 * 16), B1 = lds128(bB + j1 * 16);
-      const float dx0 = A0.x - pfx, dy0 = A0.y - pfy, dx1 = A1.x - pfx, dy1 = A1.y - pfy;
-      const float power0 = -0.5f * (B0.x * dx0 * dx0 + B0.z * dy0 * dy0) - B0.y * dx0 * dy0;
-      const float power1 = -0.5f * (B1.x * dx1 * dx1 + B1.z * dy1 * dy1) - B1.y * dx1 * dy1;
-      const float alpha0 = min(0.99f, A0.w * (kFastExp ? __expf(power0) : exp(power0)));
-      const float alpha1 = min(0.99f, A1.w * (kFastExp ? __expf(power1) : exp(power1)));
-      if (!(power0 > 0.0f) && !(alpha0 < 1.0f / 255.0f)) {
-        const float test_T = T * (1 - alpha0);
-        if (test_T < 0.0001f) {
-          done = true;
-        } else {
-          const float2 gb = lds64(bC + j0 * 8);
-          C0 += B0.w * alpha0 * T;
-          C1 += gb.x * alpha0 * T;
-          C2 += gb.y * alpha0 * T;
-          Dz += A0.z * alpha0 * T;
-          T = test_T;
-        }
-      }
-      if (two && !done && !(power1 > 0.0f) && !(alpha1 < 1.0f / 255.0f)) {
-        const float test_T = T * (1 - alpha1);
-        if (test_T < 0.0001f) {
-          done = true;
-        } else {
-          const float2 gb = lds64(bC + j1 * 8);
-          C0 += B1.w * alpha1 * T;
-          C1 += gb.x * alpha1 * T;
-          C2 += gb.y * alpha1 * T;
-          Dz += A1.z * alpha1 * T;
-          T = test_T;
-        }
-      }
-    }
-    cA = nA;
-    cB = nB;
-    cC = nC;
-  }
-  if (inside) {
-    const size_t pid = (size_t)pix_y * W + pix_x;
-    const size_t plane = (size_t)H * W;
-    out_color[pid] = C0 + T * bg[0];
-    out_color[plane + pid] = C1 + T * bg[1];
-    out_color[2 * plane + pid] = C2 + T * bg[2];
-    if (out_depth) out_depth[pid] = Dz;
-    if (out_T) out_T[pid] = T;
-  }
-}
-
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-// Compacting variant of render_warp_kernel: the lanes whose Gaussian passed the warp's footprint test
-// store their record at consecutive 48-byte slots (ballot rank) of the warp's private list, so the
-// blend loop walks plain consecutive addresses (no bit scan, no per-hit address arithmetic) and is
-// branch-free: the three thresholds of forward.cu:336-353 become predicates that gate a weight
-// w = alpha*T (0 when the pixel skips the Gaussian) and the transmittance update.  An all-zero
-// sentinel record (opacity 0 -> alpha 0 -> skipped) pads an odd hit count so the loop always takes
-// two records per trip.  Thresholds are decided on exactly the same alpha / T values as in
-// render_warp_kernel; colours accumulate as fma(c, alpha*T, C) instead of fma(c*alpha, T, C)
-// (<= 1 ulp per term).
-constexpr int kDefaultRenderImpl = 4;        // 0 block, 1 warp, 2 compact, 3 compact with two pixels per lane (GSB_RENDER_IMPL overrides)
+// forward.cu:261-374, re-organised ("dual" kernel: the blend with the reference's own exponent expression, full-precision
+// expf or ex2.approx; the default table kernel below restructures the exponent).  Per 16x16 tile four warps that never
+// wait for each other: every warp streams the tile's sorted instance list on its own, 32 Gaussians at a time -- each lane
+// gathers ONE record (the warps of the CTA hit the same lines, so all but the first gather is an L1 hit) and tests it
+// against the warp's 8x8 pixel block with the exact footprint test straight from registers.  The lanes whose Gaussian
+// passed store their record at consecutive 48-byte slots (ballot rank) of the warp's private double-buffered list, so the
+// blend loop walks plain consecutive addresses and is branch-free: the three thresholds of forward.cu:336-353 become
+// predicates that gate a weight w = alpha*T (0 when the pixel skips the Gaussian) and the transmittance update.  An
+// all-zero sentinel record (opacity 0 -> alpha 0 -> skipped) pads an odd hit count so the loop always takes two records
+// per trip.  The next chunk's gathers are in flight while the current one is blended; a warp leaves as soon as its own 64
+// pixels are saturated.  Skipped Gaussians are exactly the ones every pixel of the block would `continue` past in the
+// reference loop; colours accumulate as fma(c, alpha*T, C) (the reference: fma(c*alpha, T, C), <= 1 ulp per term).
+constexpr int kDefaultRenderImpl = 4;        // 3 dual, 4 table (GSB_RENDER_IMPL overrides)
 constexpr int kSlotBytes = 48;               // A (16) | B (16) | green, blue (8) | pad (8)
 constexpr int kSlotsPerBuf = 33;             // 32 hits + sentinel
 // kPix = pixels per lane: 1 -> 8 warps per tile, each an 8x4 block; 2 -> 4 warps per tile, each an 8x8 block whose
@@ -1992,15 +1753,10 @@ static int render_frame_impl(const Frame& f, const uint32_t* point_list, cudaStr
   const uint32_t gx = f.gx, gy = f.gy;
   {
     StageTimer tm(kStRender, stream);
-    static const int render_impl = [] {
-      // A/B switch for profiling: "block" = barrier-per-batch variant, "warp" = per-warp bit-scan variant,
-      // "compact" = per-warp compacted hit list with a branch-free blend
+    static const int render_impl = [] {  // A/B switch for profiling: "dual" | "table"
       const char* e = getenv("GSB_RENDER_IMPL");
-      if (e && e[0] == 'b') return 0;
-      if (e && e[0] == 'c') return 2;
-      if (e && e[0] == 'd') return 3;  // "dual": compact, two pixels per lane
-      if (e && e[0] == 't') return 4;  // "table": dual + per-column / per-row exponent tables, packed f32x2, predicated blend
-      if (e && e[0] == 'w') return 1;
+      if (e && e[0] == 'd') return 3;
+      if (e && e[0] == 't') return 4;
       return kDefaultRenderImpl;
     }();
     const int impl = ((a->flags >> 8) & 7u) ? (int)((a->flags >> 8) & 7u) - 1 : render_impl;
@@ -2008,31 +1764,13 @@ static int render_frame_impl(const Frame& f, const uint32_t* point_list, cudaStr
 #define GSB_LAUNCH_RENDER_T(THREADS, ...)                                                                                \
   __VA_ARGS__<<<dim3(gx, gy), THREADS, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, \
                                                     a->out_color, a->out_depth, a->out_final_T, cap)
-#define GSB_LAUNCH_RENDER(KERNEL) GSB_LAUNCH_RENDER_T(kTilePixels, KERNEL)
     if (impl == 4 && fast) {
       GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_table_kernel);
-    } else if (impl == 3 || impl == 4) {  // the table kernel only exists for the ex2 blend: full-precision expf -> dual
-      if (fast)
-        GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<true, 2>);
-      else
-        GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<false, 2>);
-    } else if (impl == 2) {
-      if (fast)
-        GSB_LAUNCH_RENDER_T(kTilePixels, render_compact_kernel<true, 1>);
-      else
-        GSB_LAUNCH_RENDER_T(kTilePixels, render_compact_kernel<false, 1>);
-    } else if (impl == 1) {
-      if (fast)
-        GSB_LAUNCH_RENDER(render_warp_kernel<true>);
-      else
-        GSB_LAUNCH_RENDER(render_warp_kernel<false>);
+    } else if (fast) {  // the table kernel only exists for the ex2 blend: full-precision expf -> dual
+      GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<true, 2>);
     } else {
-      if (fast)
-        GSB_LAUNCH_RENDER(render_kernel<true>);
-      else
-        GSB_LAUNCH_RENDER(render_kernel<false>);
+      GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<false, 2>);
     }
-#undef GSB_LAUNCH_RENDER
 #undef GSB_LAUNCH_RENDER_T
   }
   count_launch();
@@ -2165,9 +1903,9 @@ int gsb_raster_forward_pair(const GsbRasterArgs* left, const GsbRasterArgs* righ
   const int pre_blocks = (left->P + kPreThreads - 1) / kPreThreads;
   {
     StageTimer tm(kStPreprocess, sl);
-    static const int occ = [] {  // A/B switch: GSB_PRE_OCC=5 -> 96 registers (spills) for 5 CTAs per SM instead of 4
+    static const int occ = [] {  // A/B switch: GSB_PRE_OCC=4 -> 114 registers, no spills, 4 CTAs per SM
       const char* e = getenv("GSB_PRE_OCC");
-      return e ? atoi(e) : 4;
+      return e ? atoi(e) : 5;  // measured on C1: 0.194 ms (5 CTAs / SM, 96 registers, 48 B of spills) vs 0.209 ms (4 CTAs, 114)
     }();
     if (occ == 5)
       preprocess_kernel<2, 5><<<pre_blocks, kPreThreads, 0, sl>>>(pp);

@@ -80,77 +80,61 @@ __global__ void __launch_bounds__(256) mark_bricks_kernel(const MarkParams m, co
                                                           uint32_t* __restrict__ list, uint32_t* __restrict__ counters,
                                                           uint32_t frame) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= m.nsx * m.nsy) return;
-  const int i = (s / m.nsx) * 4, j = (s % m.nsx) * 4;  // depth_sampling_stride = 4
-  const float p = depth[(size_t)i * m.W + j];
-  if (!(p > 0.f)) return;
-  // PointCloudFactory.cpp CreatePointCloudFromFloatDepthImage, all in double
-  const double z = (double)p;
-  const double x = __ddiv_rn(__dmul_rn((double)j - m.cx, z), m.fx);
-  const double y = __ddiv_rn(__dmul_rn((double)i - m.cy, z), m.fy);
-  int lo[3], hi[3];
+  const int lane = threadIdx.x & 31;
+  bool valid = s < m.nsx * m.nsy;
+  int lo[3] = {0, 0, 0}, hi[3] = {-1, -1, -1};
+  if (valid) {
+    const int i = (s / m.nsx) * 4, j = (s % m.nsx) * 4;  // depth_sampling_stride = 4
+    const float p = depth[(size_t)i * m.W + j];
+    valid = p > 0.f;
+    if (valid) {
+      // PointCloudFactory.cpp CreatePointCloudFromFloatDepthImage, all in double
+      const double z = (double)p;
+      const double x = __ddiv_rn(__dmul_rn((double)j - m.cx, z), m.fx);
+      const double y = __ddiv_rn(__dmul_rn((double)i - m.cy, z), m.fy);
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m.pose[4 * r], x), __dmul_rn(m.pose[4 * r + 1], y)),
-                                         __dmul_rn(m.pose[4 * r + 2], z)),
-                               m.pose[4 * r + 3]);
-    lo[r] = (int)floor(__ddiv_rn(__dadd_rn(w, -m.trunc), m.unit_length));
-    hi[r] = (int)floor(__ddiv_rn(__dadd_rn(w, m.trunc), m.unit_length));
+      for (int r = 0; r < 3; ++r) {
+        const double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m.pose[4 * r], x), __dmul_rn(m.pose[4 * r + 1], y)),
+                                             __dmul_rn(m.pose[4 * r + 2], z)),
+                                   m.pose[4 * r + 3]);
+        lo[r] = (int)floor(__ddiv_rn(__dadd_rn(w, -m.trunc), m.unit_length));
+        hi[r] = (int)floor(__ddiv_rn(__dadd_rn(w, m.trunc), m.unit_length));
+      }
+    }
   }
-  auto queue = [&](uint32_t h) {
-    if (hv.stamp[h] == frame) return;
-    if (atomicExch(&hv.stamp[h], frame) != frame) list[atomicAdd(&counters[kCntQueued], 1u)] = h;
-  };
+  // The 32 samples of a warp are neighbours on an image row: their boxes mostly name the same few bricks.  The warp walks
+  // the boxes in lockstep; lanes that hold the same brick elect one of them (match.any), and only that lane touches the hash
+  // table -- about a tenth of the probes, stamp reads and atomics of one-probe-per-sample.
   const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
-  const int total = nx * ny * nz;
-  if (total <= 8) {
-    // the usual box (sdf_trunc < unit_length: at most 2 bricks per axis): the first probes of all its bricks are issued
-    // together -- one memory round trip instead of up to eight dependent ones; only misses walk the table
-    unsigned long long key[8], seen[8];
-    uint32_t h[8], st[8];
+  const int total = valid ? nx * ny * nz : 0;
+  int most = total;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      key[i] = kHashEmpty;
-      if (i < total) {
-        const int bz = lo[2] + i % nz, by = lo[1] + (i / nz) % ny, bx = lo[0] + i / (nz * ny);
-        if (brick_key_ok(bx, by, bz)) {
-          key[i] = brick_key(bx, by, bz);
-          h[i] = brick_hash(key[i], hv.mask);
-          seen[i] = hv.keys[h[i]];
-          st[i] = hv.stamp[h[i]];
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i >= total) break;
-      if (key[i] == kHashEmpty) {
+  for (int o = 16; o > 0; o >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, o));
+  for (int i = 0; i < most; ++i) {
+    unsigned long long key = kHashEmpty;
+    int bx = 0, by = 0, bz = 0;
+    bool mine = i < total;
+    if (mine) {
+      bz = lo[2] + i % nz;
+      by = lo[1] + (i / nz) % ny;
+      bx = lo[0] + i / (nz * ny);
+      if (brick_key_ok(bx, by, bz)) {
+        key = brick_key(bx, by, bz);
+      } else {
         atomicAdd(&counters[kCntDropped], 1u);
-        continue;
+        mine = false;
       }
-      if (seen[i] == key[i]) {  // found at its home slot
-        if (st[i] != frame && atomicExch(&hv.stamp[h[i]], frame) != frame) list[atomicAdd(&counters[kCntQueued], 1u)] = h[i];
-        continue;
-      }
-      const int bz = lo[2] + i % nz, by = lo[1] + (i / nz) % ny, bx = lo[0] + i / (nz * ny);
-      const uint32_t hh = brick_find_or_insert(hv, counters, bx, by, bz);
-      if (hh == kSlotNone)
-        atomicAdd(&counters[kCntDropped], 1u);  // reported by gsb_tsdf_last_stats; the stage class grows the pool
-      else
-        queue(hh);
     }
-    return;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (!mine || (int)(__ffs(peers) - 1) != lane) continue;  // not the group's leader
+    const uint32_t h = brick_find_or_insert(hv, counters, bx, by, bz);
+    if (h == kSlotNone) {
+      atomicAdd(&counters[kCntDropped], 1u);  // reported by gsb_tsdf_last_stats; the stage class grows the pool
+      continue;
+    }
+    if (hv.stamp[h] == frame) continue;
+    if (atomicExch(&hv.stamp[h], frame) != frame) list[atomicAdd(&counters[kCntQueued], 1u)] = h;
   }
-  for (int bx = lo[0]; bx <= hi[0]; ++bx)
-    for (int by = lo[1]; by <= hi[1]; ++by)
-      for (int bz = lo[2]; bz <= hi[2]; ++bz) {
-        const uint32_t h = brick_find_or_insert(hv, counters, bx, by, bz);
-        if (h == kSlotNone) {
-          atomicAdd(&counters[kCntDropped], 1u);
-          continue;
-        }
-        queue(h);
-      }
 }
 
 struct FrameParams {

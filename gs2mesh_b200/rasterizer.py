@@ -16,7 +16,11 @@ import torch
 from . import _lib
 from ._lib import GsbRasterArgs, ptr
 
-DEFAULT_FLAGS = _lib.RASTER_EXACT_TILE_CULL
+# ONE default for every caller (stage class, compat module, raw wrapper): exact tile culling + the ex2.approx blend (the
+# table kernel).  EXACT_EXP_FLAGS selects the blend with the reference's own exponent expression and full-precision expf
+# (transmittance bit-identical to the reference binary; ~8 % slower per frame).
+DEFAULT_FLAGS = _lib.RASTER_EXACT_TILE_CULL | _lib.RASTER_FAST_EXP
+EXACT_EXP_FLAGS = _lib.RASTER_EXACT_TILE_CULL
 # first guess of the binning capacity of a scratch block: instances per Gaussian / floor (tests shrink these to provoke overflow)
 GUESS_PER_GAUSSIAN = 4
 MIN_GUESS = 1 << 20

@@ -78,8 +78,8 @@ class Renderer:
         if output_dir_root is not None and getattr(args, "renderer_save_json", True):  # argument_utils.py:63 default
             self.save_camera_data()
         self.write_images = output_dir_root is not None
-        # blend with ex2.approx instead of full-precision expf (GSB_RASTER_FAST_EXP): ~2e-7 relative on
-        # alpha, parity-tested against the reference rasterizer inside the 1e-4 budget
+        # the library default (rasterizer.DEFAULT_FLAGS): ex2.approx blend in the table kernel, parity-tested against the
+        # reference rasterizer at C1..C4; False selects the full-precision expf kernel (rasterizer.EXACT_EXP_FLAGS)
         self.fast_exp = True
         # render the left and the right eye on two side streams (each with its own scratch) so that the
         # small latency-bound binning kernels of one eye overlap the other eye's blend kernel
@@ -215,7 +215,7 @@ class Renderer:
         if not self._ready:
             raise RuntimeError("call prepare_renderer() first")
         if flags is None:
-            flags = rast.DEFAULT_FLAGS | (rast._lib.RASTER_FAST_EXP if self.fast_exp else 0)
+            flags = rast.DEFAULT_FLAGS if self.fast_exp else rast.EXACT_EXP_FLAGS
         vt = self._views[camera_number][side]
         rec = self._camera_table[camera_number, side]
         return rast.rasterize_forward(
@@ -229,7 +229,7 @@ class Renderer:
     def _enqueue_pair(self, camera_number, b, streams):
         """Both eyes of one view into buffer set `b`: rasterize (+ u8 conversion) on `streams` (left, right)."""
         mode = os.environ.get("GSB_PAIR_MODE", "fused")  # A/B switch: fused | noshare (fused preprocess, two depth sorts) | separate
-        flags = rast.DEFAULT_FLAGS | (rast._lib.RASTER_FAST_EXP if self.fast_exp else 0)
+        flags = rast.DEFAULT_FLAGS if self.fast_exp else rast.EXACT_EXP_FLAGS
         self._status[camera_number].zero_()
         if mode == "separate":
             for s in range(2):

@@ -81,14 +81,14 @@ int gsb_profile_collect(double* total_ms, uint64_t* samples, int n_stages);
                                          expf: ~2e-7 relative on alpha (parity budget is 1e-4)   */
 /* A/B overrides of the library defaults, for tests and profiling (0 in a field = library default, which the
  * environment variables GSB_RENDER_IMPL / GSB_PRE_SH may also change):
- *   bits 8..10  blend kernel: 1 block (one barrier per 256-record batch), 2 warp (per-warp bit scan), 3 compact
- *               (per-warp compacted hit list, 8x4 pixels per warp), 4 dual (compact, 8x8 pixels per warp), 5 table (dual
- *               with per-column / per-row exponent tables, packed f32x2 and predicated accumulation; default, needs
- *               GSB_RASTER_FAST_EXP -- without it the dual kernel runs)
+ *   bits 8..10  blend kernel: 4 dual (per-warp compacted hit lists, 8x8 pixels per warp, the reference's exponent
+ *               expression), 5 table (dual with per-column / per-row exponent tables, packed f32x2 and predicated
+ *               accumulation; default, needs GSB_RASTER_FAST_EXP -- without it the dual kernel runs); 1..3 (variants
+ *               removed in round 2) select dual
  *   bits 12..13 SH staging of full-degree blocks: 1 scalar reads, 2 16-byte reads (default), 3 per-lane bulk copies
  *               into padded slots + 16-byte reads
- * Variants 1-4 produce the same transmittance bit for bit (colours differ by accumulation rounding only); 5 rounds the
- * exponent differently (~1e-6 relative on alpha). */
+ * dual produces the reference's transmittance bit for bit when GSB_RASTER_FAST_EXP is off; table rounds the exponent
+ * differently (~1e-6 relative on alpha). */
 #define GSB_RASTER_RENDER_IMPL(n) (((uint32_t)(n) & 7u) << 8)
 #define GSB_RASTER_SH_MODE(n) (((uint32_t)(n) & 3u) << 12)
 #define GSB_RASTER_PAIR_SHARED_DEPTH 64u /* gsb_raster_forward_pair only (left->flags): the caller asserts that both eyes see

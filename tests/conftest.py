@@ -39,3 +39,20 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda", 0)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Worst parity numbers any image comparison of this session saw (tests/raster_compare.py) -> gpurun_out/, so that the
+    outlier budgets in the tests can be kept within 10x of what is actually observed on hardware."""
+    try:
+        import json
+
+        from tests import raster_compare
+
+        if raster_compare.OBSERVED["n"]:
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_session_observed.json"), "w") as f:
+                json.dump(raster_compare.OBSERVED, f, indent=1)
+    except Exception:
+        pass

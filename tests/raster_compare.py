@@ -8,6 +8,7 @@ difference in expf or an FMA contraction can flip for isolated pixels (SURVEY.md
 import numpy as np
 
 TOL = 1e-4
+OBSERVED = {"n": 0, "frac_bad": 0.0, "frac_bad_rel": 0.0, "max_err": 0.0, "max_err_rel": 0.0}  # worst over this session's comparisons
 
 
 REL_FLOOR = 0.05  # colours live in [0,1]: "relative" below this magnitude is measured against the floor
@@ -25,6 +26,10 @@ def compare_images(a, b):
     bad = err > TOL
     bad_rel = rel > TOL
     n = max(err.size, 1)
+    OBSERVED["n"] += 1
+    for k, v in (("frac_bad", bad.sum() / n), ("frac_bad_rel", bad_rel.sum() / n), ("max_err", err.max() if err.size else 0.0),
+                 ("max_err_rel", rel.max() if rel.size else 0.0)):
+        OBSERVED[k] = max(OBSERVED[k], float(v))
     return dict(frac_bad=float(bad.sum() / n), max_err=float(err.max()) if err.size else 0.0, n_bad=int(bad.sum()),
                 median=float(np.median(err)) if err.size else 0.0, frac_bad_rel=float(bad_rel.sum() / n),
                 max_err_rel=float(rel.max()) if rel.size else 0.0, p9999_rel=float(np.quantile(rel, 0.9999)) if rel.size else 0.0)

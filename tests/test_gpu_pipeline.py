@@ -228,10 +228,12 @@ FULL_SIZE_CASES = {
     "C3full": dict(scene.CONFIGS["C3"], width=1920, height=1080),
     "C4": dict(scene.CONFIGS["C4"]),  # 3M Gaussians, 1920x1080 (1080 = 67.5 tile rows), 1024^3 lattice
 }
-# outlier budgets of the full-size comparison against the reference binary: <= 10x the worst value observed on B200
-# over C1..C4 (profiles/r02_parity_observed.json), plus a ceiling on the size of any single outlier
-FULL_SIZE_BUDGET = 2e-4
-FULL_SIZE_MAX_ERR = 0.25
+# Outlier budgets of the full-size comparison against the reference binary, TRUE relative criterion
+# |ours - ref| <= 1e-4 * max(|ref|, 0.05) (tests/raster_compare.py): <= 10x the worst value observed on B200 over C1..C4 and
+# both eyes (profiles/r02e_parity_observed_table_kernel.json: default ex2/table kernel 3.9e-6 of the values, worst single
+# error 2.9e-3; full-precision expf kernel: no value outside, worst error 2.4e-7), plus a ceiling on any single outlier.
+FULL_SIZE_BUDGET = {"ex2": 4e-5, "expf": 1e-6}
+FULL_SIZE_MAX_ERR = {"ex2": 3e-2, "expf": 3e-6}
 
 
 def _record_observed(name, payload):
@@ -292,9 +294,11 @@ def test_full_size_parity_vs_reference_binary_and_oracle(oracle, gsb_lib, cuda_d
                 observed[f"side{side}_{tag}"] = dict(color=cmp, final_T=cmpT, num_rendered_ref=int(ref["num_rendered"]),
                                                      instances_binned=int(ours["counts"][0]))
                 _record_observed(case, observed)
-                assert cmp["frac_bad"] <= FULL_SIZE_BUDGET and cmp["median"] <= 1e-6, (side, flags, cmp)
-                assert cmp["max_err"] <= FULL_SIZE_MAX_ERR, (side, flags, cmp)
-                assert cmpT["frac_bad"] <= FULL_SIZE_BUDGET, (side, flags, cmpT)
+                assert cmp["frac_bad_rel"] <= FULL_SIZE_BUDGET[tag] and cmp["median"] <= 1e-6, (side, tag, cmp)
+                assert cmp["max_err"] <= FULL_SIZE_MAX_ERR[tag], (side, tag, cmp)
+                assert cmpT["frac_bad_rel"] <= FULL_SIZE_BUDGET[tag] and cmpT["max_err"] <= FULL_SIZE_MAX_ERR[tag], (side, tag, cmpT)
+                if tag == "expf":  # the reference's own exponent expression + expf: transmittance bit for bit
+                    assert cmpT["max_err"] == 0.0, (side, cmpT)
                 assert int(ours["counts"][1]) == ref["num_rendered"]  # the reference's instance count, exactly
 
     pair = r.render_image_pair(3, to_host=False)

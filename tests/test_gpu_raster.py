@@ -16,7 +16,9 @@ from tests.raster_compare import compare_images
 
 pytestmark = pytest.mark.gpu
 
-BUDGET = 2e-4  # fraction of pixels allowed outside 1e-4 relative
+BUDGET = 1e-4  # fraction of values allowed outside 1e-4 (hard thresholds flip on rounding); on these small frames one flipped
+               # pixel is already 4e-6 .. 1e-5 of the values.  Full-size frames: tests/test_gpu_pipeline.py (4e-5, observed 4e-6)
+MAX_ERR = 0.05  # ceiling on the size of any single outlier (observed on B200: <= 3e-3)
 
 
 def _case(num_points, W, H, seed=0, view=0, n_views=4, sh_degree=3):
@@ -66,6 +68,7 @@ def _assert_parity(a, b, what, budget=BUDGET):
     r = compare_images(a, b)
     assert r["frac_bad"] <= budget, (what, r)
     assert r["median"] <= 1e-6, (what, r)
+    assert r["max_err"] <= MAX_ERR, (what, r)
 
 
 def _oracle_best(oracle, inp):
@@ -244,9 +247,10 @@ def test_fast_exp_stays_inside_parity_budget(oracle, gsb_lib, cuda_device):
 
 @pytest.mark.parametrize("fast", [False, True])
 def test_blend_kernel_variants_agree(gsb_lib, cuda_device, fast):
-    """block / warp / compact / dual (and, up to the rounding of alpha, table) blend kernels decide the three thresholds of forward.cu:336-353 on the same
-    alpha and T values: the transmittance image is bit-identical; colour and depth differ only by the rounding of
-    fma(c, alpha*T, C) vs fma(c*alpha, T, C)."""
+    """dual (the reference's exponent expression) vs table (default: log2-domain exponent from per-column / per-row terms, packed
+    f32x2, predicated accumulation): same thresholds of forward.cu:336-353, same instance lists; alpha differs by rounding
+    (~1e-6 relative), so the images agree like against the reference.  Without GSB_RASTER_FAST_EXP both names run the dual
+    kernel with full-precision expf: bit-identical."""
     from gs2mesh_b200 import _lib
 
     for n, W, H, seed in [(10000, 640, 480, 1), (3000, 333, 250, 5)]:  # 333x250: ragged tiles on both axes
@@ -254,24 +258,18 @@ def test_blend_kernel_variants_agree(gsb_lib, cuda_device, fast):
         inp = _np_inputs(g, vt)
         base = _lib.RASTER_EXACT_TILE_CULL | (_lib.RASTER_FAST_EXP if fast else 0)
         outs = {name: _ours(cuda_device, inp, flags=base | _lib.RASTER_RENDER_IMPL(name)) for name in _lib.RENDER_IMPLS}
-        ref = outs["warp"]
-        for name, out in outs.items():
-            if name == "table" and fast:
-                # the table kernel (default) evaluates the exponent in the log2 domain from per-column / per-row terms:
-                # same thresholds, different rounding of alpha (~1e-6 relative) -> compared like against the reference
-                for k in ("color", "final_T", "depth"):
-                    cmp = compare_images(out[k], ref[k])
-                    assert cmp["frac_bad"] <= BUDGET and cmp["median"] <= 2e-6, (name, k, cmp)
-                np.testing.assert_array_equal(out["counts"], ref["counts"], err_msg=f"counts {name}")
-                continue
-            np.testing.assert_array_equal(out["final_T"], ref["final_T"], err_msg=f"final_T {name}")
-            np.testing.assert_array_equal(out["counts"], ref["counts"], err_msg=f"counts {name}")
-            np.testing.assert_allclose(out["color"], ref["color"], rtol=0, atol=5e-6, err_msg=f"color {name}")
-            np.testing.assert_allclose(out["depth"], ref["depth"], rtol=5e-6, atol=1e-6, err_msg=f"depth {name}")
-        if not fast:  # without GSB_RASTER_FAST_EXP the table variant is the dual kernel
-            np.testing.assert_array_equal(outs["table"]["color"], outs["dual"]["color"])
-        np.testing.assert_array_equal(outs["compact"]["color"], outs["dual"]["color"])  # same arithmetic per pixel
-        np.testing.assert_array_equal(outs["block"]["color"], outs["warp"]["color"])
+        ref, out = outs["dual"], outs["table"]
+        np.testing.assert_array_equal(out["counts"], ref["counts"])
+        if fast:
+            for k in ("color", "final_T", "depth"):
+                cmp = compare_images(out[k], ref[k])
+                assert cmp["frac_bad"] <= BUDGET and cmp["median"] <= 2e-6, (k, cmp)
+            assert np.abs(out["color"] - ref["color"]).max() > 0  # they are different kernels
+        else:
+            for k in ("color", "final_T", "depth"):
+                np.testing.assert_array_equal(out[k], ref[k], err_msg=k)
+        legacy = _ours(cuda_device, inp, flags=base | _lib.RASTER_RENDER_IMPL(2))  # a removed variant's number selects dual
+        np.testing.assert_array_equal(legacy["color"], ref["color"])
 
 
 def test_sh_staging_variants_agree(gsb_lib, cuda_device):
