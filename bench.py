@@ -252,8 +252,10 @@ def run_ours(args, cfg, rank, local, world):
     sampler.start()
     barrier(world)
     ev0.record()
+    host_t0 = time.perf_counter()
     for i in mine:
         step(i)
+    host_enqueue_ms = 1e3 * (time.perf_counter() - host_t0) / max(K, 1)  # host time to ENQUEUE a step (no waiting)
     evr = torch.cuda.Event(enable_timing=True)
     evr.record()
     if world > 1:
@@ -389,6 +391,7 @@ def run_ours(args, cfg, rank, local, world):
                     "pair_mode": os.environ.get("GSB_PAIR_MODE", "fused"),
                     "pairs_sharing_one_depth_sort": round(float(np.mean([renderer._shared_depth[i] for i in mine])), 3) if mine else None,
                     "pairs_in_flight": int(renderer.pairs_in_flight),
+                    "host_enqueue_ms_per_step": round(host_enqueue_ms, 4),
                     "caller_stream_priority": int(torch.cuda.current_stream().priority),
                     "per_view": {k: round(v, 1) for k, v in mean.items()},
                     "tsdf_volume": {"kind": "unbounded hashed brick pool", "bricks_open_after_timed_region": int(pool_after["bricks"]),

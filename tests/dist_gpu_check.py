@@ -66,11 +66,22 @@ def main():
     vol.reduce_across_ranks(dst=None)
     torch.cuda.synchronize()
     n, nvox, err, cerr = compare(vol, seq, f"all-reduce on rank {rank}")
-    # (2) reduce to the last rank: only its volume changes (a small scratch first: the retry path of the workspace protocol)
+    # (2) reduce to the last rank: only its volume changes.  First with a scratch that holds the index exchange but no payload:
+    #     every rank must get GSB_ERR_WORKSPACE together, with the same required size (the workspace protocol of the C ABI)
+    from gs2mesh_b200 import _lib
+
     root = world - 1
     vol2 = fuse(mine)
     before = vol2.export_units()
-    vol2._reduce_scratch = None
+    comm = vol2._comm(None)
+    small = torch.empty(int(vol2._L.gsb_tsdf_reduce_scratch_bytes(vol2._h, world, 0)), dtype=torch.uint8, device=vol2.device)
+    rc = vol2._L.gsb_tsdf_reduce(vol2._h, comm, world, rank, root, _lib.ptr(small), small.numel(), vol2._stream())
+    assert rc == _lib.GSB_ERR_WORKSPACE, rc
+    need = torch.tensor([int(vol2._L.gsb_tsdf_reduce_required_bytes())], dtype=torch.int64, device=vol2.device)
+    lo, hi = need.clone(), need.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert int(lo) == int(hi) > small.numel(), "ranks disagree on the scratch the merge needs"
     vol2.reduce_across_ranks(dst=root)
     torch.cuda.synchronize()
     if rank == root:
