@@ -38,6 +38,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "stereo_pairs_per_sec_rendered_and_tsdf_fused"
+MERGE_DST = None if os.environ.get("BENCH_MERGE", "reduce") == "allreduce" else 0  # A/B: ncclReduce to rank 0 | ncclAllReduce
 UNIT = "stereo-pairs/s"
 
 
@@ -240,7 +241,7 @@ def run_ours(args, cfg, rank, local, world):
     for i in (mine * ((Wm // max(len(mine), 1)) + 1))[:Wm]:
         step(i)
     if world > 1:
-        vol.reduce_across_ranks(dst=0)
+        vol.reduce_across_ranks(dst=MERGE_DST)
     vol.reset()
     barrier(world)
     _lib.profile_enable(False)
@@ -259,7 +260,7 @@ def run_ours(args, cfg, rank, local, world):
     evr = torch.cuda.Event(enable_timing=True)
     evr.record()
     if world > 1:
-        vol.reduce_across_ranks(dst=0)
+        vol.reduce_across_ranks(dst=MERGE_DST)
     ev1.record()
     barrier(world)
     reduce_ms = max_over_ranks(evr.elapsed_time(ev1), world)
@@ -291,6 +292,15 @@ def run_ours(args, cfg, rank, local, world):
     prof = _lib.profile_collect()
     serial_ms_per_step = pe0.elapsed_time(pe1) / n_prof
     renderer.overlap_eyes = True
+    merge_phases = None
+    if world > 1:  # the phases of one more merge of the volume just fused (CUDA events inside gsb_tsdf_reduce, this rank's view)
+        _lib.profile_enable(True)
+        barrier(world)
+        vol.reduce_across_ranks(dst=MERGE_DST)
+        torch.cuda.synchronize()
+        _lib.profile_enable(False)
+        merge_phases = {k: round(ms / max(n, 1), 4) for k, (ms, n) in _lib.profile_collect().items() if k.startswith("merge_") and n}
+    prof = {k: v for k, v in prof.items() if not k.startswith("merge_")}
 
     # ---- e2e: public classes with host buffers, H2D + D2H every step
     vol.reset()
@@ -316,7 +326,7 @@ def run_ours(args, cfg, rank, local, world):
         stage.integrate(host_depth, out["host_left_u8"], rigs[i]["left"])
     renderer.check_status(views)
     if world > 1:
-        vol.reduce_across_ranks(dst=0)
+        vol.reduce_across_ranks(dst=MERGE_DST)
     barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
     e2e_value = total_views / e2e_s
@@ -369,10 +379,12 @@ def run_ours(args, cfg, rank, local, world):
                 "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic.get(dom),
                 "algorithmic_bytes_per_launch": int(bytes_per_launch[dom]), "avg_ms": kernels[dom]["avg_ms"]}
     if dom == "render":
-        # what ncu shows for this kernel (profiles/r01i_ncu_full_summary.txt): the records are L1/L2-resident and the
+        # what ncu shows for this kernel (profiles/r02k_ncu_full_summary.txt): the records are L1/L2-resident and the
         # kernel is limited by instruction issue, so the HBM fraction above is a lower bound on its quality, not its limiter
-        roofline["note"] = ("issue-bound: 85 % issue-slot utilisation, DRAM throughput 2.6 % of peak in the ncu capture; "
-                            "algorithmic bytes = 40 B per (Gaussian, tile) instance + 16 B per pixel")
+        roofline["note"] = ("issue-bound: 76 % issue-slot utilisation while warps are resident (31 % of the warp slots), DRAM "
+                            "throughput 2.9 % of peak in the ncu capture (profiles/r02k_ncu_full_summary.txt); algorithmic bytes = "
+                            "40 B per (Gaussian, tile) instance + 16 B per pixel, measured DRAM traffic is 0.2x of that (records are "
+                            "L1/L2 hits)")
 
     # ---- CPU baseline: Open3D-0.17-equivalent TSDF (oracle port) on a bounded sample, all host threads
     cpu_baseline = None
@@ -384,8 +396,8 @@ def run_ours(args, cfg, rank, local, world):
         "ms_per_step": round(elapsed_ms / max(K, 1), 4), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": shared_config(args, cfg, total_views, world, K),
-        "details": {"volume_merge": None if world == 1 else {"kind": "gsb_tsdf_reduce: union of the ranks' bricks, one ncclReduce to rank 0",
-                                                             "ms": round(reduce_ms, 3)},
+        "details": {"volume_merge": None if world == 1 else {"kind": "gsb_tsdf_reduce: union of the ranks' bricks, one " + ("ncclReduce to rank 0" if MERGE_DST == 0 else "ncclAllReduce"),
+                                                             "ms": round(reduce_ms, 3), "phases_ms_rank0": merge_phases},
                     "l2": f"inputs larger than L2: {236 * cfg['num_points'] / 1e6:.0f} MB of Gaussian parameters re-read per pair + brick store per view",
                     "tsdf_colour": "fused (float4 running mean)", "exact_tile_cull": True,
                     "pair_mode": os.environ.get("GSB_PAIR_MODE", "fused"),

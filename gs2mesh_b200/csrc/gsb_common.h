@@ -71,6 +71,10 @@ enum Stage {
   kStDepthPrep,
   kStMarkBricks,
   kStIntegrate,
+  kStMergeIndex,   // gsb_tsdf_reduce: brick index exchange (all-gather, union, broadcast) incl. the host read of the union size
+  kStMergePack,    //                  pack + to-sums (in-place to-sums on the canonical rank)
+  kStMergeReduce,  //                  the NCCL reduce / all-reduce of the payload
+  kStMergeUnpack,  //                  from-sums (+ unpack) where the result lives
   kStCount
 };
 

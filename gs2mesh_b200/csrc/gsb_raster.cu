@@ -40,7 +40,8 @@ thread_local char g_error[512] = {0};
 std::atomic<uint64_t> g_launches{0};
 Profiler g_prof;
 static const char* kStageNames[kStCount] = {"preprocess", "depth_sort", "emit", "tile_sort", "tile_ranges",
-                                            "render",     "to_u8", "prepare_depth", "mark_bricks", "integrate"};
+                                            "render",     "to_u8", "prepare_depth", "mark_bricks", "integrate",
+                                            "merge_index", "merge_pack", "merge_reduce", "merge_unpack"};
 static thread_local int64_t g_required_instances = 0;
 
 namespace {

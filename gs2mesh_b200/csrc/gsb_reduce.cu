@@ -328,6 +328,11 @@ int gsb_tsdf_reduce(GsbVolume* vol, void* nccl_comm, int nranks, int rank, int r
   float4* color = reinterpret_cast<float4*>(d.color);
 
   // 1. every rank's brick list
+  StageTimer* tm_index = new StageTimer(kStMergeIndex, stream);
+  struct Guard {  // the timer closes when the index phase ends, on every exit path
+    StageTimer*& t;
+    ~Guard() { delete t; t = nullptr; }
+  } guard{tm_index};
   GSB_NCCL_OK(nccl().GroupStart());
   GSB_NCCL_OK(nccl().AllGather(d.counters + kCntPool, rs.counts, 1, ncclUint32, comm, stream));
   GSB_NCCL_OK(nccl().AllGather(index, rs.gathered, (size_t)pool * 4, ncclInt32, comm, stream));
@@ -347,6 +352,8 @@ int gsb_tsdf_reduce(GsbVolume* vol, void* nccl_comm, int nranks, int rank, int r
   uint32_t n_union = 0;  // the one host read of the merge: NCCL needs the payload size as a count
   GSB_CUDA_OK(cudaMemcpyAsync(&n_union, rs.n_union, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   GSB_CUDA_OK(cudaStreamSynchronize(stream));
+  delete tm_index;
+  tm_index = nullptr;
   if (n_union > pool) n_union = pool;
   if (n_union == 0) return GSB_OK;
   rs = carve_reduce(scratch, pool, nranks, canonical ? 0 : n_union, with_color);
@@ -360,37 +367,46 @@ int gsb_tsdf_reduce(GsbVolume* vol, void* nccl_comm, int nranks, int rank, int r
   const float* send_color = nullptr;
   float* recv_tw;
   float* recv_color = nullptr;
-  if (canonical) {  // the pool prefix [0, n_union) IS the payload: convert and exchange it in place
-    prefix_sums_kernel<<<pgrid, 256, 0, stream>>>(tw, color, n_union, 0);
-    count_launch();
-    send_tw = recv_tw = d.tsdf_weight;
-    send_color = recv_color = d.color;
-  } else {
-    map_canonical_kernel<<<(n_union + 255) / 256, 256, 0, stream>>>(keys, d.hash_vals, mask, pool, rs.canon, rs.n_union, rs.slot_of);
-    pack_sums_kernel<<<pgrid, 256, 0, stream>>>(tw, color, rs.slot_of, n_union, rs.ptw, rs.pcolor);
-    count_launch(2);
-    send_tw = recv_tw = reinterpret_cast<float*>(rs.ptw);
-    send_color = recv_color = reinterpret_cast<float*>(rs.pcolor);
+  {
+    StageTimer tm(kStMergePack, stream);
+    if (canonical) {  // the pool prefix [0, n_union) IS the payload: convert and exchange it in place
+      prefix_sums_kernel<<<pgrid, 256, 0, stream>>>(tw, color, n_union, 0);
+      count_launch();
+      send_tw = recv_tw = d.tsdf_weight;
+      send_color = recv_color = d.color;
+    } else {
+      map_canonical_kernel<<<(n_union + 255) / 256, 256, 0, stream>>>(keys, d.hash_vals, mask, pool, rs.canon, rs.n_union, rs.slot_of);
+      pack_sums_kernel<<<pgrid, 256, 0, stream>>>(tw, color, rs.slot_of, n_union, rs.ptw, rs.pcolor);
+      count_launch(2);
+      send_tw = recv_tw = reinterpret_cast<float*>(rs.ptw);
+      send_color = recv_color = reinterpret_cast<float*>(rs.pcolor);
+    }
   }
   int rc;
   if ((rc = check_launch("tsdf_reduce pack", stream, false))) return rc;
   // 5. ONE reduce of the payload (two buffers in one NCCL group)
-  GSB_NCCL_OK(nccl().GroupStart());
-  if (all) {
-    GSB_NCCL_OK(nccl().AllReduce(send_tw, recv_tw, pairs * 4, ncclFloat32, ncclSum, comm, stream));
-    if (with_color) GSB_NCCL_OK(nccl().AllReduce(send_color, recv_color, pairs * 8, ncclFloat32, ncclSum, comm, stream));
-  } else {
-    GSB_NCCL_OK(nccl().Reduce(send_tw, recv_tw, pairs * 4, ncclFloat32, ncclSum, root, comm, stream));
-    if (with_color) GSB_NCCL_OK(nccl().Reduce(send_color, recv_color, pairs * 8, ncclFloat32, ncclSum, root, comm, stream));
+  {
+    StageTimer tm(kStMergeReduce, stream);
+    GSB_NCCL_OK(nccl().GroupStart());
+    if (all) {
+      GSB_NCCL_OK(nccl().AllReduce(send_tw, recv_tw, pairs * 4, ncclFloat32, ncclSum, comm, stream));
+      if (with_color) GSB_NCCL_OK(nccl().AllReduce(send_color, recv_color, pairs * 8, ncclFloat32, ncclSum, comm, stream));
+    } else {
+      GSB_NCCL_OK(nccl().Reduce(send_tw, recv_tw, pairs * 4, ncclFloat32, ncclSum, root, comm, stream));
+      if (with_color) GSB_NCCL_OK(nccl().Reduce(send_color, recv_color, pairs * 8, ncclFloat32, ncclSum, root, comm, stream));
+    }
+    GSB_NCCL_OK(nccl().GroupEnd());
   }
-  GSB_NCCL_OK(nccl().GroupEnd());
   // 6. back to (mean, weight) where the result lives
-  if (canonical) {
-    prefix_sums_kernel<<<pgrid, 256, 0, stream>>>(tw, color, n_union, 1);
-    count_launch();
-  } else if (all) {
-    unpack_means_kernel<<<pgrid, 256, 0, stream>>>(tw, color, rs.slot_of, n_union, rs.ptw, rs.pcolor);
-    count_launch();
+  {
+    StageTimer tm(kStMergeUnpack, stream);
+    if (canonical) {
+      prefix_sums_kernel<<<pgrid, 256, 0, stream>>>(tw, color, n_union, 1);
+      count_launch();
+    } else if (all) {
+      unpack_means_kernel<<<pgrid, 256, 0, stream>>>(tw, color, rs.slot_of, n_union, rs.ptw, rs.pcolor);
+      count_launch();
+    }
   }
   return check_launch("tsdf_reduce unpack", stream, false);
 }

@@ -2,9 +2,14 @@
 // delegates to Open3D.  Nothing in the product path may import, link or call this file.
 //
 // PARITY UNPINNED: the arithmetic lives in the third-party wheel open3d==0.17.0
-// (pinned in /root/reference/requirements.txt:11; README.md:371 insists on that version).
+// (pinned in /root/reference/requirements.txt:15; README.md:371 insists on that version).
 // The wheel is not installed here, its source is not under /root/reference and there is
-// no network, and the reference has no test that pins TSDF values.  This file restates
+// no network, and the reference has no test that pins TSDF values.  Round 2 tried to obtain it in the
+// dev container and on the GPU box (scripts/try_open3d.sh; transcripts profiles/r02_open3d_attempt_*.log:
+// no index reachable, nothing in /opt/wheelhouse, and 0.17.0 has no cp312 wheel).  The pin is prepared:
+// tests/golden/make_tsdf_golden.py runs the literal Open3D call sequence and writes fixtures that
+// tests/test_oracle_tsdf.py::test_open3d_golden_voxel_values / tests/test_oracle_mesh.py consume; they
+// skip until somebody with the wheel runs the script.  This file restates
 // Open3D 0.17.0's published algorithm
 //   cpp/open3d/pipelines/integration/ScalableTSDFVolume.cpp  (Integrate, OpenVolumeUnit,
 //       LocateVolumeUnit, ExtractTriangleMesh; ctor defaults volume_unit_resolution=16,
