@@ -304,26 +304,40 @@ def run_ours(args, cfg, rank, local, world):
 
     # ---- e2e: public classes with host buffers, H2D + D2H every step
     vol.reset()
-    host_depth = torch.empty(H, W, dtype=torch.float32).pin_memory()
-    dev_depth = torch.empty(H, W, dtype=torch.float32, device=dev)
+    host_depth = [torch.empty(H, W, dtype=torch.float32).pin_memory() for _ in range(2)]
+    dev_depth = [torch.empty(H, W, dtype=torch.float32, device=dev) for _ in range(2)]
+    depth_ready = [None, None]
     K_e2e = K
     barrier(world)
     t0 = time.perf_counter()
-    # software-pipelined by `pairs_in_flight` pairs: while the host consumes pair i (waits for its frames, reads the
-    # depth back, hands depth + colour to TSDF.integrate, which uploads them), the next pairs are already being rendered
+    # software-pipelined: while the host consumes pair i (waits for its frames in pinned memory, reads the depth back, hands
+    # depth + colour to TSDF.integrate, which uploads them), the next `pairs_in_flight` pairs are already being rendered; the
+    # depth read-back of pair i is consumed one iteration later, so no step waits for a copy it has just enqueued
     views = mine[:K_e2e]
     lag = max(1, int(renderer.pairs_in_flight))
     pending = [renderer.render_image_pair(v, to_host=True, wait=False) for v in views[:lag]]
+    fuse_next = None  # (view, pinned host frame, buffer index) of the pair whose depth is still travelling to the host
+
+    def fuse(item):
+        i, rgb_host, k = item
+        depth_ready[k].synchronize()  # the float depth of pair i is in pinned host memory
+        # what a host-side stereo stage would hand back: float depth + the uint8 left frame, both on the host
+        stage.integrate(host_depth[k], rgb_host, rigs[i]["left"])
+
     for n, i in enumerate(views):
+        if fuse_next is not None:  # pair n-1, before the next render call is entered (the renderer's buffer-rotation contract)
+            fuse(fuse_next)
         out = pending.pop(0)
         if n + lag < len(views):
             pending.append(renderer.render_image_pair(views[n + lag], to_host=True, wait=False))
         out["ready"].synchronize()  # both uint8 frames of pair i are in pinned host memory
-        vol.prepare_depth(out["depth"], W, H, final_T=out["final_T"], out=dev_depth)  # expected depth of the left view
-        host_depth.copy_(dev_depth, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        # what a host-side stereo stage would hand back: float depth + the uint8 left frame, both on the host
-        stage.integrate(host_depth, out["host_left_u8"], rigs[i]["left"])
+        k = n & 1
+        vol.prepare_depth(out["depth"], W, H, final_T=out["final_T"], out=dev_depth[k])  # expected depth of the left view
+        host_depth[k].copy_(dev_depth[k], non_blocking=True)
+        depth_ready[k] = torch.cuda.current_stream().record_event()
+        fuse_next = (i, out["host_left_u8"], k)
+    if fuse_next is not None:
+        fuse(fuse_next)
     renderer.check_status(views)
     if world > 1:
         vol.reduce_across_ranks(dst=MERGE_DST)
