@@ -3,29 +3,31 @@
 // Behavioural contract = the reference's forward pass
 //   DGR/cuda_rasterizer/rasterizer_impl.cu:198-336 (Rasterizer::forward)
 //   DGR/cuda_rasterizer/forward.cu:155-256 (preprocess), :261-374 (render)
-// (DGR = third_party/gaussian-splatting/submodules/diff-gaussian-rasterization), but the
-// pipeline is organised differently:
+// (DGR = third_party/gaussian-splatting/submodules/diff-gaussian-rasterization), called twice per stereo pair by
+// gs2mesh_utils/renderer_utils.py:378-389 -- but the pipeline is organised differently:
 //
-//   preprocess   one WARP per 32 consecutive Gaussians.  The warp's parameter block is
-//                contiguous in every reference tensor ([P,3] xyz / scales, [P,4] quaternions,
-//                [P] opacities, [P,M,3] SH = 6 KB per warp) and is staged into shared memory
-//                with 1-D bulk TMA copies (cp.async.bulk + mbarrier).  The 6 KB SH block is
-//                only fetched when at least one Gaussian of the warp survives culling, and is
-//                read back with 16-byte loads.  Results are written as three coalesced record planes:
-//                  recA = (px, py, z_view, opacity)  recB = (conic a, b, c, red)  recC = (green, blue)
+//   preprocess   one WARP per 32 consecutive Gaussians, ONE launch for both eyes of a stereo pair.  The warp's parameter
+//                block is contiguous in every reference tensor ([P,3] xyz / scales, [P,4] quaternions,
+//                [P] opacities, [P,M,3] SH = 6 KB per warp) and is staged into shared memory once
+//                with 1-D bulk TMA copies (cp.async.bulk + mbarrier); the 3-D covariance is computed once; projection,
+//                binning and SH shading run per eye.  The 6 KB SH block is only fetched when at least one Gaussian of the
+//                warp survives culling in some eye, and is read back with 16-byte loads.  Per eye three coalesced record
+//                planes: recA = (px, py, z_view, opacity)  recB = (conic a, b, c, red)  recC = (green, blue)
 //   binning      exact (Gaussian,tile) test: a pair is kept only if the tile's pixel lattice can
 //                reach alpha >= 1/255 -- the image is bit-identical to rectangle binning
 //                (rasterizer_impl.cu:88-107) with far fewer instances to sort and blend.
 //   sort         the reference's order inside a tile is (depth bits, Gaussian index) ascending
 //                (stable radix sort of tile << 32 | depth keys emitted in index order).  Here: stable
-//                LSD radix sort of the P (depth bits, index) pairs, instances emitted in that order,
+//                LSD radix sort of the P (depth bits, index) pairs -- ONE sort per pair when both eyes see every Gaussian at
+//                the same view depth --, a one-pass scan of the tile counts in that order, instances emitted in that order,
 //                then a stable sort of the R instances on the tile id alone (gsb_radix.cuh).
 //   render       per 16x16 tile, four warps that never wait for each other: each streams the tile's
 //                list, keeps the records its 8x8 pixel block can see (exact footprint test) in a
-//                private compacted shared-memory list and blends them branch-free, two pixels per lane;
+//                private compacted shared-memory list -- stored as per-column / per-row terms of the exponent -- and blends
+//                them with packed f32x2 arithmetic and predicated accumulation, two pixels per lane;
 //                also accumulates the expected-depth channel (sum z*alpha*T) the TSDF stage consumes.
 //
-// All kernels run on the caller's stream.
+// All kernels run on the caller's stream(s).
 #include <algorithm>
 #include <cstdlib>
 
@@ -1372,17 +1374,19 @@ __global__ void __launch_bounds__(kTilePixels / 2, 7)
         sts128(dst + kTabC, make_float4(cB.w, cC.x, cC.y, cA.z));
         sts128(dst + kTabThr, make_float4(l2o, 0.f, 0.f, 0.f));
       }
-      if (lane < kTabSlotBytes / 16) {  // sentinel after the last hit: u' = -1e30 -> alpha 0 -> skipped
-        const float big = lane < 4 ? -1.0e30f : 0.f;  // quads 0..3 = the X table: (u', v, u', v)
-        sts128(a0 + n * kTabSlotBytes + 16 * lane, make_float4(big, 0.f, big, 0.f));
+      if (n != 0) {  // (a chunk none of whose records reaches the block costs no more than the test)
+        if ((n & 1) && lane < kTabSlotBytes / 16) {  // odd count: sentinel after the last hit, u' = -1e30 -> alpha 0 -> skipped
+          const float big = lane < 4 ? -1.0e30f : 0.f;  // quads 0..3 = the X table: (u', v, u', v)
+          sts128(a0 + n * kTabSlotBytes + 16 * lane, make_float4(big, 0.f, big, 0.f));
+        }
+        __syncwarp();  // the list is visible to every lane of the warp
+        const uint32_t end = (uint32_t)n * kTabSlotBytes;
+        for (uint32_t off = 0; off < end; off += 2 * kTabSlotBytes) {
+          blend(off);
+          blend(off + kTabSlotBytes);
+        }
+        __syncwarp();  // every lane is done reading before the next chunk overwrites the slots
       }
-      __syncwarp();  // the list is visible to every lane of the warp
-      const uint32_t end = (uint32_t)n * kTabSlotBytes;
-      for (uint32_t off = 0; off < end; off += 2 * kTabSlotBytes) {
-        blend(off);
-        blend(off + kTabSlotBytes);
-      }
-      __syncwarp();  // every lane is done reading before the next chunk overwrites the slots
       cA = nA;
       cB = nB;
       cC = nC;

@@ -79,6 +79,20 @@ struct MarkParams {
 __global__ void __launch_bounds__(256) mark_bricks_kernel(const MarkParams m, const HashView hv, const float* __restrict__ depth,
                                                           uint32_t* __restrict__ list, uint32_t* __restrict__ counters,
                                                           uint32_t frame) {
+  // entries this CTA queues: collected in shared memory and appended to the frame's work list with ONE global atomic per
+  // CTA (every append used to bump the same global counter: ~2200 same-address atomics per frame, serialised in L2)
+  constexpr int kLocal = 1024;
+  __shared__ uint32_t s_list[kLocal];
+  __shared__ uint32_t s_n, s_base;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  auto append = [&](uint32_t h) {
+    const uint32_t k = atomicAdd(&s_n, 1u);
+    if (k < (uint32_t)kLocal)
+      s_list[k] = h;
+    else
+      list[atomicAdd(&counters[kCntQueued], 1u)] = h;  // more than the CTA's buffer holds: straight to the list
+  };
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool valid = s < m.nsx * m.nsy;
@@ -110,31 +124,63 @@ __global__ void __launch_bounds__(256) mark_bricks_kernel(const MarkParams m, co
   int most = total;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, o));
-  for (int i = 0; i < most; ++i) {
-    unsigned long long key = kHashEmpty;
-    int bx = 0, by = 0, bz = 0;
-    bool mine = i < total;
-    if (mine) {
-      bz = lo[2] + i % nz;
-      by = lo[1] + (i / nz) % ny;
-      bx = lo[0] + i / (nz * ny);
-      if (brick_key_ok(bx, by, bz)) {
-        key = brick_key(bx, by, bz);
-      } else {
-        atomicAdd(&counters[kCntDropped], 1u);
-        mine = false;
+  // Three box cells per trip: their votes and the leaders' first probes are independent, so the memory round trips of a trip
+  // overlap (the kernel is one warp's chain of dependent L2 accesses: 39 us with one cell per trip on C1).
+  constexpr int kPer = 3;
+  for (int i0 = 0; i0 < most; i0 += kPer) {
+    unsigned long long key[kPer], seen[kPer];
+    uint32_t h[kPer], st[kPer];
+    int bx[kPer], by[kPer], bz[kPer];
+    bool lead[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int i = i0 + u;
+      key[u] = kHashEmpty;
+      seen[u] = kHashEmpty;
+      h[u] = 0;
+      st[u] = 0;
+      bx[u] = by[u] = bz[u] = 0;
+      bool mine = i < total;
+      if (mine) {
+        bz[u] = lo[2] + i % nz;
+        by[u] = lo[1] + (i / nz) % ny;
+        bx[u] = lo[0] + i / (nz * ny);
+        if (brick_key_ok(bx[u], by[u], bz[u])) {
+          key[u] = brick_key(bx[u], by[u], bz[u]);
+        } else {
+          atomicAdd(&counters[kCntDropped], 1u);
+          mine = false;
+        }
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, key[u]);
+      lead[u] = mine && (int)(__ffs(peers) - 1) == lane;  // lanes naming the same brick elect the lowest one
+      if (lead[u]) {  // first probe at the home slot + its stamp, issued before anything waits
+        h[u] = brick_hash(key[u], hv.mask);
+        seen[u] = hv.keys[h[u]];
+        st[u] = hv.stamp[h[u]];
       }
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (!mine || (int)(__ffs(peers) - 1) != lane) continue;  // not the group's leader
-    const uint32_t h = brick_find_or_insert(hv, counters, bx, by, bz);
-    if (h == kSlotNone) {
-      atomicAdd(&counters[kCntDropped], 1u);  // reported by gsb_tsdf_last_stats; the stage class grows the pool
-      continue;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      if (!lead[u]) continue;
+      uint32_t hh = h[u];
+      if (seen[u] != key[u]) {  // not at its home slot (collision or not yet opened): walk / insert
+        hh = brick_find_or_insert(hv, counters, bx[u], by[u], bz[u]);
+        if (hh == kSlotNone) {
+          atomicAdd(&counters[kCntDropped], 1u);  // reported by gsb_tsdf_last_stats; the stage class grows the pool
+          continue;
+        }
+        st[u] = hv.stamp[hh];
+      }
+      if (st[u] == frame) continue;
+      if (atomicExch(&hv.stamp[hh], frame) != frame) append(hh);
     }
-    if (hv.stamp[h] == frame) continue;
-    if (atomicExch(&hv.stamp[h], frame) != frame) list[atomicAdd(&counters[kCntQueued], 1u)] = h;
   }
+  __syncthreads();
+  const uint32_t n_local = min(s_n, (uint32_t)kLocal);
+  if (threadIdx.x == 0 && n_local) s_base = atomicAdd(&counters[kCntQueued], n_local);
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < n_local; k += blockDim.x) list[s_base + k] = s_list[k];
 }
 
 struct FrameParams {
