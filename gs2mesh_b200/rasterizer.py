@@ -167,6 +167,13 @@ def rasterize_forward_pair(*, means3D, opacities, shs, scales, rotations, sh_deg
     W, H = int(width), int(height)
     M = int(shs.shape[1])
     L = _lib.lib()
+    if P == 0:  # rasterize_points.cu:68-77: with no points the zero-filled outputs are returned untouched
+        for eye, st in zip(eyes, streams):
+            with torch.cuda.stream(st):
+                for k in ("out_color", "out_depth", "out_final_T", "counts_out"):
+                    if eye.get(k) is not None:
+                        eye[k].zero_()
+        return
     with torch.cuda.device(device):
         blocks = []
         for s_, (eye, st) in enumerate(zip(eyes, streams)):

@@ -187,3 +187,60 @@ def test_in_memory_handoff_equals_file_round_trip(oracle, gsb_lib, cuda_device, 
     for key in a:
         np.testing.assert_array_equal(a[key][0], b[key][0], err_msg=f"tsdf/weight of unit {key}")
         np.testing.assert_array_equal(a[key][1], b[key][1], err_msg=f"colour of unit {key}")
+
+
+@pytest.mark.parametrize("num_points,W,H,deg", [(4099, 333, 250, 3), (777, 250, 130, 1), (33, 64, 48, 0)])
+def test_pair_entry_point_on_ragged_inputs(gsb_lib, cuda_device, num_points, W, H, deg):
+    """`gsb_raster_forward_pair` through the ctypes stub against two `gsb_raster_forward` calls on awkward shapes: a Gaussian
+    count that is no multiple of the warp size (the last warp takes the plain-load path), ragged tile rows / columns, lower SH
+    degrees; with and without a shared depth order; eyes on one stream and on two."""
+    import torch
+
+    from gs2mesh_b200 import _lib, camera as cam
+    from gs2mesh_b200 import rasterizer as rast
+
+    g = scene.make_gaussians(num_points, seed=40 + deg, sh_degree=deg)
+    rigs, _ = scene.make_stereo_cameras(10, W, H)
+    dev = cuda_device
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    means, op, shs, sc, ro = t(g.xyz), t(g.opacity).reshape(-1), t(g.features), t(g.scaling), t(g.rotation)
+    bg = torch.zeros(3, device=dev)
+    for view in (0, 3):  # rig 0: eyes share their view depths; rig 3: the z rows differ by an ulp
+        vts = [cam.view_transforms_from_camera(rigs[view][s]) for s in ("left", "right")]
+        zrow = [vt.world_view.reshape(-1)[[2, 6, 10, 14]].view(np.uint32) for vt in vts]
+        shared = bool(np.array_equal(zrow[0], zrow[1]))
+        assert shared == (view == 0)
+        recs = [t(vt.packed()) for vt in vts]
+        want = []
+        for vt, rec in zip(vts, recs):
+            o = rast.rasterize_forward(means3D=means, opacities=op, viewmatrix=rec[0:16], projmatrix=rec[16:32], campos=rec[32:35], bg=bg,
+                                       width=W, height=H, tan_fovx=vt.tan_fovx, tan_fovy=vt.tan_fovy, shs=shs, scales=sc, rotations=ro,
+                                       sh_degree=deg, want_counts=True)
+            want.append({k: o[k].clone() for k in ("color", "depth", "final_T", "counts")})
+        main = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        for streams in ((main, main), (main, side)):
+            for claim in ((True, False) if shared else (False,)):
+                eyes = []
+                for vt, rec in zip(vts, recs):
+                    eyes.append(dict(viewmatrix=rec[0:16], projmatrix=rec[16:32], campos=rec[32:35], tan_fovx=vt.tan_fovx,
+                                     tan_fovy=vt.tan_fovy, out_color=torch.empty(3, H, W, device=dev), out_depth=torch.empty(H, W, device=dev),
+                                     out_final_T=torch.empty(H, W, device=dev), counts_out=torch.zeros(4, dtype=torch.int64, device=dev)))
+                side.wait_stream(main)
+                rast.rasterize_forward_pair(means3D=means, opacities=op, shs=shs, scales=sc, rotations=ro, sh_degree=deg, bg=bg,
+                                            width=W, height=H, eyes=eyes, streams=streams, shared_depth=claim)
+                torch.cuda.synchronize()
+                for e, w in zip(eyes, want):
+                    assert int(e["counts_out"][2]) == 0 and int(e["counts_out"][3]) == 0
+                    assert torch.equal(e["counts_out"][:2], w["counts"][:2])
+                    for k, kk in (("out_color", "color"), ("out_depth", "depth"), ("out_final_T", "final_T")):
+                        assert torch.equal(e[k], w[kk]), (view, claim, k)
+    # no Gaussians at all: zero-filled outputs, like rasterize_points.cu:77
+    L = gsb_lib
+    empty = dict(viewmatrix=recs[0][0:16], projmatrix=recs[0][16:32], campos=recs[0][32:35], tan_fovx=vts[0].tan_fovx,
+                 tan_fovy=vts[0].tan_fovy)
+    eyes = [dict(empty, out_color=torch.ones(3, H, W, device=dev), out_depth=None, out_final_T=None, counts_out=None) for _ in range(2)]
+    rast.rasterize_forward_pair(means3D=means[:0], opacities=op[:0], shs=shs[:0], scales=sc[:0], rotations=ro[:0], sh_degree=deg, bg=bg,
+                                width=W, height=H, eyes=eyes, streams=(main, main))
+    torch.cuda.synchronize()
+    assert all(float(e["out_color"].abs().max()) == 0.0 for e in eyes)
