@@ -52,7 +52,7 @@ def main():
     # raw NCCL on the same bytes
     n = (out["merges"][-1]["union"] or 0)
     t = torch.tensor([n], device=dev); dist.broadcast(t, 0); n = int(t.item())
-    a = torch.ones(n * 512 * 2, device=dev); b = torch.ones(n * 512 * 4, device=dev)
+    a = torch.ones(n * 4096 * 2, device=dev); b = torch.ones(n * 4096 * 4, device=dev)  # 16^3 voxels per brick
     def one(fn, cold):
         if cold: torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize(); time.sleep(0.002)
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True); e0.record(); fn(); e1.record(); torch.cuda.synchronize()

@@ -1,5 +1,5 @@
 """Raw NCCL timings on the box for payloads of the merge's size (torchrun, one process per GPU): what the library gives for
-reduce / all_reduce / reduce_scatter / gather-by-send-recv at 25 + 51 MB fp32, as a yardstick for gsb_tsdf_reduce's phases."""
+reduce / all_reduce / reduce_scatter / gather-by-send-recv at the size of a C1 union (6208 bricks x 96 KB), as a yardstick for gsb_tsdf_reduce's phases."""
 import os, sys, json, torch, torch.distributed as dist
 
 def main():
@@ -7,7 +7,7 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     bricks = 6208  # a C1 union, multiple of 8
-    n = bricks * 512 * 6
+    n = bricks * 4096 * 6  # 16^3 voxels x (tsdf*w, w, rgb*w + pad) floats
     x = torch.ones(n, device="cuda")
     out = {}
     def timed(name, fn, it=10):
