@@ -40,6 +40,7 @@ namespace gsb {
 
 thread_local char g_error[512] = {0};
 std::atomic<uint64_t> g_launches{0};
+std::atomic<bool> g_blend_trace_on{false};
 Profiler g_prof;
 static const char* kStageNames[kStCount] = {"preprocess", "depth_sort", "emit", "tile_sort", "tile_ranges",
                                             "render",     "to_u8", "prepare_depth", "mark_bricks", "integrate",
@@ -1220,7 +1221,7 @@ __global__ void __launch_bounds__(kTilePixels / kPix, kPix == 1 ? 5 : 8)
 // The exponent's rounding differs from the reference's expression by a few ulp of its largest term (as any
 // re-association does); gated on the full-size parity tests against the reference binary (tests/test_gpu_pipeline.py).
 constexpr int kTabSlotBytes = 160;  // X table 8 x (u',v) | Y table 4 x (dy0,dy1,w0,w1) | (r,g,b,z) | (thr,0,0,0)
-constexpr int kTabSlots = 33;       // 32 hits + sentinel
+constexpr int kTabSlots = 36;       // 32 hits + sentinel + the pair the pipelined loop reads ahead
 constexpr int kTabX = 0, kTabY = 64, kTabC = 128, kTabThr = 144;
 
 __device__ __forceinline__ float lds32(uint32_t addr) {
@@ -1234,18 +1235,21 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 // Written in PTX so that the thresholds are exactly three compares per pixel with chained predicates, the accumulation
 // and the transmittance update are predicated FMA-pipe instructions, and T stays in one aligned register pair.
 // NaNs fall through the tests like in the reference (leu / geu are true for unordered operands).
-__device__ __forceinline__ void blend_record_tab(float u, float v, float dy0, float dy1, float w0, float w1, float thr, float r,
-                                                 float g, float b, float z, unsigned long long& TT, float& C00, float& C10,
-                                                 float& C20, float& Dz0, float& C01, float& C11, float& C21, float& Dz1) {
-  asm volatile(
-      "{\n"
-      ".reg .b64 DY, WY, U2, V2, E, AL, OMA, TN, WW, M1, P1;\n"
-      ".reg .f32 e0, e1, x0, x1, a0, a1, tn0, tn1, ww0, ww1, o0, o1, t0, t1;\n"
-      ".reg .pred p1a, p2a, oka, sata, p1b, p2b, okb, satb;\n"
-      "mov.b64 DY, {%9, %10};\n"
-      "mov.b64 WY, {%11, %12};\n"
-      "mov.b64 U2, {%13, %13};\n"
-      "mov.b64 V2, {%14, %14};\n"
+// The record is blended in two stages, for the software-pipelined loop of render_table_kernel: stage A is everything that does
+// not depend on the transmittance (alpha of the lane's two pixels, forced to 0 where the reference `continue`s, so the
+// record becomes inert: T * (1 - 0) = T, colour += c * 0), stage B the short serial part.  A warp left alone on its SM (the
+// silhouette tiles that walk their whole list end the kernel as a handful of serial chains) then pays ~the T chain per
+// record instead of load + exponent + exp + chain (tests/test_blend_formulation.py states the equivalence on the CPU).
+__device__ __forceinline__ unsigned long long blend_stage_alpha(float u, float v, float dy0, float dy1, float w0, float w1, float thr) {
+  unsigned long long al;
+  asm("{\n"
+      ".reg .b64 DY, WY, U2, V2, E;\n"
+      ".reg .f32 e0, e1, x0, x1, a0, a1;\n"
+      ".reg .pred p1a, p2a, p1b, p2b;\n"
+      "mov.b64 DY, {%1, %2};\n"
+      "mov.b64 WY, {%3, %4};\n"
+      "mov.b64 U2, {%5, %5};\n"
+      "mov.b64 V2, {%6, %6};\n"
       "fma.rn.f32x2 E, V2, DY, U2;\n"             // u'(x) + v(x) * dy(y)
       "add.rn.f32x2 E, E, WY;\n"                  //   + w(y): log2-domain exponent incl. log2(opacity)
       "mov.b64 {e0, e1}, E;\n"
@@ -1253,40 +1257,52 @@ __device__ __forceinline__ void blend_record_tab(float u, float v, float dy0, fl
       "ex2.approx.ftz.f32 x1, e1;\n"
       "min.f32 a0, x0, 0f3F7D70A4;\n"             // forward.cu:341  alpha = min(0.99f, ...)
       "min.f32 a1, x1, 0f3F7D70A4;\n"
-      "mov.b64 AL, {a0, a1};\n"
-      "mov.b64 M1, 0xBF800000BF800000;\n"
-      "mov.b64 P1, 0x3F8000003F800000;\n"
-      "fma.rn.f32x2 OMA, AL, M1, P1;\n"           // 1 - alpha (exactly rounded, like the reference's subtraction)
-      "mul.rn.f32x2 TN, %0, OMA;\n"               // test_T = T * (1 - alpha)
-      "mul.rn.f32x2 WW, AL, %0;\n"                // alpha * T
-      "mov.b64 {tn0, tn1}, TN;\n"
-      "mov.b64 {ww0, ww1}, WW;\n"
-      "mov.b64 {o0, o1}, OMA;\n"
-      "mov.b64 {t0, t1}, %0;\n"
-      "setp.leu.f32 p1a, e0, %15;\n"                    // forward.cu:336  if (power > 0.0f) continue;
-      "setp.leu.f32 p1b, e1, %15;\n"
+      "setp.leu.f32 p1a, e0, %7;\n"                    // forward.cu:336  if (power > 0.0f) continue;
+      "setp.leu.f32 p1b, e1, %7;\n"
       "setp.geu.and.f32 p2a, a0, 0f3B808081, p1a;\n"    // forward.cu:344  if (alpha < 1.0f / 255.0f) continue;
       "setp.geu.and.f32 p2b, a1, 0f3B808081, p1b;\n"
-      "setp.geu.and.f32 oka, tn0, 0f38D1B717, p2a;\n"   // forward.cu:347  if (test_T < 0.0001f) { done = true; continue; }
-      "setp.geu.and.f32 okb, tn1, 0f38D1B717, p2b;\n"
-      "setp.lt.and.f32 sata, tn0, 0f38D1B717, p2a;\n"
-      "setp.lt.and.f32 satb, tn1, 0f38D1B717, p2b;\n"
-      "@oka fma.rn.f32 %1, %16, ww0, %1;\n"
-      "@oka fma.rn.f32 %2, %17, ww0, %2;\n"
-      "@oka fma.rn.f32 %3, %18, ww0, %3;\n"
-      "@oka fma.rn.f32 %4, %19, ww0, %4;\n"
-      "@okb fma.rn.f32 %5, %16, ww1, %5;\n"
-      "@okb fma.rn.f32 %6, %17, ww1, %6;\n"
-      "@okb fma.rn.f32 %7, %18, ww1, %7;\n"
-      "@okb fma.rn.f32 %8, %19, ww1, %8;\n"
-      "@oka mul.rn.f32 t0, t0, o0;\n"             // T = test_T (same operands, same rounding)
-      "@okb mul.rn.f32 t1, t1, o1;\n"
-      "@sata or.b32 t0, t0, 0x80000000;\n"        // done: keep |T|, set the sign
-      "@satb or.b32 t1, t1, 0x80000000;\n"
+      "selp.f32 a0, a0, 0f00000000, p2a;\n"
+      "selp.f32 a1, a1, 0f00000000, p2b;\n"
+      "mov.b64 %0, {a0, a1};\n"
+      "}\n"
+      : "=l"(al)
+      : "f"(dy0), "f"(dy1), "f"(w0), "f"(w1), "f"(u), "f"(v), "f"(thr));
+  return al;
+}
+
+__device__ __forceinline__ void blend_stage_apply(unsigned long long al, float r, float g, float b, float z, unsigned long long& TT,
+                                                  float& C00, float& C10, float& C20, float& Dz0, float& C01, float& C11, float& C21,
+                                                  float& Dz1) {
+  asm("{\n"
+      ".reg .b64 OMA, TN, WW, M1, P1;\n"
+      ".reg .f32 tn0, tn1, ww0, ww1, t0, t1;\n"
+      ".reg .pred oka, okb;\n"
+      "mov.b64 M1, 0xBF800000BF800000;\n"
+      "mov.b64 P1, 0x3F8000003F800000;\n"
+      "fma.rn.f32x2 OMA, %9, M1, P1;\n"           // 1 - alpha (exactly rounded, like the reference's subtraction)
+      "mul.rn.f32x2 TN, %0, OMA;\n"               // test_T = T * (1 - alpha)
+      "mul.rn.f32x2 WW, %9, %0;\n"                // alpha * T
+      "mov.b64 {tn0, tn1}, TN;\n"
+      "mov.b64 {ww0, ww1}, WW;\n"
+      "mov.b64 {t0, t1}, %0;\n"
+      "setp.geu.f32 oka, tn0, 0f38D1B717;\n"      // forward.cu:347  if (test_T < 0.0001f) { done = true; continue; }
+      "setp.geu.f32 okb, tn1, 0f38D1B717;\n"      //   (T >= 1e-4 while the pixel lives, negative once done: an inert record passes)
+      "@oka fma.rn.f32 %1, %10, ww0, %1;\n"
+      "@oka fma.rn.f32 %2, %11, ww0, %2;\n"
+      "@oka fma.rn.f32 %3, %12, ww0, %3;\n"
+      "@oka fma.rn.f32 %4, %13, ww0, %4;\n"
+      "@okb fma.rn.f32 %5, %10, ww1, %5;\n"
+      "@okb fma.rn.f32 %6, %11, ww1, %6;\n"
+      "@okb fma.rn.f32 %7, %12, ww1, %7;\n"
+      "@okb fma.rn.f32 %8, %13, ww1, %8;\n"
+      "@oka mov.f32 t0, tn0;\n"                   // T = test_T
+      "@okb mov.f32 t1, tn1;\n"
+      "@!oka or.b32 t0, t0, 0x80000000;\n"        // done: keep |T|, set the sign
+      "@!okb or.b32 t1, t1, 0x80000000;\n"
       "mov.b64 %0, {t0, t1};\n"
       "}\n"
       : "+l"(TT), "+f"(C00), "+f"(C10), "+f"(C20), "+f"(Dz0), "+f"(C01), "+f"(C11), "+f"(C21), "+f"(Dz1)
-      : "f"(dy0), "f"(dy1), "f"(w0), "f"(w1), "f"(u), "f"(v), "f"(thr), "f"(r), "f"(g), "f"(b), "f"(z));
+      : "l"(al), "f"(r), "f"(g), "f"(b), "f"(z));
 }
 
 __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
@@ -1298,6 +1314,17 @@ __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
 // hardware order mixes long and short lists on every SM, so the gather latency of the short ones hides behind the
 // arithmetic of the long ones; sorted, the kernel ends in a long phase of latency-bound tiles, and a persistent grid
 // also keeps the kernels of the other in-flight views off the SMs.
+// profiling aid (scripts/blend_trace.py): the <true> instantiation writes, per warp, start / end %globaltimer, list length /
+// records walked, clock cycles spent in (test + slot build, blend loop, waiting for the next chunk's gather) and the
+// number of records blended to trace[(tile * 4 + block) * 8 + 0..6].  The product launch is <false>: no trace code in it.
+__device__ unsigned long long* g_blend_trace = nullptr;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <bool kTrace>
 __global__ void __launch_bounds__(kTilePixels / 2, 7)
     render_table_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
                         const float4* __restrict__ recA, const float4* __restrict__ recB, const float2* __restrict__ recC,
@@ -1321,6 +1348,12 @@ __global__ void __launch_bounds__(kTilePixels / 2, 7)
     uint2 range = ranges[tile];
     if (range.y <= range.x || (int64_t)range.y > capacity) range = make_uint2(0u, 0u);
     const int total = range.y - range.x;
+    unsigned long long* trace = nullptr;
+    uint32_t cyc_build = 0, cyc_blend = 0, cyc_wait = 0, hits = 0;
+    if (kTrace) {
+      trace = g_blend_trace + ((size_t)tile * 4 + warp) * 8;
+      if (lane == 0) trace[0] = global_timer_ns();
+    }
     const bool inside0 = pix_x < (uint32_t)W && pix_y < (uint32_t)H, inside1 = pix_x < (uint32_t)W && pix_y + 4 < (uint32_t)H;
     // the sign of T is the pixel's "done" flag
     unsigned long long TT = pack_f32x2(inside0 ? 1.0f : -1.0f, inside1 ? 1.0f : -1.0f);
@@ -1328,27 +1361,37 @@ __global__ void __launch_bounds__(kTilePixels / 2, 7)
 
     float4 cA = make_float4(0.f, 0.f, 0.f, 0.f), cB = cA, nA = cA, nB = cA;
     float2 cC = make_float2(0.f, 0.f), nC = cC;
+    // record indices run two chunks ahead of the blend, records one: the record gather of the next chunk never waits for
+    // its index (in-order issue would stall the whole chunk on that dependent load)
+    uint32_t g_next = 0;
     if (lane < total) {
       const uint32_t g = point_list[range.x + lane];
+      if (32 + lane < total) g_next = point_list[range.x + 32 + lane];
       cA = recA[g];
       cB = recB[g];
       cC = recC[g];
     }
-    auto blend = [&](uint32_t off) {
+    auto alpha_of = [&](uint32_t off) {  // stage A of the record in slot `off`
       const float2 X = lds64(xbase + off);       // u', v of this lane's column
       const float4 Y = lds128(ybase + off);      // dy, w of this lane's two rows
-      const float4 Q = lds128(a0 + kTabC + off);  // r, g, b, z
       const float thr = lds32(a0 + kTabThr + off);
-      blend_record_tab(X.x, X.y, Y.x, Y.y, Y.z, Y.w, thr, Q.x, Q.y, Q.z, Q.w, TT, C00, C10, C20, Dz0, C01, C11, C21, Dz1);
+      return blend_stage_alpha(X.x, X.y, Y.x, Y.y, Y.z, Y.w, thr);
     };
-    for (int c0 = 0; c0 < total; c0 += 32) {
+    auto apply = [&](uint32_t off, unsigned long long al) {  // stage B
+      const float4 Q = lds128(a0 + kTabC + off);  // r, g, b, z
+      blend_stage_apply(al, Q.x, Q.y, Q.z, Q.w, TT, C00, C10, C20, Dz0, C01, C11, C21, Dz1);
+    };
+    int c0 = 0;
+    for (; c0 < total; c0 += 32) {
       if (__all_sync(0xffffffffu, (TT & 0x8000000080000000ull) == 0x8000000080000000ull)) break;  // both pixels done
+      uint32_t tk0 = 0, tk1 = 0, tk2 = 0;
+      if (kTrace) tk0 = (uint32_t)clock64();
       const int nxt = c0 + 32 + lane;
       if (nxt < total) {  // next chunk's gathers fly while this one is tested and blended
-        const uint32_t g = point_list[range.x + nxt];
-        nA = recA[g];
-        nB = recB[g];
-        nC = recC[g];
+        nA = recA[g_next];
+        nB = recB[g_next];
+        nC = recC[g_next];
+        if (nxt + 32 < total) g_next = point_list[range.x + nxt + 32];
       }
       bool hit = false;
       if (c0 + lane < total) {
@@ -1374,6 +1417,11 @@ __global__ void __launch_bounds__(kTilePixels / 2, 7)
         sts128(dst + kTabC, make_float4(cB.w, cC.x, cC.y, cA.z));
         sts128(dst + kTabThr, make_float4(l2o, 0.f, 0.f, 0.f));
       }
+      if (kTrace) {
+        __syncwarp();
+        tk1 = (uint32_t)clock64();
+        hits += n;
+      }
       if (n != 0) {  // (a chunk none of whose records reaches the block costs no more than the test)
         if ((n & 1) && lane < kTabSlotBytes / 16) {  // odd count: sentinel after the last hit, u' = -1e30 -> alpha 0 -> skipped
           const float big = lane < 4 ? -1.0e30f : 0.f;  // quads 0..3 = the X table: (u', v, u', v)
@@ -1381,15 +1429,37 @@ __global__ void __launch_bounds__(kTilePixels / 2, 7)
         }
         __syncwarp();  // the list is visible to every lane of the warp
         const uint32_t end = (uint32_t)n * kTabSlotBytes;
+        unsigned long long al0 = alpha_of(0), al1 = alpha_of(kTabSlotBytes);
         for (uint32_t off = 0; off < end; off += 2 * kTabSlotBytes) {
-          blend(off);
-          blend(off + kTabSlotBytes);
+          // the next pair's alphas are in flight while this pair's T chain resolves (past the end: two slots of stale
+          // bytes, computed and dropped)
+          const unsigned long long nx0 = alpha_of(off + 2 * kTabSlotBytes), nx1 = alpha_of(off + 3 * kTabSlotBytes);
+          apply(off, al0);
+          apply(off + kTabSlotBytes, al1);
+          al0 = nx0;
+          al1 = nx1;
         }
         __syncwarp();  // every lane is done reading before the next chunk overwrites the slots
       }
+      if (kTrace) tk2 = (uint32_t)clock64();
       cA = nA;
       cB = nB;
       cC = nC;
+      if (kTrace) {  // the moves above wait for the gather: touch the values so the wait is inside the bracket
+        const float touch = cA.x + cB.x + cC.x;
+        const uint32_t tk3 = (uint32_t)clock64() + (touch == 1.2345e-30f ? 1u : 0u);
+        cyc_build += tk1 - tk0;
+        cyc_blend += tk2 - tk1;
+        cyc_wait += tk3 - tk2;
+      }
+    }
+    if (kTrace && lane == 0) {
+      trace[1] = global_timer_ns();
+      trace[2] = ((unsigned long long)(uint32_t)total << 32) | (uint32_t)min(c0, total);
+      trace[3] = cyc_build;
+      trace[4] = cyc_blend;
+      trace[5] = cyc_wait;
+      trace[6] = hits;
     }
     const size_t plane = (size_t)H * W;
     const float Tf0 = fabsf(__uint_as_float((uint32_t)TT)), Tf1 = fabsf(__uint_as_float((uint32_t)(TT >> 32)));
@@ -1534,6 +1604,15 @@ extern "C" {
 const char* gsb_last_error(void) { return g_error; }
 int gsb_version(void) { return GSB_VERSION; }
 uint64_t gsb_kernel_launch_count(void) { return g_launches.load(); }
+
+// profiling aid, not part of the reference-facing surface: per-warp timeline of the table blend
+// (device buffer of tiles * 4 * 8 uint64; NULL = off)
+int gsb_debug_blend_trace(void* device_buffer) {
+  unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+  GSB_CUDA_OK(cudaMemcpyToSymbol(g_blend_trace, &p, sizeof(p)));
+  g_blend_trace_on.store(p != nullptr);
+  return GSB_OK;
+}
 int64_t gsb_raster_required_instances(void) { return g_required_instances; }
 
 int gsb_profile_num_stages(void) { return kStCount; }
@@ -1770,7 +1849,11 @@ static int render_frame_impl(const Frame& f, const uint32_t* point_list, cudaStr
   __VA_ARGS__<<<dim3(gx, gy), THREADS, 0, stream>>>(ws.ranges, point_list, W, H, ws.recA, ws.recB, ws.recC, a->background, \
                                                     a->out_color, a->out_depth, a->out_final_T, cap)
     if (impl == 4 && fast) {
-      GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_table_kernel);
+      if (g_blend_trace_on.load()) {
+        GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_table_kernel<true>);
+      } else {
+        GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_table_kernel<false>);
+      }
     } else if (fast) {  // the table kernel only exists for the ex2 blend: full-precision expf -> dual
       GSB_LAUNCH_RENDER_T(kTilePixels / 2, render_compact_kernel<true, 2>);
     } else {

@@ -99,7 +99,7 @@ def test_nothing_contributes_after_saturation():
 # Table kernel (render_table_kernel, the default): the same loop with (a) "done" kept in the SIGN of T and (b) the
 # exponent evaluated in the log2 domain from per-column / per-row terms, alpha = 2^e with log2(opacity) folded in.
 def table_pixel(recs, px, py, bx0=0.0, by0=0.0):
-    """float32 restatement of blend_record_tab for one pixel: e = fma(v, dy, u') + w; skip if e > thr;
+    """float32 restatement of the table blend (blend_stage_alpha + blend_stage_apply) for one pixel: e = fma(v, dy, u') + w; skip if e > thr;
     alpha = min(0.99, 2^e); three chained predicates; T keeps |T| with the sign bit set once saturated."""
     LOG2E = F(1.4426950408889634)
     T, C, D, n = F(1), np.zeros(3, F), F(0), 0
@@ -163,6 +163,45 @@ def test_sign_of_T_is_an_exact_done_flag():
         sT, sC, sD, sn = sign_pixel(recs + [SENTINEL], px, py)
         assert sT == rT and sn == rn
         np.testing.assert_allclose(sC, rC, rtol=0, atol=2e-6)
+        sat += rT < F(0.001)
+    assert sat > 50
+
+
+def test_two_stage_blend_with_inert_records_equals_the_sign_scheme():
+    """The pipelined loop of render_table_kernel splits a record into a T-independent stage (alpha, forced to 0 where the
+    reference `continue`s) and the serial stage (T*(1-alpha) >= 1e-4 ? accumulate, T = test_T : set the sign) that no longer
+    looks at the `continue` predicates: a record with alpha 0 is inert (T*1 = T >= 1e-4 while the pixel lives, negative once
+    it is done; colour += c*0), so transmittance, contributor count and colour are those of the reference loop."""
+    rng = np.random.default_rng(35)
+
+    def two_stage_pixel(recs, px, py):
+        T, C, D, n = F(1), np.zeros(3, F), F(0), 0
+        for (gx, gy, z, op, a, b, c, col) in recs:
+            dx, dy = F(gx - px), F(gy - py)
+            power = F(F(-0.5) * F(F(a * dx * dx) + F(c * dy * dy)) - F(b * dx * dy))
+            alpha = min(F(0.99), F(op * np.exp(power)))  # stage A
+            if (power > 0) or (alpha < F(1.0 / 255.0)):
+                alpha = F(0)
+            tt = F(T * F(1 - alpha))  # stage B
+            if tt >= F(0.0001):
+                w = F(alpha * T)
+                C = (col * w + C).astype(F)
+                D = F(z * w + D)
+                T = tt
+                n += int(alpha > 0)
+            else:
+                T = -abs(T)
+        return abs(T), C, D, n
+
+    sat = 0
+    for trial in range(300):
+        recs = _records(rng, int(rng.integers(0, 60)), dense=trial % 2 == 1)
+        px, py = F(rng.integers(0, 16)), F(rng.integers(0, 16))
+        rT, rC, rD, rn = reference_pixel(recs, px, py)
+        sT, sC, sD, sn = two_stage_pixel(recs + [SENTINEL, SENTINEL, SENTINEL], px, py)
+        assert sT == rT and sn == rn
+        np.testing.assert_allclose(sC, rC, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(sD, rD, rtol=0, atol=1e-5)
         sat += rT < F(0.001)
     assert sat > 50
 
