@@ -31,6 +31,8 @@ from . import camera as cam
 from . import rasterizer as rast
 
 
+# two stream sets: the device-resident rate is the same from 2 up (the GPU is busy); three gained 3-4 % on the host-buffer path
+# on one box and nothing on another, and two of five runs with three showed a slow device-resident loop (profiles/r03a_*, r03c_*)
 DEFAULT_PAIRS_IN_FLIGHT = 2
 
 

@@ -6,7 +6,7 @@ from tests.test_gpu_pipeline import Args, small_scene  # noqa: F401  (fixture + 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("in_flight", [1, 2, 3])
+@pytest.mark.parametrize("in_flight", [1, 2, 3, 4])
 def test_pipelined_pairs_equal_synchronous_renders(gsb_lib, cuda_device, small_scene, in_flight):
     """`render_image_pair(..., wait=False)` with `pairs_in_flight` stream sets, consumed the way bench.py's e2e loop
     does (pair n after the next `pairs_in_flight` pairs were enqueued), returns exactly what synchronous calls return:
