@@ -181,6 +181,9 @@ def workload_name(name, cfg, total_views):
 
 
 # ------------------------------------------------------------------------------------------------ ours
+DEFAULT_E2E_ORDER = "lagged"
+
+
 def run_ours(args, cfg, rank, local, world):
     from gs2mesh_b200 import _lib
     from gs2mesh_b200.renderer import Renderer
@@ -324,18 +327,33 @@ def run_ours(args, cfg, rank, local, world):
         # what a host-side stereo stage would hand back: float depth + the uint8 left frame, both on the host
         stage.integrate(host_depth[k], rgb_host, rigs[i]["left"])
 
+    # BENCH_E2E_ORDER (A/B switch): "lagged" = pair n-1 is fused at the top of iteration n, right after its depth read-back
+    # was enqueued (the host then idles for that copy before it enqueues the next render); "overlap" = the depth read-back of
+    # pair n is enqueued, THEN the render of pair n + lag (the host is busy enqueueing while the depth travels), then pair n
+    # is fused.  Both respect the renderer's buffer rotation: the tensors of call n are valid until call
+    # n + pairs_in_flight + 1 is entered, and pair n is fused after call n + lag = n + pairs_in_flight was.
+    order = os.environ.get("BENCH_E2E_ORDER", DEFAULT_E2E_ORDER)
     for n, i in enumerate(views):
-        if fuse_next is not None:  # pair n-1, before the next render call is entered (the renderer's buffer-rotation contract)
-            fuse(fuse_next)
-        out = pending.pop(0)
-        if n + lag < len(views):
-            pending.append(renderer.render_image_pair(views[n + lag], to_host=True, wait=False))
-        out["ready"].synchronize()  # both uint8 frames of pair i are in pinned host memory
+        if order == "lagged":
+            if fuse_next is not None:  # pair n-1
+                fuse(fuse_next)
+            out = pending.pop(0)
+            if n + lag < len(views):
+                pending.append(renderer.render_image_pair(views[n + lag], to_host=True, wait=False))
+            out["ready"].synchronize()  # both uint8 frames of pair i are in pinned host memory
+        else:
+            out = pending.pop(0)
+            out["ready"].synchronize()  # both uint8 frames of pair i are in pinned host memory
         k = n & 1
         vol.prepare_depth(out["depth"], W, H, final_T=out["final_T"], out=dev_depth[k])  # expected depth of the left view
         host_depth[k].copy_(dev_depth[k], non_blocking=True)
         depth_ready[k] = torch.cuda.current_stream().record_event()
         fuse_next = (i, out["host_left_u8"], k)
+        if order != "lagged":
+            if n + lag < len(views):
+                pending.append(renderer.render_image_pair(views[n + lag], to_host=True, wait=False))
+            fuse(fuse_next)
+            fuse_next = None
     if fuse_next is not None:
         fuse(fuse_next)
     renderer.check_status(views)
@@ -417,6 +435,9 @@ def run_ours(args, cfg, rank, local, world):
                     "pair_mode": os.environ.get("GSB_PAIR_MODE", "fused"),
                     "pairs_sharing_one_depth_sort": round(float(np.mean([renderer._shared_depth[i] for i in mine])), 3) if mine else None,
                     "pairs_in_flight": int(renderer.pairs_in_flight),
+                    "frame_copies_on_own_streams": bool(renderer.copy_streams),
+                    "spare_buffer_sets": int(renderer.spare_buffer_sets),
+                    "e2e_loop_order": os.environ.get("BENCH_E2E_ORDER", DEFAULT_E2E_ORDER),
                     "host_enqueue_ms_per_step": round(host_enqueue_ms, 4),
                     "caller_stream_priority": int(torch.cuda.current_stream().priority),
                     "per_view": {k: round(v, 1) for k, v in mean.items()},

@@ -34,6 +34,17 @@ from . import rasterizer as rast
 # two stream sets: the device-resident rate is the same from 2 up (the GPU is busy); three gained 3-4 % on the host-buffer path
 # on one box and nothing on another, and two of five runs with three showed a slow device-resident loop (profiles/r03a_*, r03c_*)
 DEFAULT_PAIRS_IN_FLIGHT = 2
+# D2H copies of the uint8 frames on their own streams (one per eye and stream set) instead of the eye's render stream: the
+# render stream is free for the next pair of its set as soon as the frame is converted, not once it has crossed PCIe.
+# GSB_COPY_STREAMS=0|1 overrides (A/B switch)
+DEFAULT_COPY_STREAMS = 0
+# Buffer sets beyond pairs_in_flight + 2.  The tensors of call n stay valid until call n + pairs_in_flight + 1 is entered,
+# so the renders of call c may overwrite their buffer set once everything the caller enqueued before call
+# c - (spare sets) - 1 was entered has run.  With no spare set that is the PREVIOUS call's entry -- which, in a loop that
+# fuses every pair right after rendering it, sits behind the TSDF kernels of the pair that has just left this call's stream
+# set: the set idles for their duration.  One spare set moves the gate one call back (the other stream set's pair).
+# GSB_SPARE_BUFFER_SETS=0|1|2 overrides (A/B switch)
+DEFAULT_SPARE_BUFFER_SETS = 0
 
 
 class _PairReady:
@@ -88,6 +99,8 @@ class Renderer:
         self.overlap_eyes = True
         # how many stereo pairs may be in flight at once (stream sets); GSB_PAIRS_IN_FLIGHT overrides (A/B switch)
         self.pairs_in_flight = int(os.environ.get("GSB_PAIRS_IN_FLIGHT", DEFAULT_PAIRS_IN_FLIGHT))
+        self.copy_streams = bool(int(os.environ.get("GSB_COPY_STREAMS", DEFAULT_COPY_STREAMS)))
+        self.spare_buffer_sets = max(0, int(os.environ.get("GSB_SPARE_BUFFER_SETS", DEFAULT_SPARE_BUFFER_SETS)))
         self.keep_frames = False
         self._frames = {}
         self._ready = False
@@ -283,10 +296,12 @@ class Renderer:
             to_host = self.write_images if to_host is None else to_host
             if self.write_images:
                 to_host = True  # PNGs are written from the pinned host copies
+            cstreams = None  # streams of the D2H copies, when they do not ride on the render streams
             if self.overlap_eyes:
                 self._call_index = getattr(self, "_call_index", -1) + 1
                 depth = max(1, int(self.pairs_in_flight))
-                nslots = depth + 2
+                spare = int(self.spare_buffer_sets)
+                nslots = depth + 2 + spare
                 slot = self._call_index % nslots
                 if not hasattr(self, "_side_streams") or len(self._side_streams) != depth:
                     # `pairs_in_flight` sets of (left, right) streams, used round-robin: consecutive pairs run on
@@ -302,11 +317,15 @@ class Renderer:
                 b = self._buffers(vt.width, vt.height, slot)
                 entry = torch.cuda.Event()
                 entry.record(main)
-                # everything that read this buffer set (handed out nslots calls ago) was enqueued on the caller's
-                # stream before the PREVIOUS call was entered
-                gate = self._entry_events[(self._call_index - 1) % nslots]
+                # everything that read this buffer set (handed out nslots calls ago, valid until call
+                # c - nslots + depth + 1 = c - 1 - spare was entered) was enqueued on the caller's stream before that entry
+                gate = self._entry_events[(self._call_index - 1 - spare) % nslots] if self._call_index > spare else None
                 self._entry_events[slot] = entry
                 streams = self._side_streams[self._call_index % depth]
+                if self.copy_streams and to_host:
+                    if not hasattr(self, "_copy_streams") or len(self._copy_streams) != depth:
+                        self._copy_streams = [[torch.cuda.Stream(dev), torch.cuda.Stream(dev)] for _ in range(depth)]
+                    cstreams = self._copy_streams[self._call_index % depth]
                 for st in streams:
                     if gate is not None:
                         st.wait_event(gate)
@@ -318,11 +337,17 @@ class Renderer:
                 b = self._buffers(vt.width, vt.height)
                 streams = [main, main]
 
+            # the streams whose completion means "this pair is done": the copy streams when the frames travel on their own
+            # streams (each copy is ordered behind everything its eye's render stream holds at that point), else the render streams
+            tails = streams if cstreams is None else cstreams
+
             def enqueue():
                 self._enqueue_pair(camera_number, b, streams)
                 if to_host:
                     for s in range(2):
-                        with torch.cuda.stream(streams[s]):
+                        if cstreams is not None:
+                            cstreams[s].wait_stream(streams[s])
+                        with torch.cuda.stream(tails[s]):
                             b["host_u8"][s].copy_(b["u8"][s], non_blocking=True)
 
             def redo_if_invalid():
@@ -332,7 +357,7 @@ class Renderer:
                     if self._frame_ok(camera_number):
                         return
                     enqueue()
-                    for st in streams:
+                    for st in tails:
                         st.synchronize()
                 self.check_status([camera_number])
 
@@ -340,15 +365,15 @@ class Renderer:
             result = dict(left=b["color"][0], right=b["color"][1], left_u8=b["u8"][0], right_u8=b["u8"][1],
                           depth=b["depth"], final_T=b["final_T"])
             if self.overlap_eyes:
-                self._slot_done[slot] = [st.record_event() for st in streams]
+                self._slot_done[slot] = [st.record_event() for st in tails]
             asynchronous = to_host and not wait and not self.write_images and not self.keep_frames and self.overlap_eyes
             if self.overlap_eyes and not asynchronous:
-                for st in streams:
+                for st in tails:
                     main.wait_stream(st)  # device-side dependency only: later work on the caller's stream sees both eyes
             if to_host:
                 result["host_left_u8"], result["host_right_u8"] = b["host_u8"]
                 if asynchronous:
-                    result["ready"] = _PairReady([st.record_event() for st in streams], redo_if_invalid)
+                    result["ready"] = _PairReady([st.record_event() for st in tails], redo_if_invalid)
                 else:
                     main.synchronize()
                     redo_if_invalid()
