@@ -153,6 +153,7 @@ def _tsdf_lib():
         L.orc_tsdf_create.restype = C.c_void_p
         L.orc_tsdf_create.argtypes = [C.c_double, C.c_double, C.c_int]
         L.orc_tsdf_destroy.argtypes = [C.c_void_p]
+        L.orc_tsdf_set_variant.argtypes = [C.c_int]
         L.orc_tsdf_num_units.restype = C.c_int64
         L.orc_tsdf_num_units.argtypes = [C.c_void_p]
         L.orc_depth_convert.argtypes = [_f32p, C.c_int64, C.c_double, C.c_double, _f32p]
@@ -166,6 +167,12 @@ def _tsdf_lib():
         L.orc_tsdf_export_bricks.argtypes = [C.c_void_p, _i32p, _i32p, _f32p, _u8p]
         L._tsdf_ready = True
     return L
+
+
+def tsdf_set_variant(bits: int) -> None:
+    """Sensitivity study of the restatement's two DOUBT points (oracle/tsdf_oracle.cpp): bit 0 pairwise 4x4*4x1 sum,
+    bit 1 `sdf / trunc`, bit 2 FMA-contracted product.  0 restores the restatement.  Process-wide: reset after use."""
+    _tsdf_lib().orc_tsdf_set_variant(int(bits))
 
 
 def depth_convert(depth, depth_scale, depth_trunc):

@@ -70,6 +70,15 @@ struct Volume {
 
 inline int floor_div(double p, double len) { return (int)std::floor(p / len); }
 
+// Sensitivity switches for the two DOUBT points (tests/test_oracle_tsdf.py::test_doubt_sensitivity): how far the results
+// move if Open3D's binary resolves them the other way.  0 = the restatement (what the CUDA path is bit-exact with).
+//   bit 0: 4x4 * 4x1 summed pairwise, (a0 + a1) + (a2 + a3) -- Eigen's NON-vectorised fixed-size reduction; the restatement
+//          follows the vectorised evaluator (res = c0*x; res += c1*y; res += c2*z; res += c3*w), which is what a default
+//          x86-64 build of Eigen 3.4 instantiates for aligned Matrix4f * Vector4f
+//   bit 1: sdf / trunc instead of sdf * (1 / trunc)
+//   bit 2: the product contracted to fused multiply-adds (a wheel built with -mfma)
+int g_variant = 0;
+
 // UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier for one 16^3 unit.
 void integrate_unit(Unit& u, const Volume& vol, const float* depth, const uint8_t* rgb, const float* mult, int W,
                     int H, float fx, float fy, float cx, float cy, const float E[16]) {
@@ -89,6 +98,15 @@ void integrate_unit(Unit& u, const Volume& vol, const float* depth, const uint8_
       float cxm = ((E[0] * px + E[1] * py) + E[2] * pz) + E[3] * 1.f;
       float cym = ((E[4] * px + E[5] * py) + E[6] * pz) + E[7] * 1.f;
       float czm = ((E[8] * px + E[9] * py) + E[10] * pz) + E[11] * 1.f;
+      if (g_variant & 1) {
+        cxm = (E[0] * px + E[1] * py) + (E[2] * pz + E[3] * 1.f);
+        cym = (E[4] * px + E[5] * py) + (E[6] * pz + E[7] * 1.f);
+        czm = (E[8] * px + E[9] * py) + (E[10] * pz + E[11] * 1.f);
+      } else if (g_variant & 4) {
+        cxm = std::fmaf(E[3], 1.f, std::fmaf(E[2], pz, std::fmaf(E[1], py, E[0] * px)));
+        cym = std::fmaf(E[7], 1.f, std::fmaf(E[6], pz, std::fmaf(E[5], py, E[4] * px)));
+        czm = std::fmaf(E[11], 1.f, std::fmaf(E[10], pz, std::fmaf(E[9], py, E[8] * px)));
+      }
       for (int z = 0; z < kRes; ++z, cxm += sx, cym += sy, czm += sz) {
         if (czm <= 0) continue;
         const float u_f = cxm * fx / czm + cx + 0.5f;
@@ -100,7 +118,7 @@ void integrate_unit(Unit& u, const Volume& vol, const float* depth, const uint8_
         const int ind = (x * kRes + y) * kRes + z;
         const float sdf = (d - czm) * mult[(size_t)vi * W + ui];
         if (sdf > -trunc) {
-          const float t = std::min(1.0f, sdf * trunc_inv);  // DOUBT: multiply by reciprocal
+          const float t = std::min(1.0f, (g_variant & 2) ? sdf / trunc : sdf * trunc_inv);  // DOUBT: multiply by reciprocal
           const float w = u.weight[ind];
           u.tsdf[ind] = (u.tsdf[ind] * w + t) / (w + 1.0f);
           if (vol.with_color && rgb) {
@@ -129,6 +147,8 @@ void* orc_tsdf_create(double voxel_length, double sdf_trunc, int with_color) {
 }
 
 void orc_tsdf_destroy(void* h) { delete static_cast<Volume*>(h); }
+
+void orc_tsdf_set_variant(int bits) { g_variant = bits; }  // sensitivity study only; 0 = the restatement
 
 int64_t orc_tsdf_num_units(void* h) { return (int64_t)static_cast<Volume*>(h)->order.size(); }
 
